@@ -1,0 +1,203 @@
+/*
+ * openems_b200.h -- C ABI of the B200-native openEMS FDTD engine (libopenems_b200.so).
+ *
+ * This is the drop-in boundary for the hot path named in BASELINE.json: everything the
+ * reference's Operator / Engine / Engine_Extension / Engine_Interface_Base classes need from
+ * a device engine, as plain C.  The reference has no C ABI or plugin loader for engines
+ * (engines are C++ classes created by Operator::CreateEngine, FDTD/operator.h:56), so each
+ * entry point below names the reference interface it replaces; INTEGRATION.md shows the
+ * Engine_CUDA / Operator_CUDA C++ classes that bind these calls inside openEMS.
+ *
+ * Conventions
+ *  - every call returns 0 on success, non-zero on error; oems_cuda_last_error() gives the text.
+ *    The reference reports errors by cerr + return code / exit (openems.cpp:1133-1344); no
+ *    exception crosses this boundary.
+ *  - all pointers are HOST pointers, copied during the call; the caller keeps ownership.
+ *  - dense arrays use the reference's ArrayNIJK order [n][i][j][k], k (z) fastest
+ *    (tools/arraylib/array_nijk.h) unless stated otherwise.
+ *  - one handle per host thread (the reference calls IterateTS and all Processing from one
+ *    thread, openems.cpp:1427-1476); calls on one handle must not overlap.
+ *  - there is no CPU fallback: create() fails if no CUDA device is usable.
+ */
+#ifndef OPENEMS_B200_H
+#define OPENEMS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oems_cuda_engine oems_cuda_engine;
+
+#define OEMS_ABI_VERSION 1
+
+/* one de-duplicated coefficient tuple of the device operator.  Replaces the
+   SSE_coeff key of Operator_SSE_Compressed (FDTD/operator_sse_compressed.h:77-85), re-keyed
+   per cell and extended by the UPML auxiliary coefficients so that one index serves the
+   stencil and the PML (FDTD/extensions/operator_ext_upml.h:108-113). 32 floats = 128 B. */
+typedef struct oems_coeff_entry {
+	float vv[3], vi[3], ii[3], iv[3];
+	float pml;                 /* != 0: cell lies inside a UPML box, aux coefficients valid */
+	float pml_vv[3], pml_vvfn[3], pml_vvfo[3];
+	float pml_ii[3], pml_iifn[3], pml_iifo[3];
+	float reserved;
+} oems_coeff_entry;
+
+int         oems_cuda_abi_version(void);
+/* text of the last error on this handle (or of the last failed create() when h == NULL) */
+const char* oems_cuda_last_error(const oems_cuda_engine* h);
+
+/* ---- life cycle: Engine::New / ~Engine (FDTD/engine.cpp:27-49); numLines as
+   Operator::GetNumberOfLines(n,true).  device < 0 selects the current CUDA device. */
+int oems_cuda_create(unsigned nx, unsigned ny, unsigned nz, int device, oems_cuda_engine** out);
+int oems_cuda_destroy(oems_cuda_engine* h);
+
+/* ---- z-slab sharding (multi-GPU; template: FDTD/engine_mpi.cpp:84-210, openems_fdtd_mpi.cpp:201-299).
+   Must be called before any upload.  The handle then holds global planes
+   [z_begin - (z_begin>0), z_end + (z_end<nz)) : owned planes plus one ghost plane per
+   interface; all positions passed to other calls stay GLOBAL.  Single GPU: never call it. */
+int oems_cuda_set_slab(oems_cuda_engine* h, unsigned z_begin, unsigned z_end);
+
+/* ---- operator upload (once) */
+/* dense coefficients as held by Operator (GetVV/GetVI/GetII/GetIV, FDTD/operator.h:215-218):
+   the library re-keys them per cell (replaces Operator_SSE_Compressed::CompressOperator,
+   FDTD/operator_sse_compressed.cpp:114-175). */
+int oems_cuda_set_operator_dense(oems_cuda_engine* h, const float* vv, const float* vi,
+                                 const float* ii, const float* iv);
+/* already compressed operator: table[n_unique] + per-cell index [nz][ny][nx] (x fastest),
+   index_bytes 2 or 4.  Used when the dense arrays do not fit the host (1024^3 and up). */
+int oems_cuda_set_operator_compressed(oems_cuda_engine* h, unsigned n_unique,
+                                      const oems_coeff_entry* table, const void* index,
+                                      int index_bytes);
+/* Excitation::GetVoltageSignal/GetCurrentSignal/GetLength/GetSignalPeriod (FDTD/excitation.h);
+   period_ts = int(GetSignalPeriod()/GetTimestep()) or 0 (engine_ext_excitation.cpp:43-45) */
+int oems_cuda_set_signal(oems_cuda_engine* h, const float* sig_volt, const float* sig_curr,
+                         unsigned length, unsigned period_ts);
+/* Operator_Ext_Excitation lists Volt_index/Volt_dir/Volt_amp/Volt_delay and Curr_*
+   (FDTD/extensions/operator_ext_excitation.h:81-94); idx3 is [3][count]. */
+int oems_cuda_add_excitation(oems_cuda_engine* h, int is_curr, unsigned count,
+                             const unsigned* idx3, const unsigned* dir, const float* amp,
+                             const unsigned* delay);
+/* one Operator_Ext_UPML box: m_StartPos, m_numLines and the six coefficient arrays
+   vv, vvfn, vvfo, ii, iifn, iifo, each ArrayNIJK local to the box
+   (FDTD/extensions/operator_ext_upml.h:96-113).  With a compressed operator pass NULL
+   coefficient pointers: the aux coefficients then come from the table entries. */
+int oems_cuda_add_upml(oems_cuda_engine* h, const unsigned start[3], const unsigned nlines[3],
+                       const float* vv, const float* vvfn, const float* vvfo,
+                       const float* ii, const float* iifn, const float* iifo);
+/* one Operator_Ext_Mur_ABC plane: m_ny, m_LineNr, m_LineNr_Shift, m_numLines, the two
+   coefficient arrays ArrayIJ [nyP][nyPP] (FDTD/extensions/operator_ext_mur_abc.h:93-103) and
+   the engine's m_start_TS (engine_ext_mur_abc.cpp:44-60).  Call in the reference's insertion
+   order xmin..zmax (openems.cpp:388-396). */
+int oems_cuda_add_mur(oems_cuda_engine* h, int ny, unsigned line_nr, unsigned line_nr_shift,
+                      const unsigned nlines[2], const float* coeff_nyP, const float* coeff_nyPP,
+                      unsigned start_ts);
+/* one dispersion order of Operator_Ext_LorentzMaterial / ConductingSheet: m_LM_pos[o],
+   v_int/v_ext/v_Lor/i_int/i_ext/i_Lor[o] as [3][count]; NULL = that ADE is off
+   (FDTD/extensions/operator_ext_lorentzmaterial.h:53-62, operator_ext_dispersive.h).
+   Call once per order, in order. */
+int oems_cuda_add_lorentz(oems_cuda_engine* h, unsigned count, const unsigned* pos3,
+                          const float* v_int, const float* v_ext, const float* v_lor,
+                          const float* i_int, const float* i_ext, const float* i_lor);
+/* Operator_Ext_LumpedRLC: v_RLC_dir, v_RLC_pos[3][count] and the nine coefficient arrays
+   (FDTD/extensions/operator_ext_lumpedRLC.h:65-82) */
+int oems_cuda_add_rlc(oems_cuda_engine* h, unsigned count, const int* dir, const unsigned* pos3,
+                      const float* ilv, const float* i2v, const float* vvd, const float* vv2,
+                      const float* vj1, const float* vj2, const float* ib0, const float* b1,
+                      const float* b2);
+/* ends the upload: compresses, moves everything to HBM, fixes the extension schedule in the
+   order of Engine::SortExtensionByPriority (FDTD/engine.cpp:87-98) and captures the
+   per-timestep CUDA graph.  Replaces Engine::Init (engine.cpp:51-59). */
+int oems_cuda_finalize(oems_cuda_engine* h);
+
+/* ---- time stepping: Engine::IterateTS / GetNumberOfTimesteps (FDTD/engine.h:48-50).
+   iterate() only enqueues; reads synchronise. */
+int oems_cuda_iterate(oems_cuda_engine* h, unsigned n_ts);
+int oems_cuda_sync(oems_cuda_engine* h);
+int oems_cuda_num_ts(oems_cuda_engine* h, unsigned* ts);
+int oems_cuda_reset(oems_cuda_engine* h); /* fields, extension state and numTS back to 0 */
+
+/* ---- readout (replaces the per-cell virtual Engine::GetVolt/GetCurr walks of L3/L4) */
+/* Engine_Interface_FDTD::CalcVoltageIntegral (FDTD/engine_interface_fdtd.cpp:206-232): fp64
+   sum of fp32 edge voltages in the reference's order.  Values: 1. */
+int oems_cuda_add_probe_voltage(oems_cuda_engine* h, const unsigned start[3],
+                                const unsigned stop[3], int* probe_id);
+/* ProcessCurrent::CalcIntegral (Common/processcurrent.cpp:96-171): fp32 loop sum, same order,
+   with the m_start_inside / m_stop_inside flags of Processing.  Values: 1. */
+int oems_cuda_add_probe_current(oems_cuda_engine* h, const unsigned start[3],
+                                const unsigned stop[3], int norm_dir, const int start_inside[3],
+                                const int stop_inside[3], int* probe_id);
+/* ProcessFieldProbe (Common/processfieldprobe.cpp:77-92): raw V (is_H=0) or I (is_H=1) of the
+   three components at one node; the caller divides by the edge length like
+   GetRawField/GetRawDualField (engine_interface_fdtd.cpp:263-268,136-141).  Values: 3. */
+int oems_cuda_add_probe_field(oems_cuda_engine* h, int is_H, const unsigned pos[3], int* probe_id);
+int oems_cuda_num_probe_values(oems_cuda_engine* h, unsigned* n_values);
+/* all probe values now, in probe_id order (Processing::Process between bursts) */
+int oems_cuda_read_probes(oems_cuda_engine* h, double* out);
+/* device-side recording: every `interval` timesteps (numTS % interval == 0, the cadence of
+   Processing::CheckTimestep, Common/processing.cpp:82-105) all probe values are appended to
+   a device series, read back later in one copy.  interval 0 switches recording off. */
+int oems_cuda_record_probes(oems_cuda_engine* h, unsigned interval, unsigned max_samples);
+/* out: [n_samples][n_values]; ts_out (optional): numTS of each sample */
+int oems_cuda_read_probe_series(oems_cuda_engine* h, double* out, unsigned* ts_out,
+                                unsigned capacity_samples, unsigned* n_samples);
+/* Engine_Interface_FDTD::CalcFastEnergy (engine_interface_fdtd.cpp:302-347) */
+int oems_cuda_energy(oems_cuda_engine* h, double* energy);
+
+/* ProcessFields::CalcField box dump (Common/processfields.cpp:283-409) with the
+   NO/NODE/CELL interpolation of engine_interface_fdtd.cpp:63-124,150-204, gathered and
+   interpolated on the device.  px/py/pz are the posLines index lists; edge_len[n] /
+   dual_edge_len[n] are Operator::GetEdgeLength(n,pos,false/true) per line of direction n
+   (lengths nx, ny, nz).  Output order {3,nz,ny,nx}, x fastest, float
+   (tools/hdf5_file_writer.cpp:286-302). interp: 0 none, 1 node, 2 cell. */
+int oems_cuda_add_dump(oems_cuda_engine* h, int is_H, int interp, unsigned nx, unsigned ny,
+                       unsigned nz, const unsigned* px, const unsigned* py, const unsigned* pz,
+                       const double* edge_len[3], const double* dual_edge_len[3], int* dump_id);
+/* computes the dump on the device at the current numTS and copies it to `out`
+   (asynchronously into pinned staging, then to the caller's buffer) */
+int oems_cuda_read_dump(oems_cuda_engine* h, int dump_id, float* out);
+
+/* slow path for unknown callers: Engine::GetVolt/SetVolt/GetCurr/SetCurr (FDTD/engine.h:55-101) */
+int oems_cuda_get_field(oems_cuda_engine* h, int is_curr, unsigned n, unsigned x, unsigned y,
+                        unsigned z, float* value);
+int oems_cuda_set_field(oems_cuda_engine* h, int is_curr, unsigned n, unsigned x, unsigned y,
+                        unsigned z, float value);
+/* whole field, ArrayNIJK order over the planes this handle holds (all of them on one GPU) */
+int oems_cuda_get_fields(oems_cuda_engine* h, int is_curr, float* out_nijk);
+int oems_cuda_set_fields(oems_cuda_engine* h, int is_curr, const float* in_nijk);
+/* UPML flux state of box b (Engine_Ext_UPML::volt_flux / curr_flux), box-local ArrayNIJK */
+int oems_cuda_get_upml_flux(oems_cuda_engine* h, int box, int is_curr, float* out_nijk);
+
+/* ---- statistics for DESIGN/bench: de-duplicated entries, index width, bytes in HBM,
+   kernels launched so far, kernels per timestep */
+typedef struct oems_cuda_stats {
+	unsigned n_unique;
+	int      index_bytes;
+	uint64_t hbm_bytes;
+	uint64_t kernels_launched;
+	unsigned kernels_per_step;
+	unsigned pml_cells_lo, pml_cells_hi; /* 64-bit count split */
+	int      uses_graph;
+} oems_cuda_stats;
+int oems_cuda_get_stats(oems_cuda_engine* h, oems_cuda_stats* out);
+/* tuning knobs (0 keeps the default): block rows and z-chunk of the stencil kernels, graph on/off */
+int oems_cuda_set_tuning(oems_cuda_engine* h, int block_rows, int z_chunk, int use_graph);
+
+/* ---- multi-GPU halo exchange over NVLink peer memory (one process per GPU).
+   Each rank exports IPC handles of its field buffers, gathers its neighbours' with
+   torch.distributed / any host channel, and opens them here; the halo planes are then written
+   straight into the neighbour's ghost plane by the boundary kernels (no host staging, no
+   collective), with device-side flags ordering the steps.  See DESIGN.md "multi-GPU". */
+#define OEMS_IPC_BYTES 256
+int oems_cuda_export_ipc(oems_cuda_engine* h, unsigned char out[OEMS_IPC_BYTES]);
+int oems_cuda_open_peers(oems_cuda_engine* h, const unsigned char* lower /*OEMS_IPC_BYTES or NULL*/,
+                         const unsigned char* upper);
+/* same-process variant (tests, or one process driving several GPUs) */
+int oems_cuda_link_peers(oems_cuda_engine* h, oems_cuda_engine* lower, oems_cuda_engine* upper);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

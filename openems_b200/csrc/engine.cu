@@ -1,0 +1,1313 @@
+// engine.cu -- host side of the B200 FDTD engine: upload, operator compression, extension
+// schedule, CUDA-graph time stepping, readout.  No CPU compute fallback exists: every field
+// update runs in the kernels of kernels.cuh.
+#include "engine.h"
+
+#include <omp.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+#define CK(call)                                                         \
+	do {                                                                 \
+		cudaError_t e_ = (call);                                         \
+		if (e_ != cudaSuccess) return check(e_, #call);                  \
+	} while (0)
+
+int Engine::check(cudaError_t e, const char* what)
+{
+	if (e == cudaSuccess) return 0;
+	err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+	return 1;
+}
+
+template <typename T> T* Engine::dalloc(size_t n, bool zero)
+{
+	T* p = nullptr;
+	if (n == 0) n = 1;
+	if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+	if (zero) cudaMemsetAsync(p, 0, n * sizeof(T), stream);
+	allocs.push_back(p);
+	hbm_bytes += n * sizeof(T);
+	return p;
+}
+template <typename T> T* Engine::upload(const std::vector<T>& v)
+{
+	T* p = dalloc<T>(v.size(), v.empty());
+	if (p && !v.empty()) cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream);
+	return p;
+}
+
+Engine::Engine(unsigned nx, unsigned ny, unsigned nz, int dev)
+{
+	gn[0] = nx; gn[1] = ny; gn[2] = nz;
+	device = dev;
+	zb = 0; ze = nz; z0 = 0; nzl = (int)nz;
+	pitch = (int)((nx + 31) / 32 * 32);
+	plane = (long long)pitch * ny;
+	comp = plane * nzl;
+}
+
+Engine::~Engine()
+{
+	cudaSetDevice(device);
+	if (stream) cudaStreamSynchronize(stream);
+	if (graph_exec) cudaGraphExecDestroy(graph_exec);
+	if (graph) cudaGraphDestroy(graph);
+	for (auto& d : dumps) {
+		if (d.h_pinned) cudaFreeHost(d.h_pinned);
+	}
+	for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
+	for (void* p : allocs) cudaFree(p);
+	if (stream) cudaStreamDestroy(stream);
+}
+
+int Engine::set_slab(unsigned b, unsigned e)
+{
+	if (have_dense || have_compressed || finalized) return fail("set_slab must precede all uploads");
+	if (b >= e || e > gn[2]) return fail("set_slab: bad range");
+	zb = b; ze = e;
+	z0 = (int)b - (b > 0 ? 1 : 0);
+	const int z1 = (int)e + (e < gn[2] ? 1 : 0);
+	nzl = z1 - z0;
+	comp = plane * nzl;
+	slab_set = true;
+	return 0;
+}
+
+// ------------------------------------------------------------------------------ uploads
+int Engine::set_operator_dense(const float* vv, const float* vi, const float* ii, const float* iv)
+{
+	if (finalized) return fail("engine already finalized");
+	if (!vv || !vi || !ii || !iv) return fail("set_operator_dense: null pointer");
+	const float* src[4] = {vv, vi, ii, iv};
+	const size_t nl = (size_t)3 * gn[0] * gn[1] * nzl;
+	for (int a = 0; a < 4; ++a) {
+		h_dense[a].resize(nl);
+		// keep ArrayNIJK order but only the held planes: [n][i][j][kl]
+#pragma omp parallel for collapse(2) schedule(static)
+		for (int n = 0; n < 3; ++n)
+			for (unsigned i = 0; i < gn[0]; ++i)
+				for (unsigned j = 0; j < gn[1]; ++j) {
+					const float* s = src[a] + (((size_t)n * gn[0] + i) * gn[1] + j) * gn[2] + z0;
+					float* d = h_dense[a].data() + (((size_t)n * gn[0] + i) * gn[1] + j) * nzl;
+					memcpy(d, s, (size_t)nzl * sizeof(float));
+				}
+	}
+	have_dense = true;
+	have_compressed = false;
+	return 0;
+}
+
+int Engine::set_operator_compressed(unsigned nu, const oems_coeff_entry* table, const void* index, int ib)
+{
+	if (finalized) return fail("engine already finalized");
+	if (!table || !index || nu == 0) return fail("set_operator_compressed: null/empty input");
+	if (ib != 2 && ib != 4) return fail("set_operator_compressed: index_bytes must be 2 or 4");
+	if (ib == 2 && nu > 65535) return fail("set_operator_compressed: more than 65535 entries need a 32-bit index");
+	CK(cudaSetDevice(device));
+	if (!stream) CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+	h_table.assign(table, table + nu);
+	index_bytes = ib;
+	n_unique = nu;
+	// index goes straight to HBM, re-pitched; padding cells point at the zero entry nu
+	const size_t cells = (size_t)plane * nzl;
+	if (d_idx) return fail("operator already uploaded");
+	void* p = nullptr;
+	CK(cudaMalloc(&p, cells * ib));
+	allocs.push_back(p);
+	hbm_bytes += cells * ib;
+	d_idx = p;
+	if (ib == 2) {
+		std::vector<uint16_t> fill(pitch, (uint16_t)nu);
+		for (long long r = 0; r < (long long)gn[1] * nzl; ++r)
+			CK(cudaMemcpyAsync((uint16_t*)p + r * pitch, fill.data(), pitch * 2, cudaMemcpyHostToDevice, stream));
+	} else {
+		std::vector<uint32_t> fill(pitch, nu);
+		for (long long r = 0; r < (long long)gn[1] * nzl; ++r)
+			CK(cudaMemcpyAsync((uint32_t*)p + r * pitch, fill.data(), pitch * 4, cudaMemcpyHostToDevice, stream));
+	}
+	CK(cudaStreamSynchronize(stream));
+	const char* src = (const char*)index + (size_t)z0 * gn[1] * gn[0] * ib;
+	CK(cudaMemcpy2DAsync(p, (size_t)pitch * ib, src, (size_t)gn[0] * ib, (size_t)gn[0] * ib, (size_t)gn[1] * nzl,
+	                     cudaMemcpyHostToDevice, stream));
+	CK(cudaStreamSynchronize(stream));
+	have_compressed = true;
+	have_dense = false;
+	return 0;
+}
+
+int Engine::set_signal(const float* sv, const float* si, unsigned len, unsigned period)
+{
+	if (finalized) return fail("engine already finalized");
+	if (!sv || !si || len == 0) return fail("set_signal: empty signal");
+	h_sig[0].assign(sv, sv + len);
+	h_sig[1].assign(si, si + len);
+	sig_len = len;
+	sig_period = period;
+	return 0;
+}
+
+int Engine::add_excitation(int is_curr, unsigned count, const unsigned* idx3, const unsigned* dir, const float* amp,
+                           const unsigned* delay)
+{
+	if (finalized) return fail("engine already finalized");
+	ExcHost& E = h_exc[is_curr ? 1 : 0];
+	for (unsigned n = 0; n < count; ++n) {
+		for (int a = 0; a < 3; ++a) {
+			if (idx3[(size_t)a * count + n] >= gn[a]) return fail("add_excitation: position outside the mesh");
+			E.idx[a].push_back(idx3[(size_t)a * count + n]);
+		}
+		if (dir[n] > 2) return fail("add_excitation: bad direction");
+		E.dir.push_back(dir[n]);
+		E.amp.push_back(amp[n]);
+		E.delay.push_back(delay[n]);
+	}
+	return 0;
+}
+
+int Engine::add_upml(const unsigned start[3], const unsigned n[3], const float* const c[6])
+{
+	if (finalized) return fail("engine already finalized");
+	if (h_upml.size() >= OEMS_MAX_PML_BOXES) return fail("add_upml: too many boxes");
+	UpmlBoxHost B;
+	for (int a = 0; a < 3; ++a) {
+		if (n[a] == 0 || start[a] + n[a] > gn[a]) return fail("add_upml: box outside the mesh");
+		B.start[a] = start[a];
+		B.n[a] = n[a];
+	}
+	const size_t cnt = (size_t)3 * n[0] * n[1] * n[2];
+	bool any = false, all = true;
+	for (int w = 0; w < 6; ++w) { any |= c[w] != nullptr; all &= c[w] != nullptr; }
+	if (any && !all) return fail("add_upml: pass all six coefficient arrays or none");
+	if (all)
+		for (int w = 0; w < 6; ++w) B.c[w].assign(c[w], c[w] + cnt);
+	h_upml.push_back(std::move(B));
+	return 0;
+}
+
+int Engine::add_mur(int ny, unsigned line, unsigned shift, const unsigned n[2], const float* cP, const float* cPP,
+                    unsigned start_ts)
+{
+	if (finalized) return fail("engine already finalized");
+	if (h_mur.size() >= OEMS_MAX_MUR) return fail("add_mur: too many planes");
+	if (ny < 0 || ny > 2) return fail("add_mur: bad direction");
+	const int nyP = (ny + 1) % 3, nyPP = (ny + 2) % 3;
+	if (n[0] != gn[nyP] || n[1] != gn[nyPP] || line >= gn[ny] || shift >= gn[ny]) return fail("add_mur: plane does not match the mesh");
+	MurHost M;
+	M.ny = ny; M.line = line; M.shift = shift; M.n[0] = n[0]; M.n[1] = n[1]; M.start_ts = start_ts;
+	M.cP.assign(cP, cP + (size_t)n[0] * n[1]);
+	M.cPP.assign(cPP, cPP + (size_t)n[0] * n[1]);
+	h_mur.push_back(std::move(M));
+	return 0;
+}
+
+int Engine::add_lorentz(unsigned count, const unsigned* pos3, const float* const c[6])
+{
+	if (finalized) return fail("engine already finalized");
+	LorHost L;
+	L.count = count;
+	L.pos.assign(pos3, pos3 + (size_t)3 * count);
+	for (unsigned i = 0; i < count; ++i)
+		for (int a = 0; a < 3; ++a)
+			if (pos3[(size_t)a * count + i] >= gn[a]) return fail("add_lorentz: position outside the mesh");
+	if ((c[0] == nullptr) != (c[1] == nullptr) || (c[3] == nullptr) != (c[4] == nullptr)) return fail("add_lorentz: int/ext coefficients come in pairs");
+	if ((c[2] && !c[0]) || (c[5] && !c[3])) return fail("add_lorentz: Lorentz pole without its Drude ADE");
+	for (int w = 0; w < 6; ++w)
+		if (c[w]) L.c[w].assign(c[w], c[w] + (size_t)3 * count);
+	h_lor.push_back(std::move(L));
+	return 0;
+}
+
+int Engine::add_rlc(unsigned count, const int* dir, const unsigned* pos3, const float* const c[9])
+{
+	if (finalized) return fail("engine already finalized");
+	RlcHost R;
+	R.count = count;
+	R.dir.assign(dir, dir + count);
+	R.pos.assign(pos3, pos3 + (size_t)3 * count);
+	for (unsigned i = 0; i < count; ++i) {
+		if (dir[i] < 0 || dir[i] > 2) return fail("add_rlc: bad direction");
+		for (int a = 0; a < 3; ++a)
+			if (pos3[(size_t)a * count + i] >= gn[a]) return fail("add_rlc: position outside the mesh");
+	}
+	for (int w = 0; w < 9; ++w) {
+		if (!c[w]) return fail("add_rlc: null coefficient array");
+		R.c[w].assign(c[w], c[w] + count);
+	}
+	h_rlc.push_back(std::move(R));
+	return 0;
+}
+
+// ------------------------------------------------------------------------------ compression
+// Re-keys the operator per cell: the 12 stencil coefficients plus, inside UPML
+// boxes, the 18 auxiliary coefficients form one 128-byte tuple; equal tuples (memcmp, like
+// SSE_coeff operator_sse_compressed.cpp:197-200) share an entry.
+namespace {
+struct EntrySet {
+	std::vector<oems_coeff_entry> items;
+	std::vector<int64_t> slots;
+	size_t mask;
+	EntrySet() : slots(1 << 12, -1), mask((1 << 12) - 1) {}
+	static uint64_t hash(const oems_coeff_entry& e)
+	{
+		const uint64_t* w = reinterpret_cast<const uint64_t*>(&e);
+		uint64_t h = 0x9E3779B97F4A7C15ull;
+		for (size_t i = 0; i < sizeof(oems_coeff_entry) / 8; ++i) {
+			h ^= w[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+			h *= 0xff51afd7ed558ccdull;
+		}
+		return h ^ (h >> 29);
+	}
+	void grow()
+	{
+		std::vector<int64_t> ns(slots.size() * 4, -1);
+		const size_t nm = ns.size() - 1;
+		for (size_t u = 0; u < items.size(); ++u) {
+			size_t s = hash(items[u]) & nm;
+			while (ns[s] >= 0) s = (s + 1) & nm;
+			ns[s] = (int64_t)u;
+		}
+		slots.swap(ns);
+		mask = nm;
+	}
+	uint32_t insert(const oems_coeff_entry& e)
+	{
+		size_t s = hash(e) & mask;
+		while (slots[s] >= 0) {
+			if (memcmp(&items[slots[s]], &e, sizeof(e)) == 0) return (uint32_t)slots[s];
+			s = (s + 1) & mask;
+		}
+		slots[s] = (int64_t)items.size();
+		items.push_back(e);
+		if (items.size() * 2 > slots.size()) grow();
+		return (uint32_t)(items.size() - 1);
+	}
+};
+} // namespace
+
+int Engine::compress_dense(std::vector<uint32_t>& index32)
+{
+	const unsigned nx = gn[0], ny = gn[1];
+	index32.assign((size_t)nx * ny * nzl, 0);
+	const int nthreads = std::max(1, std::min(omp_get_max_threads(), nzl));
+	std::vector<EntrySet> sets(nthreads);
+	for (auto& B : h_upml)
+		if (B.c[0].empty()) return fail("dense operator needs dense UPML coefficient arrays");
+#pragma omp parallel num_threads(nthreads)
+	{
+		const int t = omp_get_thread_num();
+		EntrySet& S = sets[t];
+#pragma omp for schedule(static)
+		for (int kl = 0; kl < nzl; ++kl) {
+			const unsigned gz = (unsigned)(z0 + kl);
+			for (unsigned j = 0; j < ny; ++j)
+				for (unsigned i = 0; i < nx; ++i) {
+					oems_coeff_entry e;
+					memset(&e, 0, sizeof(e));
+					for (int n = 0; n < 3; ++n) {
+						const size_t o = (((size_t)n * nx + i) * ny + j) * nzl + kl;
+						e.vv[n] = h_dense[0][o]; e.vi[n] = h_dense[1][o];
+						e.ii[n] = h_dense[2][o]; e.iv[n] = h_dense[3][o];
+					}
+					for (const auto& B : h_upml) {
+						const unsigned li = i - B.start[0], lj = j - B.start[1], lk = gz - B.start[2];
+						if (li < B.n[0] && lj < B.n[1] && lk < B.n[2]) {
+							e.pml = 1.0f;
+							for (int n = 0; n < 3; ++n) {
+								const size_t o = (((size_t)n * B.n[0] + li) * B.n[1] + lj) * B.n[2] + lk;
+								e.pml_vv[n] = B.c[0][o]; e.pml_vvfn[n] = B.c[1][o]; e.pml_vvfo[n] = B.c[2][o];
+								e.pml_ii[n] = B.c[3][o]; e.pml_iifn[n] = B.c[4][o]; e.pml_iifo[n] = B.c[5][o];
+							}
+							break;
+						}
+					}
+					// thread-local id, tagged with the thread in the upper bits for the merge
+					index32[((size_t)kl * ny + j) * nx + i] = S.insert(e);
+				}
+		}
+	}
+	// merge the thread-local sets
+	EntrySet G;
+	std::vector<std::vector<uint32_t>> remap(nthreads);
+	for (int t = 0; t < nthreads; ++t) {
+		remap[t].resize(sets[t].items.size());
+		for (size_t u = 0; u < sets[t].items.size(); ++u) remap[t][u] = G.insert(sets[t].items[u]);
+	}
+#pragma omp parallel num_threads(nthreads)
+	{
+		const int t = omp_get_thread_num();
+#pragma omp for schedule(static)
+		for (int kl = 0; kl < nzl; ++kl) {
+			uint32_t* row = index32.data() + (size_t)kl * ny * nx;
+			for (size_t q = 0; q < (size_t)ny * nx; ++q) row[q] = remap[t][row[q]];
+		}
+	}
+	h_table.swap(G.items);
+	n_unique = (unsigned)h_table.size();
+	for (int a = 0; a < 4; ++a) std::vector<float>().swap(h_dense[a]);
+	return 0;
+}
+
+int Engine::build_tables_and_index(const std::vector<uint32_t>& index32)
+{
+	const unsigned U = n_unique;
+	// device tables: U real entries + the all-zero entry U used by padding cells
+	std::vector<float4> t[10];
+	for (int w = 0; w < 10; ++w) t[w].assign(U + 1, make_float4(0, 0, 0, 0));
+	for (unsigned u = 0; u < U; ++u) {
+		const oems_coeff_entry& e = h_table[u];
+		const float flag = e.pml != 0.0f ? 1.0f : 0.0f;
+		t[0][u] = make_float4(e.vv[0], e.vv[1], e.vv[2], flag);
+		t[1][u] = make_float4(e.vi[0], e.vi[1], e.vi[2], 0);
+		t[2][u] = make_float4(e.pml_vv[0], e.pml_vv[1], e.pml_vv[2], 0);
+		t[3][u] = make_float4(e.pml_vvfn[0], e.pml_vvfn[1], e.pml_vvfn[2], 0);
+		t[4][u] = make_float4(e.pml_vvfo[0], e.pml_vvfo[1], e.pml_vvfo[2], 0);
+		t[5][u] = make_float4(e.ii[0], e.ii[1], e.ii[2], flag);
+		t[6][u] = make_float4(e.iv[0], e.iv[1], e.iv[2], 0);
+		t[7][u] = make_float4(e.pml_ii[0], e.pml_ii[1], e.pml_ii[2], 0);
+		t[8][u] = make_float4(e.pml_iifn[0], e.pml_iifn[1], e.pml_iifn[2], 0);
+		t[9][u] = make_float4(e.pml_iifo[0], e.pml_iifo[1], e.pml_iifo[2], 0);
+	}
+	for (int w = 0; w < 10; ++w) {
+		d_tab[w] = upload(t[w]);
+		if (!d_tab[w]) return fail("out of device memory (tables)");
+	}
+	if (have_compressed) return 0; // index already in HBM
+	index_bytes = (U + 1 <= 65536) ? 2 : 4;
+	const size_t cells = (size_t)plane * nzl;
+	const unsigned nx = gn[0], ny = gn[1];
+	if (index_bytes == 2) {
+		std::vector<uint16_t> h(cells, (uint16_t)U);
+#pragma omp parallel for schedule(static)
+		for (long long r = 0; r < (long long)ny * nzl; ++r)
+			for (unsigned i = 0; i < nx; ++i) h[(size_t)r * pitch + i] = (uint16_t)index32[(size_t)r * nx + i];
+		d_idx = upload(h);
+		CK(cudaStreamSynchronize(stream));
+	} else {
+		std::vector<uint32_t> h(cells, U);
+#pragma omp parallel for schedule(static)
+		for (long long r = 0; r < (long long)ny * nzl; ++r)
+			for (unsigned i = 0; i < nx; ++i) h[(size_t)r * pitch + i] = index32[(size_t)r * nx + i];
+		d_idx = upload(h);
+		CK(cudaStreamSynchronize(stream));
+	}
+	if (!d_idx) return fail("out of device memory (index)");
+	return 0;
+}
+
+// ------------------------------------------------------------------------------ extensions
+int Engine::build_pml()
+{
+	flux_floats = 0;
+	pml_cells = 0;
+	int nb = 0;
+	std::vector<long long> e_cell, e_fo, e_cs;
+	for (auto& B : h_upml) {
+		// part of the box on the planes this GPU updates (owned planes)
+		const unsigned bz0 = std::max(B.start[2], zb), bz1 = std::min(B.start[2] + B.n[2], ze);
+		B.ln[2] = 0;
+		if (bz1 <= bz0) continue;
+		B.ls[0] = (int)B.start[0]; B.ls[1] = (int)B.start[1]; B.ls[2] = (int)bz0 - z0;
+		B.ln[0] = (int)B.n[0]; B.ln[1] = (int)B.n[1]; B.ln[2] = (int)(bz1 - bz0);
+		B.gz0 = bz0;
+		B.flux_off = flux_floats;
+		const long long cs = (long long)B.ln[0] * B.ln[1] * B.ln[2];
+		flux_floats += 3 * cs;
+		pml_cells += (uint64_t)cs;
+		PmlBox pb;
+		for (int a = 0; a < 3; ++a) { pb.s[a] = B.ls[a]; pb.n[a] = B.ln[a]; }
+		pb.off = B.flux_off;
+		pE.box[nb] = pb;
+		pH.box[nb] = pb;
+		++nb;
+		// cells of the box the H stencil never visits (last line of a direction)
+		for (int lk = 0; lk < B.ln[2]; ++lk)
+			for (int lj = 0; lj < B.ln[1]; ++lj)
+				for (int li = 0; li < B.ln[0]; ++li) {
+					const unsigned x = B.ls[0] + li, y = B.ls[1] + lj, gz = bz0 + lk;
+					if (x == gn[0] - 1 || y == gn[1] - 1 || gz == gn[2] - 1) {
+						e_cell.push_back(cell_off(x, y, gz));
+						e_fo.push_back(B.flux_off + ((long long)lk * B.ln[1] + lj) * B.ln[0] + li);
+						e_cs.push_back(cs);
+					}
+				}
+	}
+	pE.nboxes = pH.nboxes = nb;
+	has_pml = nb > 0;
+	if (has_pml) {
+		d_flux_v = dalloc<float>((size_t)flux_floats);
+		d_flux_i = dalloc<float>((size_t)flux_floats);
+		if (!d_flux_v || !d_flux_i) return fail("out of device memory (UPML flux)");
+	}
+	pEdge.count = (long long)e_cell.size();
+	if (pEdge.count) {
+		pEdge.cell = upload(e_cell);
+		pEdge.fluxoff = upload(e_fo);
+		pEdge.fluxcs = upload(e_cs);
+		pEdge.X = d_I;
+		pEdge.idx = d_idx;
+		pEdge.tP0 = d_tab[7]; pEdge.tP1 = d_tab[8]; pEdge.tP2 = d_tab[9];
+		pEdge.flux = d_flux_i;
+		pEdge.comp = comp;
+	}
+	return 0;
+}
+
+int Engine::build_mur()
+{
+	memset(&pMur, 0, sizeof(pMur));
+	if (h_mur.empty()) return 0;
+	long long total = 0;
+	std::vector<float> cP, cPP;
+	for (size_t m = 0; m < h_mur.size(); ++m) {
+		const MurHost& M = h_mur[m];
+		MurPlane& P = pMur.pl[m];
+		P.ny = M.ny; P.nyP = (M.ny + 1) % 3; P.nyPP = (M.ny + 2) % 3;
+		P.line = (int)M.line; P.shift = (int)M.shift;
+		P.n0 = (int)M.n[0]; P.n1 = (int)M.n[1];
+		P.start_ts = M.start_ts;
+		P.eoff = total;
+		total += (long long)M.n[0] * M.n[1];
+		cP.insert(cP.end(), M.cP.begin(), M.cP.end());
+		cPP.insert(cPP.end(), M.cPP.begin(), M.cPP.end());
+	}
+	// write conflicts on shared edges: Apply2Voltages runs the planes in reverse insertion order
+	// (engine.cpp:87-91,239-244), so the plane inserted FIRST writes last and wins.  A component
+	// c of a cell is written by at most two planes (normals != c).
+	std::vector<unsigned char> winner((size_t)total, 3);
+	for (size_t m = 0; m < h_mur.size(); ++m) {
+		const MurPlane& P = pMur.pl[m];
+		for (int a = 0; a < P.n0; ++a)
+			for (int b = 0; b < P.n1; ++b) {
+				int pos[3];
+				pos[P.ny] = P.line; pos[P.nyP] = a; pos[P.nyPP] = b;
+				unsigned char w = 3;
+				const int comps[2] = {P.nyP, P.nyPP};
+				for (int q = 0; q < 2; ++q) {
+					const int other = 3 - P.ny - comps[q]; // normal of the other plane that writes comps[q]
+					for (size_t m2 = 0; m2 < m; ++m2)
+						if (pMur.pl[m2].ny == other && pos[other] == pMur.pl[m2].line) {
+							// the earlier plane overrides this write; exact only if both are active at the
+							// same time, which holds unless their start delays differ
+							if (pMur.pl[m2].start_ts <= P.start_ts) w &= (unsigned char)~(1u << q);
+						}
+				}
+				winner[(size_t)P.eoff + (size_t)a * P.n1 + b] = w;
+			}
+	}
+	pMur.V = d_V;
+	pMur.cP = upload(cP); pMur.cPP = upload(cPP);
+	pMur.vP = dalloc<float>((size_t)total); pMur.vPP = dalloc<float>((size_t)total);
+	pMur.winner = upload(winner);
+	pMur.numTS = d_numTS;
+	pMur.nplanes = (int)h_mur.size();
+	pMur.total = total;
+	pMur.pitch = pitch; pMur.plane = plane; pMur.comp = comp;
+	pMur.z0 = z0; pMur.zown0 = (int)zb; pMur.zown1 = (int)ze;
+	if (!pMur.cP || !pMur.cPP || !pMur.vP || !pMur.vPP || !pMur.winner) return fail("out of device memory (Mur)");
+	return 0;
+}
+
+int Engine::build_exc()
+{
+	for (int w = 0; w < 2; ++w) {
+		memset(&pExc[w], 0, sizeof(ExcParams));
+		const ExcHost& E = h_exc[w];
+		const size_t cnt = E.dir.size();
+		if (cnt == 0) continue;
+		if (sig_len == 0) return fail("excitation without a signal (set_signal)");
+		// group by target, keep list order inside a group (sequential += of the CPU loop)
+		std::map<long long, std::vector<unsigned>> groups;
+		std::vector<long long> order;
+		for (unsigned n = 0; n < cnt; ++n) {
+			if (!owned(E.idx[2][n])) continue;
+			const long long t = (long long)E.dir[n] * comp + cell_off(E.idx[0][n], E.idx[1][n], E.idx[2][n]);
+			auto it = groups.find(t);
+			if (it == groups.end()) { groups[t] = {n}; order.push_back(t); }
+			else it->second.push_back(n);
+		}
+		if (order.empty()) continue;
+		std::vector<long long> tgt;
+		std::vector<unsigned> gstart, delay;
+		std::vector<float> amp;
+		for (long long t : order) {
+			tgt.push_back(t);
+			gstart.push_back((unsigned)amp.size());
+			for (unsigned n : groups[t]) { amp.push_back(E.amp[n]); delay.push_back(E.delay[n]); }
+		}
+		gstart.push_back((unsigned)amp.size());
+		ExcParams& P = pExc[w];
+		P.X = w ? d_I : d_V;
+		P.tgt = upload(tgt); P.gstart = upload(gstart); P.amp = upload(amp); P.delay = upload(delay);
+		P.sig = d_sig[w];
+		P.numTS = d_numTS;
+		P.groups = (unsigned)tgt.size();
+		P.length = sig_len;
+		P.period = sig_period;
+		if (!P.tgt || !P.gstart || !P.amp || !P.delay) return fail("out of device memory (excitation)");
+	}
+	return 0;
+}
+
+int Engine::build_lorentz()
+{
+	lor_dev.clear();
+	for (const LorHost& L : h_lor) {
+		// keep only the cells on owned planes
+		std::vector<unsigned> keep;
+		for (unsigned i = 0; i < L.count; ++i)
+			if (owned(L.pos[(size_t)2 * L.count + i])) keep.push_back(i);
+		const unsigned cnt = (unsigned)keep.size();
+		std::vector<long long> cell(cnt);
+		for (unsigned q = 0; q < cnt; ++q) {
+			const unsigned i = keep[q];
+			cell[q] = cell_off(L.pos[i], L.pos[(size_t)L.count + i], L.pos[(size_t)2 * L.count + i]);
+		}
+		auto pick = [&](const std::vector<float>& src) {
+			std::vector<float> d((size_t)3 * cnt);
+			for (int n = 0; n < 3; ++n)
+				for (unsigned q = 0; q < cnt; ++q) d[(size_t)n * cnt + q] = src[(size_t)n * L.count + keep[q]];
+			return d;
+		};
+		LorDev D;
+		memset(&D.v, 0, sizeof(LorParams));
+		memset(&D.i, 0, sizeof(LorParams));
+		D.v_on = !L.c[0].empty() && cnt > 0;
+		D.i_on = !L.c[3].empty() && cnt > 0;
+		const long long* d_cell = cnt ? upload(cell) : nullptr;
+		if (D.v_on) {
+			D.v.X = d_V; D.v.cell = d_cell; D.v.count = cnt; D.v.comp = comp;
+			D.v.c_int = upload(pick(L.c[0])); D.v.c_ext = upload(pick(L.c[1]));
+			D.v.ade = dalloc<float>((size_t)3 * cnt);
+			if (!L.c[2].empty()) { D.v.c_lor = upload(pick(L.c[2])); D.v.lor_ade = dalloc<float>((size_t)3 * cnt); }
+		}
+		if (D.i_on) {
+			D.i.X = d_I; D.i.cell = d_cell; D.i.count = cnt; D.i.comp = comp;
+			D.i.c_int = upload(pick(L.c[3])); D.i.c_ext = upload(pick(L.c[4]));
+			D.i.ade = dalloc<float>((size_t)3 * cnt);
+			if (!L.c[5].empty()) { D.i.c_lor = upload(pick(L.c[5])); D.i.lor_ade = dalloc<float>((size_t)3 * cnt); }
+		}
+		lor_dev.push_back(D);
+	}
+	return 0;
+}
+
+int Engine::build_rlc()
+{
+	rlc_dev.clear();
+	for (const RlcHost& R : h_rlc) {
+		std::vector<unsigned> keep;
+		for (unsigned i = 0; i < R.count; ++i)
+			if (owned(R.pos[(size_t)2 * R.count + i])) keep.push_back(i);
+		const unsigned cnt = (unsigned)keep.size();
+		if (!cnt) continue;
+		std::vector<long long> tgt(cnt);
+		for (unsigned q = 0; q < cnt; ++q) {
+			const unsigned i = keep[q];
+			tgt[q] = (long long)R.dir[i] * comp + cell_off(R.pos[i], R.pos[(size_t)R.count + i], R.pos[(size_t)2 * R.count + i]);
+		}
+		auto pick = [&](const std::vector<float>& src) {
+			std::vector<float> d(cnt);
+			for (unsigned q = 0; q < cnt; ++q) d[q] = src[keep[q]];
+			return d;
+		};
+		RlcParams P;
+		memset(&P, 0, sizeof(P));
+		P.V = d_V;
+		P.tgt = upload(tgt);
+		P.ilv = upload(pick(R.c[0])); P.i2v = upload(pick(R.c[1])); P.vvd = upload(pick(R.c[2]));
+		P.vv2 = upload(pick(R.c[3])); P.vj1 = upload(pick(R.c[4])); P.vj2 = upload(pick(R.c[5]));
+		P.ib0 = upload(pick(R.c[6])); P.b1 = upload(pick(R.c[7])); P.b2 = upload(pick(R.c[8]));
+		P.Vd = dalloc<float>((size_t)3 * cnt); P.J = dalloc<float>((size_t)3 * cnt); P.Il = dalloc<float>(cnt);
+		P.numTS = d_numTS;
+		P.count = cnt;
+		rlc_dev.push_back(P);
+	}
+	return 0;
+}
+
+// ------------------------------------------------------------------------------ finalize
+int Engine::finalize()
+{
+	if (finalized) return fail("engine already finalized");
+	if (!have_dense && !have_compressed) return fail("finalize: no operator uploaded");
+	CK(cudaSetDevice(device));
+	if (!stream) CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+
+	std::vector<uint32_t> index32;
+	if (have_dense) {
+		if (compress_dense(index32)) return 1;
+	}
+	if (build_tables_and_index(index32)) return 1;
+	std::vector<uint32_t>().swap(index32);
+
+	const size_t nfield = (size_t)3 * comp;
+	d_V = dalloc<float>(nfield);
+	d_I = dalloc<float>(nfield);
+	if (!d_V || !d_I) return fail("out of device memory (fields)");
+	d_numTS = dalloc<unsigned>(1);
+	d_energy = dalloc<double>(2);
+	d_flagE = dalloc<unsigned>(8);
+	d_flagH = d_flagE + 1;
+	d_halo_cnt = d_flagE + 2;
+	d_halo_err = d_flagE + 4;
+	if (sig_len) {
+		d_sig[0] = upload(h_sig[0]);
+		d_sig[1] = upload(h_sig[1]);
+	}
+
+	// stencil parameter blocks
+	StencilParams base;
+	memset(&base, 0, sizeof(base));
+	base.V = d_V; base.I = d_I; base.idx = d_idx;
+	base.nx = (int)gn[0]; base.ny = (int)gn[1]; base.nz = nzl;
+	base.pitch = pitch; base.plane = plane; base.comp = comp;
+	base.zchunk = tune_zchunk;
+	pE = base; pH = base;
+	pE.tA = d_tab[0]; pE.tB = d_tab[1]; pE.tP0 = d_tab[2]; pE.tP1 = d_tab[3]; pE.tP2 = d_tab[4];
+	pH.tA = d_tab[5]; pH.tB = d_tab[6]; pH.tP0 = d_tab[7]; pH.tP1 = d_tab[8]; pH.tP2 = d_tab[9];
+	// update ranges in local planes: E on all owned planes, H on owned planes below the global top
+	pE.k0 = (int)zb - z0; pE.k1 = (int)ze - z0;
+	pH.k0 = (int)zb - z0; pH.k1 = (int)std::min(ze, gn[2] - 1) - z0;
+
+	if (build_pml()) return 1;
+	pE.flux = d_flux_v; pH.flux = d_flux_i;
+	if (build_mur()) return 1;
+	if (build_exc()) return 1;
+	if (build_lorentz()) return 1;
+	if (build_rlc()) return 1;
+	CK(cudaStreamSynchronize(stream));
+	CK(cudaGetLastError());
+
+	build_schedule();
+	finalized = true;
+	// free host staging
+	std::vector<oems_coeff_entry>().swap(h_table);
+	for (auto& B : h_upml) for (int w = 0; w < 6; ++w) std::vector<float>().swap(B.c[w]);
+	return 0;
+}
+
+// ------------------------------------------------------------------------------ schedule
+template <typename K, typename P> static void launch1d(K kern, const P& p, long long n, cudaStream_t s)
+{
+	if (n <= 0) return;
+	const int bs = 128;
+	kern<<<(unsigned)((n + bs - 1) / bs), bs, 0, s>>>(p);
+}
+
+void Engine::build_schedule()
+{
+	step.clear();
+	const bool i16 = index_bytes == 2;
+	const dim3 block(32, tune_rows);
+	auto stencil_grid = [&](const StencilParams& p, int rows_total) {
+		return dim3((unsigned)((pitch / 4 + 31) / 32), (unsigned)((rows_total + tune_rows - 1) / tune_rows),
+		            (unsigned)std::max(1, (p.k1 - p.k0 + p.zchunk - 1) / p.zchunk));
+	};
+	const bool multi = peers_linked;
+
+	// ---- pre-voltage hooks, reverse priority order (engine.cpp:224-230):
+	//      Mur, Lorentz, RLC  (UPML pre is fused into the E kernel; Excitation has no pre hook)
+	if (pMur.nplanes) step.push_back([this](cudaStream_t s) { launch1d(k_mur_pre, pMur, pMur.total, s); });
+	// list order: [.., RLC, CondSheet, Lorentz, Mur, Excitation]; pre-hooks walk it
+	// back to front: Mur, Lorentz, RLC
+	for (size_t o = 0; o < lor_dev.size(); ++o)
+		if (lor_dev[o].v_on) step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_pre, lor_dev[o].v, lor_dev[o].v.count, s); });
+	for (size_t r = 0; r < rlc_dev.size(); ++r)
+		step.push_back([this, r](cudaStream_t s) { launch1d(k_rlc_pre, rlc_dev[r], rlc_dev[r].count, s); });
+	// ---- multi-GPU: the ghost H plane of this step must have arrived
+	if (multi && peer_lo)
+		step.push_back([this](cudaStream_t s) {
+			WaitParams w{d_flagH, d_numTS, 0u, d_halo_err, 4000000000ll};
+			k_halo_wait<<<1, 1, 0, s>>>(w);
+		});
+	// ---- E half-step with fused UPML
+	if (pE.k1 > pE.k0)
+		step.push_back([this, i16, block, stencil_grid](cudaStream_t s) {
+			const dim3 g = stencil_grid(pE, pE.ny);
+			if (i16) { if (has_pml) k_update_E<uint16_t, true><<<g, block, 0, s>>>(pE); else k_update_E<uint16_t, false><<<g, block, 0, s>>>(pE); }
+			else { if (has_pml) k_update_E<uint32_t, true><<<g, block, 0, s>>>(pE); else k_update_E<uint32_t, false><<<g, block, 0, s>>>(pE); }
+		});
+	// ---- post-voltage hooks (UPML fused), then Mur post
+	if (pMur.nplanes) step.push_back([this](cudaStream_t s) { launch1d(k_mur_post, pMur, pMur.total, s); });
+	// ---- apply-voltage hooks in list order: RLC, Lorentz, Mur, Excitation
+	for (size_t r = rlc_dev.size(); r-- > 0;) // same priority: reversed insertion order
+		step.push_back([this, r](cudaStream_t s) { launch1d(k_rlc_apply, rlc_dev[r], rlc_dev[r].count, s); });
+	for (size_t o = 0; o < lor_dev.size(); ++o)
+		if (lor_dev[o].v_on) step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_apply, lor_dev[o].v, lor_dev[o].v.count, s); });
+	if (pMur.nplanes) step.push_back([this](cudaStream_t s) { launch1d(k_mur_apply, pMur, pMur.total, s); });
+	if (pExc[0].groups) step.push_back([this](cudaStream_t s) { launch1d(k_excite, pExc[0], pExc[0].groups, s); });
+	// ---- multi-GPU: tangential E of my lowest owned plane -> lower neighbour's ghost plane
+	if (multi && peer_lo)
+		step.push_back([this](cudaStream_t s) {
+			HaloParams h{d_V, peer_lo_V, (long long)((int)zb - z0) * plane, peer_lo_ghostE_off, comp, peer_lo_comp, plane,
+			             d_halo_cnt, peer_lo_flagE, d_numTS, 1u};
+			k_halo_push<<<64, 256, 0, s>>>(h);
+		});
+	// ---- pre-current hooks: Lorentz (UPML fused)
+	for (size_t o = 0; o < lor_dev.size(); ++o)
+		if (lor_dev[o].i_on) step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_pre, lor_dev[o].i, lor_dev[o].i.count, s); });
+	if (multi && peer_hi)
+		step.push_back([this](cudaStream_t s) {
+			WaitParams w{d_flagE, d_numTS, 1u, d_halo_err, 4000000000ll};
+			k_halo_wait<<<1, 1, 0, s>>>(w);
+		});
+	// ---- H half-step with fused UPML, then the UPML cells the stencil never visits
+	if (pH.k1 > pH.k0)
+		step.push_back([this, i16, block, stencil_grid](cudaStream_t s) {
+			const dim3 g = stencil_grid(pH, pH.ny - 1);
+			if (i16) { if (has_pml) k_update_H<uint16_t, true><<<g, block, 0, s>>>(pH); else k_update_H<uint16_t, false><<<g, block, 0, s>>>(pH); }
+			else { if (has_pml) k_update_H<uint32_t, true><<<g, block, 0, s>>>(pH); else k_update_H<uint32_t, false><<<g, block, 0, s>>>(pH); }
+		});
+	if (pEdge.count)
+		step.push_back([this, i16](cudaStream_t s) {
+			if (i16) launch1d(k_upml_untouched_H<uint16_t>, pEdge, pEdge.count, s);
+			else launch1d(k_upml_untouched_H<uint32_t>, pEdge, pEdge.count, s);
+		});
+	// ---- apply-current hooks: Lorentz, Excitation
+	for (size_t o = 0; o < lor_dev.size(); ++o)
+		if (lor_dev[o].i_on) step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_apply, lor_dev[o].i, lor_dev[o].i.count, s); });
+	if (pExc[1].groups) step.push_back([this](cudaStream_t s) { launch1d(k_excite, pExc[1], pExc[1].groups, s); });
+	if (multi && peer_hi)
+		step.push_back([this](cudaStream_t s) {
+			HaloParams h{d_I, peer_hi_I, (long long)((int)ze - 1 - z0) * plane, peer_hi_ghostH_off, comp, peer_hi_comp, plane,
+			             d_halo_cnt + 1, peer_hi_flagH, d_numTS, 1u};
+			k_halo_push<<<64, 256, 0, s>>>(h);
+		});
+	step.push_back([this](cudaStream_t s) { k_tick<<<1, 1, 0, s>>>(d_numTS); });
+	kernels_per_step = (unsigned)step.size();
+
+	// ---- capture one timestep into a CUDA graph (launch-bound small meshes)
+	if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+	if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+	use_graph = tune_graph != 0;
+	if (use_graph) {
+		if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+			for (auto& f : step) f(stream);
+			if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || !graph ||
+			    cudaGraphInstantiate(&graph_exec, graph, 0) != cudaSuccess) {
+				use_graph = false;
+				cudaGetLastError();
+			}
+		} else {
+			use_graph = false;
+			cudaGetLastError();
+		}
+	}
+}
+
+void Engine::launch_probes(double* dst)
+{
+	if (!n_values) return;
+	ProbeParams p = pProbe;
+	p.out = dst;
+	const unsigned wpb = 4;
+	k_probes<<<(p.nprobes + wpb - 1) / wpb, wpb * 32, 0, stream>>>(p);
+	++kernels_launched;
+}
+
+int Engine::iterate(unsigned n)
+{
+	if (!finalized) return fail("iterate: engine not finalized");
+	CK(cudaSetDevice(device));
+	if (!probes_built && !h_probes.empty())
+		if (build_probes()) return 1;
+	for (unsigned it = 0; it < n; ++it) {
+		if (use_graph) {
+			CK(cudaGraphLaunch(graph_exec, stream));
+		} else {
+			for (auto& f : step) f(stream);
+		}
+		kernels_launched += kernels_per_step;
+		++numTS_host;
+		if (rec_interval && numTS_host % rec_interval == 0 && rec_count < rec_cap && n_values) {
+			launch_probes(d_series + (size_t)rec_count * n_values);
+			rec_ts.push_back(numTS_host);
+			++rec_count;
+		}
+	}
+	CK(cudaGetLastError());
+	return 0;
+}
+
+int Engine::sync()
+{
+	CK(cudaSetDevice(device));
+	if (stream) CK(cudaStreamSynchronize(stream));
+	if (d_halo_err) {
+		unsigned e = 0;
+		CK(cudaMemcpy(&e, d_halo_err, sizeof(e), cudaMemcpyDeviceToHost));
+		if (e) return fail("halo exchange timed out waiting for a neighbour GPU");
+	}
+	return 0;
+}
+
+int Engine::reset()
+{
+	if (!finalized) return fail("reset: engine not finalized");
+	CK(cudaSetDevice(device));
+	CK(cudaStreamSynchronize(stream));
+	const size_t nfield = (size_t)3 * comp;
+	CK(cudaMemsetAsync(d_V, 0, nfield * sizeof(float), stream));
+	CK(cudaMemsetAsync(d_I, 0, nfield * sizeof(float), stream));
+	if (has_pml) {
+		CK(cudaMemsetAsync(d_flux_v, 0, (size_t)flux_floats * sizeof(float), stream));
+		CK(cudaMemsetAsync(d_flux_i, 0, (size_t)flux_floats * sizeof(float), stream));
+	}
+	if (pMur.nplanes) {
+		CK(cudaMemsetAsync(pMur.vP, 0, (size_t)pMur.total * sizeof(float), stream));
+		CK(cudaMemsetAsync(pMur.vPP, 0, (size_t)pMur.total * sizeof(float), stream));
+	}
+	for (auto& D : lor_dev) {
+		for (LorParams* P : {&D.v, &D.i}) {
+			if (P->ade) CK(cudaMemsetAsync(P->ade, 0, (size_t)3 * P->count * sizeof(float), stream));
+			if (P->lor_ade) CK(cudaMemsetAsync(P->lor_ade, 0, (size_t)3 * P->count * sizeof(float), stream));
+		}
+	}
+	for (auto& R : rlc_dev) {
+		CK(cudaMemsetAsync(R.Vd, 0, (size_t)3 * R.count * sizeof(float), stream));
+		CK(cudaMemsetAsync(R.J, 0, (size_t)3 * R.count * sizeof(float), stream));
+		CK(cudaMemsetAsync(R.Il, 0, (size_t)R.count * sizeof(float), stream));
+	}
+	CK(cudaMemsetAsync(d_numTS, 0, sizeof(unsigned), stream));
+	CK(cudaMemsetAsync(d_flagE, 0, 8 * sizeof(unsigned), stream));
+	numTS_host = 0;
+	rec_count = 0;
+	rec_ts.clear();
+	CK(cudaStreamSynchronize(stream));
+	return 0;
+}
+
+// ------------------------------------------------------------------------------ probes
+int Engine::add_probe_voltage(const unsigned start[3], const unsigned stop[3], int* id)
+{
+	if (rec_count) return fail("probes cannot be added while a recorded series holds samples");
+	probes_built = false;
+	for (int a = 0; a < 3; ++a)
+		if (start[a] >= gn[a] || stop[a] >= gn[a]) return fail("add_probe_voltage: position outside the mesh");
+	ProbeHost P;
+	P.kind = 0;
+	// engine_interface_fdtd.cpp:206-232
+	if (((start[0] != stop[0]) + (start[1] != stop[1]) + (start[2] != stop[2])) == 1) {
+		for (int n = 0; n < 3; ++n) {
+			if (start[n] < stop[n]) {
+				unsigned pos[3] = {start[0], start[1], start[2]};
+				for (; pos[n] < stop[n]; ++pos[n])
+					if (owned(pos[2])) { P.off.push_back(n * comp + cell_off(pos[0], pos[1], pos[2])); P.sign.push_back(1); }
+			} else {
+				unsigned pos[3] = {stop[0], stop[1], stop[2]};
+				for (; pos[n] < start[n]; ++pos[n])
+					if (owned(pos[2])) { P.off.push_back(n * comp + cell_off(pos[0], pos[1], pos[2])); P.sign.push_back(-1); }
+			}
+		}
+	}
+	if (id) *id = (int)h_probes.size();
+	h_probes.push_back(std::move(P));
+	return 0;
+}
+
+int Engine::add_probe_current(const unsigned start[3], const unsigned stop[3], int nd, const int si[3], const int ei[3], int* id)
+{
+	if (rec_count) return fail("probes cannot be added while a recorded series holds samples");
+	probes_built = false;
+	for (int a = 0; a < 3; ++a)
+		if (start[a] >= gn[a] || stop[a] >= gn[a] || start[a] > stop[a]) return fail("add_probe_current: bad box");
+	if (nd < 0 || nd > 2) return fail("add_probe_current: bad normal direction");
+	ProbeHost P;
+	P.kind = 1;
+	auto term = [&](int n, unsigned x, unsigned y, unsigned z, int sgn) {
+		if (owned(z)) { P.off.push_back(n * comp + cell_off(x, y, z)); P.sign.push_back((signed char)sgn); }
+	};
+	// Common/processcurrent.cpp:96-171
+	switch (nd) {
+	case 0:
+		if (ei[0] && si[2]) for (unsigned i = start[1] + 1; i <= stop[1]; ++i) term(1, stop[0], i, start[2], 1);
+		if (ei[0] && ei[1]) for (unsigned i = start[2] + 1; i <= stop[2]; ++i) term(2, stop[0], stop[1], i, 1);
+		if (si[0] && ei[2]) for (unsigned i = start[1] + 1; i <= stop[1]; ++i) term(1, start[0], i, stop[2], -1);
+		if (si[0] && si[1]) for (unsigned i = start[2] + 1; i <= stop[2]; ++i) term(2, start[0], start[1], i, -1);
+		break;
+	case 1:
+		if (si[0] && si[1]) for (unsigned i = start[2] + 1; i <= stop[2]; ++i) term(2, start[0], start[1], i, 1);
+		if (ei[1] && ei[2]) for (unsigned i = start[0] + 1; i <= stop[0]; ++i) term(0, i, stop[1], stop[2], 1);
+		if (ei[0] && ei[1]) for (unsigned i = start[2] + 1; i <= stop[2]; ++i) term(2, stop[0], stop[1], i, -1);
+		if (si[1] && si[2]) for (unsigned i = start[0] + 1; i <= stop[0]; ++i) term(0, i, start[1], start[2], -1);
+		break;
+	default:
+		if (si[1] && si[2]) for (unsigned i = start[0] + 1; i <= stop[0]; ++i) term(0, i, start[1], start[2], 1);
+		if (ei[0] && si[2]) for (unsigned i = start[1] + 1; i <= stop[1]; ++i) term(1, stop[0], i, start[2], 1);
+		if (ei[1] && ei[2]) for (unsigned i = start[0] + 1; i <= stop[0]; ++i) term(0, i, stop[1], stop[2], -1);
+		if (si[0] && ei[2]) for (unsigned i = start[1] + 1; i <= stop[1]; ++i) term(1, start[0], i, stop[2], -1);
+		break;
+	}
+	if (id) *id = (int)h_probes.size();
+	h_probes.push_back(std::move(P));
+	return 0;
+}
+
+int Engine::add_probe_field(int is_H, const unsigned pos[3], int* id)
+{
+	if (rec_count) return fail("probes cannot be added while a recorded series holds samples");
+	probes_built = false;
+	for (int a = 0; a < 3; ++a)
+		if (pos[a] >= gn[a]) return fail("add_probe_field: position outside the mesh");
+	ProbeHost P;
+	P.kind = is_H ? 3 : 2;
+	if (owned(pos[2]))
+		for (int n = 0; n < 3; ++n) { P.off.push_back(n * comp + cell_off(pos[0], pos[1], pos[2])); P.sign.push_back(1); }
+	if (id) *id = (int)h_probes.size();
+	h_probes.push_back(std::move(P));
+	return 0;
+}
+
+int Engine::build_probes()
+{
+	if (!finalized) return fail("probes need a finalized engine");
+	std::vector<long long> off;
+	std::vector<signed char> sign;
+	std::vector<unsigned> pstart, pvalue;
+	std::vector<unsigned char> kind;
+	n_values = 0;
+	for (const ProbeHost& P : h_probes) {
+		pstart.push_back((unsigned)off.size());
+		pvalue.push_back(n_values);
+		kind.push_back((unsigned char)P.kind);
+		off.insert(off.end(), P.off.begin(), P.off.end());
+		sign.insert(sign.end(), P.sign.begin(), P.sign.end());
+		n_values += P.kind >= 2 ? 3 : 1;
+	}
+	pstart.push_back((unsigned)off.size());
+	memset(&pProbe, 0, sizeof(pProbe));
+	pProbe.V = d_V; pProbe.I = d_I;
+	pProbe.term_off = upload(off); pProbe.term_sign = upload(sign);
+	pProbe.pstart = upload(pstart); pProbe.pvalue = upload(pvalue); pProbe.pkind = upload(kind);
+	pProbe.nprobes = (unsigned)h_probes.size();
+	d_probe_now = dalloc<double>(n_values);
+	if (rec_interval && rec_cap) {
+		d_series = dalloc<double>((size_t)rec_cap * n_values);
+		if (!d_series) return fail("out of device memory (probe series)");
+	}
+	probes_built = true;
+	return 0;
+}
+
+int Engine::read_probes(double* out)
+{
+	if (!finalized) return fail("read_probes: engine not finalized");
+	CK(cudaSetDevice(device));
+	if (!probes_built && build_probes()) return 1;
+	if (!n_values) return 0;
+	launch_probes(d_probe_now);
+	CK(cudaMemcpyAsync(out, d_probe_now, n_values * sizeof(double), cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	return 0;
+}
+
+int Engine::record_probes(unsigned interval, unsigned max_samples)
+{
+	if (probes_built && max_samples > rec_cap && interval) {
+		CK(cudaSetDevice(device));
+		d_series = dalloc<double>((size_t)max_samples * n_values);
+		if (!d_series) return fail("out of device memory (probe series)");
+	}
+	rec_interval = interval;
+	rec_cap = interval ? max_samples : 0;
+	rec_count = 0;
+	rec_ts.clear();
+	return 0;
+}
+
+int Engine::read_probe_series(double* out, unsigned* ts_out, unsigned cap, unsigned* n)
+{
+	CK(cudaSetDevice(device));
+	const unsigned cnt = std::min(cap, rec_count);
+	if (cnt && n_values) {
+		CK(cudaMemcpyAsync(out, d_series, (size_t)cnt * n_values * sizeof(double), cudaMemcpyDeviceToHost, stream));
+		CK(cudaStreamSynchronize(stream));
+	}
+	if (ts_out) for (unsigned i = 0; i < cnt; ++i) ts_out[i] = rec_ts[i];
+	if (n) *n = cnt;
+	return 0;
+}
+
+int Engine::energy(double* e)
+{
+	if (!finalized) return fail("energy: engine not finalized");
+	CK(cudaSetDevice(device));
+	EnergyParams p;
+	p.V = d_V; p.I = d_I;
+	p.nx = (int)gn[0]; p.ny = (int)gn[1];
+	p.k0 = (int)zb - z0; p.k1 = (int)std::min(ze, gn[2] - 1) - z0;
+	p.pitch = pitch; p.plane = plane; p.comp = comp;
+	p.acc = d_energy;
+	CK(cudaMemsetAsync(d_energy, 0, 2 * sizeof(double), stream));
+	const long long rows = (long long)(p.k1 - p.k0) * (p.ny - 1);
+	if (rows > 0) {
+		const unsigned blocks = (unsigned)std::min<long long>((rows + 7) / 8, 148 * 8);
+		k_energy<<<blocks, dim3(32, 8), 0, stream>>>(p);
+		++kernels_launched;
+	}
+	double acc[2];
+	CK(cudaMemcpyAsync(acc, d_energy, sizeof(acc), cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	*e = 8.85418781762e-12 * acc[0] + 1.256637062e-6 * acc[1];
+	return 0;
+}
+
+// ------------------------------------------------------------------------------ dumps
+int Engine::add_dump(int is_H, int interp, unsigned nx, unsigned ny, unsigned nz, const unsigned* px, const unsigned* py,
+                     const unsigned* pz, const double* const el[3], const double* const del[3], int* id)
+{
+	if (!finalized) return fail("add_dump: engine not finalized");
+	if (interp < 0 || interp > 2) return fail("add_dump: bad interpolation type");
+	if (slab_set) return fail("add_dump: dumps on a z-slab engine are not supported yet");
+	CK(cudaSetDevice(device));
+	for (unsigned i = 0; i < nx; ++i) if (px[i] >= gn[0]) return fail("add_dump: x index outside the mesh");
+	for (unsigned i = 0; i < ny; ++i) if (py[i] >= gn[1]) return fail("add_dump: y index outside the mesh");
+	for (unsigned i = 0; i < nz; ++i) if (pz[i] >= gn[2]) return fail("add_dump: z index outside the mesh");
+	DumpHost D;
+	memset(&D.p, 0, sizeof(D.p));
+	D.count = (size_t)nx * ny * nz;
+	D.p.V = d_V; D.p.I = d_I;
+	D.p.px = upload(std::vector<unsigned>(px, px + nx));
+	D.p.py = upload(std::vector<unsigned>(py, py + ny));
+	D.p.pz = upload(std::vector<unsigned>(pz, pz + nz));
+	for (int a = 0; a < 3; ++a) {
+		D.p.el[a] = upload(std::vector<double>(el[a], el[a] + gn[a]));
+		D.p.del[a] = upload(std::vector<double>(del[a], del[a] + gn[a]));
+	}
+	D.d_out = dalloc<float>(3 * D.count);
+	D.p.out = D.d_out;
+	D.p.is_H = is_H; D.p.interp = interp;
+	D.p.onx = nx; D.p.ony = ny; D.p.onz = nz;
+	D.p.nx = (int)gn[0]; D.p.ny = (int)gn[1]; D.p.gnz = (int)gn[2]; D.p.z0 = z0;
+	D.p.pitch = pitch; D.p.plane = plane; D.p.comp = comp;
+	D.h_pinned = nullptr;
+	CK(cudaMallocHost(&D.h_pinned, 3 * D.count * sizeof(float)));
+	if (id) *id = (int)dumps.size();
+	dumps.push_back(D);
+	return 0;
+}
+
+int Engine::read_dump(int id, float* out)
+{
+	if (id < 0 || id >= (int)dumps.size()) return fail("read_dump: bad id");
+	CK(cudaSetDevice(device));
+	DumpHost& D = dumps[id];
+	launch1d(k_dump, D.p, (long long)D.count, stream);
+	++kernels_launched;
+	CK(cudaMemcpyAsync(D.h_pinned, D.d_out, 3 * D.count * sizeof(float), cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	memcpy(out, D.h_pinned, 3 * D.count * sizeof(float));
+	return 0;
+}
+
+// ------------------------------------------------------------------------------ field access
+int Engine::get_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned z, float* v)
+{
+	if (!finalized) return fail("get_field: engine not finalized");
+	if (n > 2 || x >= gn[0] || y >= gn[1] || !held(z)) return fail("get_field: position not on this engine");
+	CK(cudaSetDevice(device));
+	const float* base = is_curr ? d_I : d_V;
+	CK(cudaMemcpyAsync(v, base + n * comp + cell_off(x, y, z), sizeof(float), cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	return 0;
+}
+int Engine::set_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned z, float v)
+{
+	if (!finalized) return fail("set_field: engine not finalized");
+	if (n > 2 || x >= gn[0] || y >= gn[1] || !held(z)) return fail("set_field: position not on this engine");
+	CK(cudaSetDevice(device));
+	float* base = is_curr ? d_I : d_V;
+	CK(cudaMemcpyAsync(base + n * comp + cell_off(x, y, z), &v, sizeof(float), cudaMemcpyHostToDevice, stream));
+	CK(cudaStreamSynchronize(stream));
+	return 0;
+}
+
+int Engine::get_fields(int is_curr, float* out)
+{
+	if (!finalized) return fail("get_fields: engine not finalized");
+	CK(cudaSetDevice(device));
+	std::vector<float> h((size_t)3 * comp);
+	CK(cudaMemcpyAsync(h.data(), is_curr ? d_I : d_V, h.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	const unsigned nx = gn[0], ny = gn[1];
+#pragma omp parallel for collapse(2) schedule(static)
+	for (int n = 0; n < 3; ++n)
+		for (unsigned i = 0; i < nx; ++i)
+			for (unsigned j = 0; j < ny; ++j)
+				for (int k = 0; k < nzl; ++k)
+					out[(((size_t)n * nx + i) * ny + j) * nzl + k] = h[n * comp + (long long)k * plane + (long long)j * pitch + i];
+	return 0;
+}
+int Engine::set_fields(int is_curr, const float* in)
+{
+	if (!finalized) return fail("set_fields: engine not finalized");
+	CK(cudaSetDevice(device));
+	std::vector<float> h((size_t)3 * comp, 0.0f);
+	const unsigned nx = gn[0], ny = gn[1];
+#pragma omp parallel for collapse(2) schedule(static)
+	for (int n = 0; n < 3; ++n)
+		for (unsigned i = 0; i < nx; ++i)
+			for (unsigned j = 0; j < ny; ++j)
+				for (int k = 0; k < nzl; ++k)
+					h[n * comp + (long long)k * plane + (long long)j * pitch + i] = in[(((size_t)n * nx + i) * ny + j) * nzl + k];
+	CK(cudaMemcpyAsync(is_curr ? d_I : d_V, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+	CK(cudaStreamSynchronize(stream));
+	return 0;
+}
+
+int Engine::get_upml_flux(int box, int is_curr, float* out)
+{
+	if (!finalized) return fail("get_upml_flux: engine not finalized");
+	if (box < 0 || box >= (int)h_upml.size()) return fail("get_upml_flux: bad box");
+	CK(cudaSetDevice(device));
+	const UpmlBoxHost& B = h_upml[box];
+	const size_t full = (size_t)3 * B.n[0] * B.n[1] * B.n[2];
+	memset(out, 0, full * sizeof(float));
+	if (B.ln[2] == 0) return 0;
+	const long long cs = (long long)B.ln[0] * B.ln[1] * B.ln[2];
+	std::vector<float> h((size_t)3 * cs);
+	CK(cudaMemcpyAsync(h.data(), (is_curr ? d_flux_i : d_flux_v) + B.flux_off, h.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	for (int n = 0; n < 3; ++n)
+		for (int li = 0; li < B.ln[0]; ++li)
+			for (int lj = 0; lj < B.ln[1]; ++lj)
+				for (int lk = 0; lk < B.ln[2]; ++lk) {
+					const unsigned gk = B.gz0 + lk - B.start[2];
+					out[(((size_t)n * B.n[0] + li) * B.n[1] + lj) * B.n[2] + gk] = h[n * cs + ((long long)lk * B.ln[1] + lj) * B.ln[0] + li];
+				}
+	return 0;
+}
+
+int Engine::get_stats(oems_cuda_stats* s)
+{
+	memset(s, 0, sizeof(*s));
+	s->n_unique = n_unique;
+	s->index_bytes = index_bytes;
+	s->hbm_bytes = hbm_bytes;
+	s->kernels_launched = kernels_launched;
+	s->kernels_per_step = kernels_per_step;
+	s->pml_cells_lo = (unsigned)(pml_cells & 0xffffffffu);
+	s->pml_cells_hi = (unsigned)(pml_cells >> 32);
+	s->uses_graph = use_graph ? 1 : 0;
+	return 0;
+}
+
+int Engine::set_tuning(int rows, int zchunk, int graph_on)
+{
+	if (rows > 0) {
+		if (rows > 8) return fail("set_tuning: at most 8 rows per block (256 threads)");
+		tune_rows = rows;
+	}
+	if (zchunk > 0) tune_zchunk = zchunk;
+	if (graph_on >= 0) tune_graph = graph_on;
+	if (finalized) {
+		CK(cudaSetDevice(device));
+		CK(cudaStreamSynchronize(stream));
+		pE.zchunk = pH.zchunk = tune_zchunk;
+		build_schedule();
+	}
+	return 0;
+}
+
+// ------------------------------------------------------------------------------ multi-GPU
+struct IpcBlob {
+	cudaIpcMemHandle_t hV, hI, hFlags;
+	long long comp, plane;
+	int z0, nzl, zb, ze, pitch, ny;
+	int device;
+};
+static_assert(sizeof(IpcBlob) <= OEMS_IPC_BYTES, "IPC blob too large");
+
+int Engine::export_ipc(unsigned char* out)
+{
+	if (!finalized) return fail("export_ipc: engine not finalized");
+	CK(cudaSetDevice(device));
+	IpcBlob b;
+	memset(&b, 0, sizeof(b));
+	CK(cudaIpcGetMemHandle(&b.hV, d_V));
+	CK(cudaIpcGetMemHandle(&b.hI, d_I));
+	CK(cudaIpcGetMemHandle(&b.hFlags, d_flagE));
+	b.comp = comp; b.plane = plane; b.z0 = z0; b.nzl = nzl; b.zb = (int)zb; b.ze = (int)ze; b.pitch = pitch; b.ny = (int)gn[1];
+	b.device = device;
+	memset(out, 0, OEMS_IPC_BYTES);
+	memcpy(out, &b, sizeof(b));
+	return 0;
+}
+
+int Engine::open_peers(const unsigned char* lower, const unsigned char* upper)
+{
+	if (!finalized) return fail("open_peers: engine not finalized");
+	CK(cudaSetDevice(device));
+	CK(cudaStreamSynchronize(stream));
+	peer_lo = peer_hi = nullptr;
+	if (lower) {
+		IpcBlob b;
+		memcpy(&b, lower, sizeof(b));
+		if (b.pitch != pitch || b.ny != (int)gn[1] || b.ze != (int)zb) return fail("open_peers: lower neighbour does not match");
+		void *pV = nullptr, *pF = nullptr;
+		CK(cudaIpcOpenMemHandle(&pV, b.hV, cudaIpcMemLazyEnablePeerAccess));
+		CK(cudaIpcOpenMemHandle(&pF, b.hFlags, cudaIpcMemLazyEnablePeerAccess));
+		ipc_opened.push_back(pV); ipc_opened.push_back(pF);
+		peer_lo_V = (float*)pV;
+		peer_lo_flagE = (unsigned*)pF; // neighbour's flagE
+		peer_lo_comp = b.comp;
+		peer_lo_ghostE_off = (long long)((int)zb - b.z0) * plane;
+		peer_lo = this; // marker: has a lower neighbour
+	}
+	if (upper) {
+		IpcBlob b;
+		memcpy(&b, upper, sizeof(b));
+		if (b.pitch != pitch || b.ny != (int)gn[1] || b.zb != (int)ze) return fail("open_peers: upper neighbour does not match");
+		void *pI = nullptr, *pF = nullptr;
+		CK(cudaIpcOpenMemHandle(&pI, b.hI, cudaIpcMemLazyEnablePeerAccess));
+		CK(cudaIpcOpenMemHandle(&pF, b.hFlags, cudaIpcMemLazyEnablePeerAccess));
+		ipc_opened.push_back(pI); ipc_opened.push_back(pF);
+		peer_hi_I = (float*)pI;
+		peer_hi_flagH = (unsigned*)pF + 1; // neighbour's flagH
+		peer_hi_comp = b.comp;
+		peer_hi_ghostH_off = (long long)((int)ze - 1 - b.z0) * plane;
+		peer_hi = this;
+	}
+	peers_linked = lower || upper;
+	build_schedule();
+	return 0;
+}
+
+int Engine::link_peers(Engine* lower, Engine* upper)
+{
+	if (!finalized) return fail("link_peers: engine not finalized");
+	CK(cudaSetDevice(device));
+	CK(cudaStreamSynchronize(stream));
+	peer_lo = lower; peer_hi = upper;
+	for (Engine* o : {lower, upper}) {
+		if (!o) continue;
+		if (!o->finalized) return fail("link_peers: neighbour not finalized");
+		if (o->device != device) {
+			int can = 0;
+			CK(cudaDeviceCanAccessPeer(&can, device, o->device));
+			if (!can) return fail("link_peers: no peer access between the two GPUs");
+			cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return check(e, "cudaDeviceEnablePeerAccess");
+			cudaGetLastError();
+		}
+	}
+	if (lower) {
+		if (lower->pitch != pitch || lower->ze != zb) return fail("link_peers: lower neighbour does not match");
+		peer_lo_V = lower->d_V; peer_lo_flagE = lower->d_flagE; peer_lo_comp = lower->comp;
+		peer_lo_ghostE_off = (long long)((int)zb - lower->z0) * plane;
+	}
+	if (upper) {
+		if (upper->pitch != pitch || upper->zb != ze) return fail("link_peers: upper neighbour does not match");
+		peer_hi_I = upper->d_I; peer_hi_flagH = upper->d_flagH; peer_hi_comp = upper->comp;
+		peer_hi_ghostH_off = (long long)((int)ze - 1 - upper->z0) * plane;
+	}
+	peers_linked = lower || upper;
+	build_schedule();
+	return 0;
+}
+
+#include "abi.inc"

@@ -1,0 +1,201 @@
+// engine.h -- host-side state of one B200 FDTD engine instance (one GPU, one z-slab).
+// The C ABI in include/openems_b200.h is a thin wrapper over this class (abi.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "../../include/openems_b200.h"
+#include "kernels.cuh"
+
+struct UpmlBoxHost {
+	unsigned start[3], n[3];          // global
+	std::vector<float> c[6];          // dense aux coefficients (may be empty with a compressed operator)
+	// part of the box held by this GPU (owned planes only)
+	int ls[3], ln[3];                 // local start (x, y, LOCAL z) and lines; ln[2]==0: not on this GPU
+	unsigned gz0;                     // global z of the first held plane of the box
+	long long flux_off;
+};
+struct MurHost {
+	int ny; unsigned line, shift, n[2], start_ts;
+	std::vector<float> cP, cPP;
+};
+struct LorHost {
+	unsigned count;
+	std::vector<unsigned> pos;        // [3][count]
+	std::vector<float> c[6];          // v_int v_ext v_lor i_int i_ext i_lor, [3][count] or empty
+};
+struct RlcHost {
+	unsigned count;
+	std::vector<int> dir;
+	std::vector<unsigned> pos;
+	std::vector<float> c[9];
+};
+struct ExcHost {
+	std::vector<unsigned> idx[3], dir, delay;
+	std::vector<float> amp;
+};
+struct ProbeHost {
+	int kind; // 0 voltage, 1 current, 2 raw E, 3 raw H
+	std::vector<long long> off;
+	std::vector<signed char> sign;
+};
+struct DumpHost {
+	DumpParams p;
+	size_t count;
+	float* d_out;
+	float* h_pinned;
+	std::vector<void*> dev_allocs;
+};
+
+struct LorDev {
+	LorParams v, i;
+	bool v_on, i_on;
+};
+
+class Engine {
+public:
+	Engine(unsigned nx, unsigned ny, unsigned nz, int device);
+	~Engine();
+
+	std::string err;
+	int fail(const std::string& m) { err = m; return 1; }
+
+	int set_slab(unsigned zb, unsigned ze);
+	int set_operator_dense(const float* vv, const float* vi, const float* ii, const float* iv);
+	int set_operator_compressed(unsigned n_unique, const oems_coeff_entry* table, const void* index, int index_bytes);
+	int set_signal(const float* sv, const float* si, unsigned len, unsigned period);
+	int add_excitation(int is_curr, unsigned count, const unsigned* idx3, const unsigned* dir, const float* amp, const unsigned* delay);
+	int add_upml(const unsigned start[3], const unsigned n[3], const float* const c[6]);
+	int add_mur(int ny, unsigned line, unsigned shift, const unsigned n[2], const float* cP, const float* cPP, unsigned start_ts);
+	int add_lorentz(unsigned count, const unsigned* pos3, const float* const c[6]);
+	int add_rlc(unsigned count, const int* dir, const unsigned* pos3, const float* const c[9]);
+	int finalize();
+
+	int iterate(unsigned n);
+	int sync();
+	int reset();
+	unsigned num_ts() const { return numTS_host; }
+
+	int add_probe_voltage(const unsigned start[3], const unsigned stop[3], int* id);
+	int add_probe_current(const unsigned start[3], const unsigned stop[3], int nd, const int si[3], const int ei[3], int* id);
+	int add_probe_field(int is_H, const unsigned pos[3], int* id);
+	unsigned num_probe_values() const { return n_values; }
+	int read_probes(double* out);
+	int record_probes(unsigned interval, unsigned max_samples);
+	int read_probe_series(double* out, unsigned* ts_out, unsigned cap, unsigned* n);
+	int energy(double* e);
+	int add_dump(int is_H, int interp, unsigned nx, unsigned ny, unsigned nz, const unsigned* px, const unsigned* py,
+	             const unsigned* pz, const double* const el[3], const double* const del[3], int* id);
+	int read_dump(int id, float* out);
+	int get_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned z, float* v);
+	int set_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned z, float v);
+	int get_fields(int is_curr, float* out);
+	int set_fields(int is_curr, const float* in);
+	int get_upml_flux(int box, int is_curr, float* out);
+	int get_stats(oems_cuda_stats* s);
+	int set_tuning(int rows, int zchunk, int use_graph);
+	int export_ipc(unsigned char* out);
+	int open_peers(const unsigned char* lower, const unsigned char* upper);
+	int link_peers(Engine* lower, Engine* upper);
+
+private:
+	// geometry
+	unsigned gn[3];
+	int device;
+	unsigned zb, ze;      // owned global planes [zb, ze)
+	int z0;               // global z of local plane 0
+	int nzl;              // local planes (owned + ghosts)
+	int pitch;
+	long long plane, comp;
+	bool finalized = false, slab_set = false;
+	cudaStream_t stream = nullptr;
+
+	// host staging
+	std::vector<float> h_dense[4];    // local slab, NIJK over local planes
+	bool have_dense = false, have_compressed = false;
+	std::vector<oems_coeff_entry> h_table;
+	int index_bytes = 0;
+	std::vector<float> h_sig[2];
+	unsigned sig_len = 0, sig_period = 0;
+	ExcHost h_exc[2];
+	std::vector<UpmlBoxHost> h_upml;
+	std::vector<MurHost> h_mur;
+	std::vector<LorHost> h_lor;
+	std::vector<RlcHost> h_rlc;
+	std::vector<ProbeHost> h_probes;
+
+	// device
+	float *d_V = nullptr, *d_I = nullptr;
+	void* d_idx = nullptr;
+	float4* d_tab[10] = {nullptr}; // Evv Evi Pvv Pvvfn Pvvfo Hii Hiv Pii Piifn Piifo
+	float *d_flux_v = nullptr, *d_flux_i = nullptr;
+	long long flux_floats = 0;
+	unsigned* d_numTS = nullptr;
+	unsigned numTS_host = 0;
+	float* d_sig[2] = {nullptr, nullptr};
+	std::vector<void*> allocs; // everything else, freed in the destructor
+	uint64_t hbm_bytes = 0;
+	uint64_t pml_cells = 0;
+	unsigned n_unique = 0;
+
+	StencilParams pE{}, pH{};
+	PmlEdgeParams pEdge{};
+	bool has_pml = false;
+	MurParams pMur{};
+	ExcParams pExc[2]{};
+	std::vector<LorDev> lor_dev;
+	std::vector<RlcParams> rlc_dev;
+	// probes
+	ProbeParams pProbe{};
+	unsigned n_values = 0;
+	double* d_probe_now = nullptr;
+	double* d_series = nullptr;
+	unsigned* d_series_ts = nullptr;
+	unsigned rec_interval = 0, rec_cap = 0, rec_count = 0;
+	std::vector<unsigned> rec_ts;
+	bool probes_built = false;
+	double* d_energy = nullptr;
+	std::vector<DumpHost> dumps;
+
+	// schedule
+	int tune_rows = 8, tune_zchunk = 32, tune_graph = -1;
+	std::vector<std::function<void(cudaStream_t)>> step;
+	unsigned kernels_per_step = 0;
+	uint64_t kernels_launched = 0;
+	cudaGraph_t graph = nullptr;
+	cudaGraphExec_t graph_exec = nullptr;
+	bool use_graph = false;
+
+	// multi-GPU
+	Engine *peer_lo = nullptr, *peer_hi = nullptr;
+	float *peer_lo_V = nullptr, *peer_hi_I = nullptr; // mapped neighbour field bases
+	unsigned *peer_lo_flagE = nullptr, *peer_hi_flagH = nullptr;
+	unsigned *d_flagE = nullptr, *d_flagH = nullptr, *d_halo_cnt = nullptr, *d_halo_err = nullptr;
+	long long peer_lo_comp = 0, peer_hi_comp = 0, peer_lo_ghostE_off = 0, peer_hi_ghostH_off = 0;
+	bool peers_linked = false;
+	std::vector<void*> ipc_opened;
+
+	template <typename T> T* dalloc(size_t n, bool zero = true);
+	template <typename T> T* upload(const std::vector<T>& v);
+	int compress_dense(std::vector<uint32_t>& index32);
+	int build_tables_and_index(const std::vector<uint32_t>& index32);
+	int build_pml();
+	int build_mur();
+	int build_exc();
+	int build_lorentz();
+	int build_rlc();
+	int build_probes();
+	void build_schedule();
+	void launch_probes(double* dst);
+	bool owned(unsigned z) const { return z >= zb && z < ze; }
+	bool held(unsigned z) const { return (int)z >= z0 && (int)z < z0 + nzl; }
+	long long cell_off(unsigned x, unsigned y, unsigned z) const
+	{
+		return (long long)((int)z - z0) * plane + (long long)y * pitch + x;
+	}
+	int check(cudaError_t e, const char* what);
+};

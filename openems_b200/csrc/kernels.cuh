@@ -1,0 +1,758 @@
+// kernels.cuh -- sm_100a device kernels of the openEMS FDTD hot path.
+//
+// Arithmetic contract (parity with the reference's sse-compressed engine, bit for bit):
+// fp32, every multiply and add rounded separately (explicit __fmul_rn/__fadd_rn, and the
+// library is compiled -fmad=false), left-to-right sums exactly as written in
+// FDTD/engine.cpp:110-222, denormals flushed (-ftz=true == tools/denormal.h:19-30).
+//
+// Data layout in HBM: fields V[3][nz][ny][pitch], I[3][nz][ny][pitch], x contiguous,
+// pitch = nx rounded up to 32 floats (rows start on 128 B lines); one operator index per
+// cell idx[nz][ny][pitch] (u16 or u32) into de-duplicated float4 coefficient tables.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define OEMS_MAX_PML_BOXES 8
+#define OEMS_MAX_MUR 6
+
+struct PmlBox {
+	int s[3];       // start (x, y, local z)
+	int n[3];       // lines
+	long long off;  // offset of this box inside the flux buffer (floats); box layout [c][k][j][i]
+};
+
+struct StencilParams {
+	float* V;
+	float* I;
+	const void* idx;
+	// E step: tA = {vv0,vv1,vv2,pml flag}, tB = {vi0,vi1,vi2,0}, tP0..2 = aux vv, vvfn, vvfo
+	// H step: tA = {ii0,ii1,ii2,pml flag}, tB = {iv0,iv1,iv2,0}, tP0..2 = aux ii, iifn, iifo
+	const float4* tA;
+	const float4* tB;
+	const float4* tP0;
+	const float4* tP1;
+	const float4* tP2;
+	float* flux;
+	int nx, ny, nz;      // lines held by this GPU (nz = local planes incl. ghosts)
+	int pitch;
+	long long plane;     // pitch*ny
+	long long comp;      // plane*nz
+	int k0, k1;          // local plane range to update
+	int zchunk;
+	int nboxes;
+	PmlBox box[OEMS_MAX_PML_BOXES];
+};
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+template <typename IdxT> struct Idx4;
+template <> struct Idx4<uint16_t> {
+	__device__ __forceinline__ static void load(const void* base, long long off, unsigned e[4])
+	{
+		ushort4 v = *reinterpret_cast<const ushort4*>(reinterpret_cast<const uint16_t*>(base) + off);
+		e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
+	}
+};
+template <> struct Idx4<uint32_t> {
+	__device__ __forceinline__ static void load(const void* base, long long off, unsigned e[4])
+	{
+		uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(base) + off);
+		e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
+	}
+};
+
+__device__ __forceinline__ float comp(const float4& v, int c)
+{
+	return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
+}
+__device__ __forceinline__ void setcomp(float4& v, int c, float x)
+{
+	if (c == 0) v.x = x; else if (c == 1) v.y = x; else if (c == 2) v.z = x; else v.w = x;
+}
+
+// flux offset of cell (i,j,k) if it lies in a UPML box, -1 otherwise; cs = component stride
+__device__ __forceinline__ long long pml_flux_offset(const StencilParams& p, int i, int j, int k, long long& cs)
+{
+#pragma unroll 1
+	for (int b = 0; b < p.nboxes; ++b) {
+		const PmlBox& B = p.box[b];
+		const int li = i - B.s[0], lj = j - B.s[1], lk = k - B.s[2];
+		if ((unsigned)li < (unsigned)B.n[0] && (unsigned)lj < (unsigned)B.n[1] && (unsigned)lk < (unsigned)B.n[2]) {
+			cs = (long long)B.n[0] * B.n[1] * B.n[2];
+			return B.off + ((long long)lk * B.n[1] + lj) * B.n[0] + li;
+		}
+	}
+	return -1;
+}
+
+// One field component of one cell: plain leapfrog (engine.cpp:137-146) or, inside a UPML box,
+// the fused sequence pre-update / leapfrog / post-update of Engine_Ext_UPML
+// (engine_ext_upml.cpp:52-137 for voltages, :144-229 for currents):
+//   f  = a_vv*X - a_fo*F ;  F' = F*m_vv + m_vi*curl ;  X' = f + a_fn*F'
+__device__ __forceinline__ float leap(float X, float m_vv, float m_vi, float curl)
+{
+	return fadd(fmul(X, m_vv), fmul(m_vi, curl));
+}
+__device__ __forceinline__ float leap_pml(float X, float m_vv, float m_vi, float curl, float a_vv,
+                                          float a_fn, float a_fo, float* fluxp)
+{
+	const float F = *fluxp;
+	const float f = fsub(fmul(a_vv, X), fmul(a_fo, F));
+	const float Fn = fadd(fmul(F, m_vv), fmul(m_vi, curl));
+	*fluxp = Fn;
+	return fadd(f, fmul(a_fn, Fn));
+}
+
+// ---------------------------------------------------------------------------------------
+// E half-step: Engine::UpdateVoltages engine.cpp:110-168 (+ fused UPML hooks).
+// block = (32, rows): a warp owns 128 consecutive x cells of one row (float4 per lane) and
+// marches zchunk planes in z, carrying the k-1 plane of I0/I1 in registers; the j-1 row comes
+// through L1/L2 (it is the row the warp above just loaded), the i-1 element by warp shuffle.
+// ---------------------------------------------------------------------------------------
+template <typename IdxT, bool HAS_PML>
+__global__ void __launch_bounds__(256) k_update_E(const __grid_constant__ StencilParams p)
+{
+	const int lane = threadIdx.x;
+	const int i0 = (blockIdx.x * 32 + lane) * 4;
+	const int j = blockIdx.y * blockDim.y + threadIdx.y;
+	const int kb = p.k0 + blockIdx.z * p.zchunk;
+	const int ke = min(kb + p.zchunk, p.k1);
+	if (j >= p.ny || kb >= ke) return;
+	const bool active = i0 < p.pitch;
+	const int ic = active ? i0 : 0;
+	const int jm = j - (j > 0);
+	const long long row = (long long)j * p.pitch + ic;
+	const long long rowm = (long long)jm * p.pitch + ic;
+	const float* __restrict__ I0 = p.I;
+	const float* __restrict__ I1 = p.I + p.comp;
+	const float* __restrict__ I2 = p.I + 2 * p.comp;
+	float* V0 = p.V;
+	float* V1 = p.V + p.comp;
+	float* V2 = p.V + 2 * p.comp;
+
+	float4 i0km, i1km;
+	{
+		const int km = kb - (kb > 0);
+		const long long o = (long long)km * p.plane + row;
+		i0km = ld4(I0 + o);
+		i1km = ld4(I1 + o);
+	}
+	for (int k = kb; k < ke; ++k) {
+		const long long o = (long long)k * p.plane + row;
+		const long long om = (long long)k * p.plane + rowm;
+		unsigned e[4];
+		Idx4<IdxT>::load(p.idx, o, e);
+		const float4 i0c = ld4(I0 + o), i1c = ld4(I1 + o), i2c = ld4(I2 + o);
+		const float4 i0jm = ld4(I0 + om), i2jm = ld4(I2 + om);
+		float4 v0 = ld4(V0 + o), v1 = ld4(V1 + o), v2 = ld4(V2 + o);
+		// i-1 neighbours of I1, I2
+		float l1 = __shfl_up_sync(0xffffffffu, i1c.w, 1);
+		float l2 = __shfl_up_sync(0xffffffffu, i2c.w, 1);
+		if (lane == 0) {
+			if (ic > 0) { l1 = I1[o - 1]; l2 = I2[o - 1]; }
+			else { l1 = i1c.x; l2 = i2c.x; }
+		}
+		const float4 i1xm = make_float4(l1, i1c.x, i1c.y, i1c.z);
+		const float4 i2xm = make_float4(l2, i2c.x, i2c.y, i2c.z);
+		if (active) {
+			const bool uni = (e[0] == e[1]) & (e[1] == e[2]) & (e[2] == e[3]);
+			float4 A = __ldg(p.tA + e[0]), B = __ldg(p.tB + e[0]);
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				if (c > 0 && !uni) { A = __ldg(p.tA + e[c]); B = __ldg(p.tB + e[c]); }
+				// ((a - b) - c) + d, engine.cpp:139-144
+				const float curl0 = fadd(fsub(fsub(comp(i2c, c), comp(i2jm, c)), comp(i1c, c)), comp(i1km, c));
+				const float curl1 = fadd(fsub(fsub(comp(i0c, c), comp(i0km, c)), comp(i2c, c)), comp(i2xm, c));
+				const float curl2 = fadd(fsub(fsub(comp(i1c, c), comp(i1xm, c)), comp(i0c, c)), comp(i0jm, c));
+				if (HAS_PML && A.w != 0.0f) {
+					long long cs;
+					const long long fo = pml_flux_offset(p, ic + c, j, k, cs);
+					const float4 P0 = __ldg(p.tP0 + e[c]), P1 = __ldg(p.tP1 + e[c]), P2 = __ldg(p.tP2 + e[c]);
+					if (fo >= 0) {
+						setcomp(v0, c, leap_pml(comp(v0, c), A.x, B.x, curl0, P0.x, P1.x, P2.x, p.flux + fo));
+						setcomp(v1, c, leap_pml(comp(v1, c), A.y, B.y, curl1, P0.y, P1.y, P2.y, p.flux + fo + cs));
+						setcomp(v2, c, leap_pml(comp(v2, c), A.z, B.z, curl2, P0.z, P1.z, P2.z, p.flux + fo + 2 * cs));
+					}
+				} else {
+					setcomp(v0, c, leap(comp(v0, c), A.x, B.x, curl0));
+					setcomp(v1, c, leap(comp(v1, c), A.y, B.y, curl1));
+					setcomp(v2, c, leap(comp(v2, c), A.z, B.z, curl2));
+				}
+			}
+			st4(V0 + o, v0);
+			st4(V1 + o, v1);
+			st4(V2 + o, v2);
+		}
+		i0km = i0c;
+		i1km = i1c;
+	}
+}
+
+// ---------------------------------------------------------------------------------------
+// H half-step: Engine::UpdateCurrents engine.cpp:170-222 (+ fused UPML hooks); cells with
+// i < nx-1, j < ny-1, global k < nz-1 only.  Marches z upward carrying plane k+1 of V0/V1.
+// ---------------------------------------------------------------------------------------
+template <typename IdxT, bool HAS_PML>
+__global__ void __launch_bounds__(256) k_update_H(const __grid_constant__ StencilParams p)
+{
+	const int lane = threadIdx.x;
+	const int i0 = (blockIdx.x * 32 + lane) * 4;
+	const int j = blockIdx.y * blockDim.y + threadIdx.y;
+	const int kb = p.k0 + blockIdx.z * p.zchunk;
+	const int ke = min(kb + p.zchunk, p.k1);
+	if (j >= p.ny - 1 || kb >= ke) return;
+	const bool active = i0 < p.pitch;
+	const int ic = active ? i0 : 0;
+	const long long row = (long long)j * p.pitch + ic;
+	const long long rowp = (long long)(j + 1) * p.pitch + ic;
+	const float* __restrict__ V0 = p.V;
+	const float* __restrict__ V1 = p.V + p.comp;
+	const float* __restrict__ V2 = p.V + 2 * p.comp;
+	float* I0 = p.I;
+	float* I1 = p.I + p.comp;
+	float* I2 = p.I + 2 * p.comp;
+	const bool has_right = ic + 4 < p.pitch;
+
+	float4 v0c, v1c;
+	{
+		const long long o = (long long)kb * p.plane + row;
+		v0c = ld4(V0 + o);
+		v1c = ld4(V1 + o);
+	}
+	for (int k = kb; k < ke; ++k) {
+		const long long o = (long long)k * p.plane + row;
+		const long long op = (long long)k * p.plane + rowp;
+		const long long on = o + p.plane;
+		unsigned e[4];
+		Idx4<IdxT>::load(p.idx, o, e);
+		const float4 v2c = ld4(V2 + o);
+		const float4 v0n = ld4(V0 + on), v1n = ld4(V1 + on);
+		const float4 v0jp = ld4(V0 + op), v2jp = ld4(V2 + op);
+		float4 c0 = ld4(I0 + o), c1 = ld4(I1 + o), c2 = ld4(I2 + o);
+		float r1 = __shfl_down_sync(0xffffffffu, v1c.x, 1);
+		float r2 = __shfl_down_sync(0xffffffffu, v2c.x, 1);
+		if (lane == 31) {
+			if (has_right) { r1 = V1[o + 4]; r2 = V2[o + 4]; }
+			else { r1 = 0.0f; r2 = 0.0f; } // only reached by cells that are never written
+		}
+		const float4 v1xp = make_float4(v1c.y, v1c.z, v1c.w, r1);
+		const float4 v2xp = make_float4(v2c.y, v2c.z, v2c.w, r2);
+		if (active) {
+			const bool uni = (e[0] == e[1]) & (e[1] == e[2]) & (e[2] == e[3]);
+			float4 A = __ldg(p.tA + e[0]), B = __ldg(p.tB + e[0]);
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				if (c > 0 && !uni) { A = __ldg(p.tA + e[c]); B = __ldg(p.tB + e[c]); }
+				if (ic + c < p.nx - 1) {
+					const float curl0 = fadd(fsub(fsub(comp(v2c, c), comp(v2jp, c)), comp(v1c, c)), comp(v1n, c));
+					const float curl1 = fadd(fsub(fsub(comp(v0c, c), comp(v0n, c)), comp(v2c, c)), comp(v2xp, c));
+					const float curl2 = fadd(fsub(fsub(comp(v1c, c), comp(v1xp, c)), comp(v0c, c)), comp(v0jp, c));
+					if (HAS_PML && A.w != 0.0f) {
+						long long cs;
+						const long long fo = pml_flux_offset(p, ic + c, j, k, cs);
+						const float4 P0 = __ldg(p.tP0 + e[c]), P1 = __ldg(p.tP1 + e[c]), P2 = __ldg(p.tP2 + e[c]);
+						if (fo >= 0) {
+							setcomp(c0, c, leap_pml(comp(c0, c), A.x, B.x, curl0, P0.x, P1.x, P2.x, p.flux + fo));
+							setcomp(c1, c, leap_pml(comp(c1, c), A.y, B.y, curl1, P0.y, P1.y, P2.y, p.flux + fo + cs));
+							setcomp(c2, c, leap_pml(comp(c2, c), A.z, B.z, curl2, P0.z, P1.z, P2.z, p.flux + fo + 2 * cs));
+						}
+					} else {
+						setcomp(c0, c, leap(comp(c0, c), A.x, B.x, curl0));
+						setcomp(c1, c, leap(comp(c1, c), A.y, B.y, curl1));
+						setcomp(c2, c, leap(comp(c2, c), A.z, B.z, curl2));
+					}
+				}
+			}
+			st4(I0 + o, c0);
+			st4(I1 + o, c1);
+			st4(I2 + o, c2);
+		}
+		v0c = v0n;
+		v1c = v1n;
+	}
+}
+
+// ---------------------------------------------------------------------------------------
+// UPML cells the stencil kernels do not visit.  Engine_Ext_UPML runs its pre/post hooks on
+// EVERY cell of a box (engine_ext_upml.cpp:63-90), but UpdateCurrents skips the last line of
+// each direction (engine.cpp:179-183).  For those cells pre+post collapse to
+//   f = a_vv*I - a_fo*F ; F' = F ; I' = f + a_fn*F
+// (the flux is swapped in and straight back out).  One thread per listed cell (list built at upload).
+// ---------------------------------------------------------------------------------------
+struct PmlEdgeParams {
+	float* X;                 // I base
+	const void* idx;
+	const float4 *tP0, *tP1, *tP2;
+	float* flux;
+	const long long* cell;    // [count] cell offset (without component)
+	const long long* fluxoff; // [count] flux offset of component 0
+	const long long* fluxcs;  // [count] flux component stride of the entry's box
+	long long count;
+	long long comp;
+};
+
+template <typename IdxT>
+__global__ void k_upml_untouched_H(const __grid_constant__ PmlEdgeParams p)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= p.count) return;
+	const long long o = p.cell[t];
+	const unsigned e = reinterpret_cast<const IdxT*>(p.idx)[o];
+	const float4 P0 = __ldg(p.tP0 + e), P1 = __ldg(p.tP1 + e), P2 = __ldg(p.tP2 + e);
+	const long long cs = p.fluxcs[t], fo = p.fluxoff[t];
+	const float a_vv[3] = {P0.x, P0.y, P0.z}, a_fn[3] = {P1.x, P1.y, P1.z}, a_fo[3] = {P2.x, P2.y, P2.z};
+#pragma unroll
+	for (int n = 0; n < 3; ++n) {
+		const float F = p.flux[fo + n * cs];
+		const float X = p.X[n * p.comp + o];
+		const float f = fsub(fmul(a_vv[n], X), fmul(a_fo[n], F));
+		p.X[n * p.comp + o] = fadd(f, fmul(a_fn[n], F));
+	}
+}
+
+// ---------------------------------------------------------------------------------------
+// Mur ABC: Engine_Ext_Mur_ABC engine_ext_mur_abc.cpp:82-173, all planes in one launch.
+// ---------------------------------------------------------------------------------------
+struct MurPlane {
+	int ny, nyP, nyPP;
+	int line, shift;
+	int n0, n1;
+	unsigned start_ts;
+	long long eoff; // first entry of this plane in the concatenated arrays
+};
+struct MurParams {
+	float* V;
+	const float* cP; const float* cPP;
+	float* vP; float* vPP;
+	const unsigned char* winner; // bit0: this entry's nyP write survives, bit1: nyPP
+	const unsigned* numTS;
+	int nplanes;
+	long long total;
+	int pitch; long long plane, comp;
+	int z0, zown0, zown1;
+	MurPlane pl[OEMS_MAX_MUR];
+};
+
+__device__ __forceinline__ bool mur_locate(const MurParams& p, long long t, int& m, long long offs[2], long long offs_shift[2])
+{
+	if (t >= p.total) return false;
+	m = 0;
+	while (m + 1 < p.nplanes && t >= p.pl[m + 1].eoff) ++m;
+	const MurPlane& M = p.pl[m];
+	if (*p.numTS < M.start_ts) return false; // IsActive(), engine_ext_mur_abc.h:56
+	const long long l = t - M.eoff;
+	int pos[3], ps[3];
+	pos[M.ny] = M.line; ps[M.ny] = M.shift;
+	pos[M.nyP] = ps[M.nyP] = (int)(l / M.n1);
+	pos[M.nyPP] = ps[M.nyPP] = (int)(l % M.n1);
+	// ownership by the z of the boundary cell (slab sharding); the shift cell of a z-normal
+	// plane is one plane further in and always held (ghost or owned)
+	if (pos[2] < p.zown0 || pos[2] >= p.zown1) return false;
+	const long long c = (long long)(pos[2] - p.z0) * p.plane + (long long)pos[1] * p.pitch + pos[0];
+	const long long cs = (long long)(ps[2] - p.z0) * p.plane + (long long)ps[1] * p.pitch + ps[0];
+	offs[0] = M.nyP * p.comp + c; offs[1] = M.nyPP * p.comp + c;
+	offs_shift[0] = M.nyP * p.comp + cs; offs_shift[1] = M.nyPP * p.comp + cs;
+	return true;
+}
+
+__global__ void k_mur_pre(const __grid_constant__ MurParams p)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	int m; long long o[2], os[2];
+	if (!mur_locate(p, t, m, o, os)) return;
+	p.vP[t] = fsub(p.V[os[0]], fmul(p.cP[t], p.V[o[0]]));
+	p.vPP[t] = fsub(p.V[os[1]], fmul(p.cPP[t], p.V[o[1]]));
+}
+__global__ void k_mur_post(const __grid_constant__ MurParams p)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	int m; long long o[2], os[2];
+	if (!mur_locate(p, t, m, o, os)) return;
+	p.vP[t] = fadd(p.vP[t], fmul(p.cP[t], p.V[os[0]]));
+	p.vPP[t] = fadd(p.vPP[t], fmul(p.cPP[t], p.V[os[1]]));
+}
+__global__ void k_mur_apply(const __grid_constant__ MurParams p)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	int m; long long o[2], os[2];
+	if (!mur_locate(p, t, m, o, os)) return;
+	const unsigned char w = p.winner[t];
+	if (w & 1) p.V[o[0]] = p.vP[t];
+	if (w & 2) p.V[o[1]] = p.vPP[t];
+}
+
+// ---------------------------------------------------------------------------------------
+// Excitation: Engine_Ext_Excitation::Apply2Voltages/Apply2Current engine_ext_excitation.cpp:33-94.
+// Entries that hit the same (component, cell) are grouped at upload; one thread per group adds
+// its entries in list order, so the fp32 result equals the sequential CPU loop.
+// ---------------------------------------------------------------------------------------
+struct ExcParams {
+	float* X;
+	const long long* tgt;      // [groups] field offset incl. component
+	const unsigned* gstart;    // [groups+1]
+	const float* amp;
+	const unsigned* delay;
+	const float* sig;
+	const unsigned* numTS;
+	unsigned groups, length, period;
+};
+__global__ void k_excite(const __grid_constant__ ExcParams p)
+{
+	const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= p.groups) return;
+	const int numTS = (int)*p.numTS;
+	int per = numTS + 1;
+	if (p.period > 0) per = (int)p.period;
+	float x = p.X[p.tgt[g]];
+	for (unsigned n = p.gstart[g]; n < p.gstart[g + 1]; ++n) {
+		int pos = numTS - (int)p.delay[n];
+		pos *= (pos > 0);
+		pos %= per;
+		pos *= (pos < (int)p.length);
+		x = fadd(x, fmul(p.amp[n], p.sig[pos]));
+	}
+	p.X[p.tgt[g]] = x;
+}
+
+// ---------------------------------------------------------------------------------------
+// Lorentz / Drude / conducting sheet ADE, one dispersion order per launch:
+// pre-hooks engine_ext_lorentzmaterial.cpp:79-168, apply engine_ext_dispersive.cpp:76-127.
+// ---------------------------------------------------------------------------------------
+struct LorParams {
+	float* X;               // V or I base
+	const long long* cell;  // [count] cell offset (without component)
+	const float* c_int;     // [3][count]
+	const float* c_ext;
+	const float* c_lor;     // may be NULL
+	float* ade;             // [3][count]
+	float* lor_ade;         // [3][count] or NULL
+	unsigned count;
+	long long comp;
+};
+__global__ void k_lorentz_pre(const __grid_constant__ LorParams p)
+{
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= p.count) return;
+	const long long c = p.cell[i];
+#pragma unroll
+	for (int n = 0; n < 3; ++n) {
+		const size_t q = (size_t)n * p.count + i;
+		const float x = p.X[n * p.comp + c];
+		float a = p.ade[q];
+		if (p.c_lor) {
+			const float l = fadd(p.lor_ade[q], fmul(p.c_lor[q], a));
+			p.lor_ade[q] = l;
+			a = fmul(a, p.c_int[q]);
+			a = fadd(a, fmul(p.c_ext[q], fsub(x, l)));
+		} else {
+			a = fmul(a, p.c_int[q]);
+			a = fadd(a, fmul(p.c_ext[q], x));
+		}
+		p.ade[q] = a;
+	}
+}
+__global__ void k_lorentz_apply(const __grid_constant__ LorParams p)
+{
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= p.count) return;
+	const long long c = p.cell[i];
+#pragma unroll
+	for (int n = 0; n < 3; ++n) {
+		const size_t q = (size_t)n * p.count + i;
+		p.X[n * p.comp + c] = fsub(p.X[n * p.comp + c], p.ade[q]);
+	}
+}
+
+// ---------------------------------------------------------------------------------------
+// Lumped RLC: Engine_Ext_LumpedRLC engine_ext_lumpedRLC.cpp:83-142.  The reference rotates
+// three array pointers; here the ring position is derived from numTS.
+// ---------------------------------------------------------------------------------------
+struct RlcParams {
+	float* V;
+	const long long* tgt; // field offset incl. component
+	const float *ilv, *i2v, *vvd, *vv2, *vj1, *vj2, *ib0, *b1, *b2;
+	float* Vd;  // [3][count] ring
+	float* J;   // [3][count] ring
+	float* Il;
+	const unsigned* numTS;
+	unsigned count;
+};
+// ring slot of logical index q (0 = newest) at timestep ts: after ts+1 rotations logical 0
+// sits at physical (3 - (ts+1)%3)%3
+__device__ __forceinline__ unsigned ring(unsigned ts_plus1, unsigned q) { return (q + 3u - ts_plus1 % 3u) % 3u; }
+__global__ void k_rlc_pre(const __grid_constant__ RlcParams p)
+{
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= p.count) return;
+	const unsigned r = *p.numTS + 1; // rotation count after this call
+	const float vd1 = p.Vd[(size_t)ring(r, 1) * p.count + i];
+	p.Il[i] = fadd(p.Il[i], fmul(fmul(p.i2v[i], p.ilv[i]), vd1));
+}
+__global__ void k_rlc_apply(const __grid_constant__ RlcParams p)
+{
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= p.count) return;
+	const unsigned r = *p.numTS + 1;
+	const size_t s0 = (size_t)ring(r, 0) * p.count + i, s1 = (size_t)ring(r, 1) * p.count + i,
+	             s2 = (size_t)ring(r, 2) * p.count + i;
+	const float v = p.V[p.tgt[i]];
+	// vvd*(V - Il + vv2*Vd[2] + vj1*J[1] + vj2*J[2]), left to right
+	float t = fsub(v, p.Il[i]);
+	t = fadd(t, fmul(p.vv2[i], p.Vd[s2]));
+	t = fadd(t, fmul(p.vj1[i], p.J[s1]));
+	t = fadd(t, fmul(p.vj2[i], p.J[s2]));
+	const float vd0 = fmul(p.vvd[i], t);
+	p.Vd[s0] = vd0;
+	float jn = fmul(p.ib0[i], fsub(vd0, p.Vd[s2]));
+	jn = fsub(jn, fmul(fmul(p.b1[i], p.ib0[i]), p.J[s1]));
+	jn = fsub(jn, fmul(fmul(p.b2[i], p.ib0[i]), p.J[s2]));
+	p.J[s0] = jn;
+	p.V[p.tgt[i]] = vd0;
+}
+
+__global__ void k_tick(unsigned* numTS) { *numTS += 1; }
+
+// ---------------------------------------------------------------------------------------
+// Probes: ordered signed sums.  One warp per probe: lanes gather 32 terms at a time, then every
+// lane accumulates them in list order through shuffles, so the result equals the reference's
+// sequential loop (fp64 for voltages engine_interface_fdtd.cpp:206-232, fp32 for currents
+// processcurrent.cpp:96-171).
+// ---------------------------------------------------------------------------------------
+struct ProbeParams {
+	const float* V; const float* I;
+	const long long* term_off;   // offset incl. component
+	const signed char* term_sign;
+	const unsigned* pstart;      // [nprobes+1] term ranges
+	const unsigned* pvalue;      // [nprobes] first value slot
+	const unsigned char* pkind;  // 0 voltage fp64, 1 current fp32, 2 raw E (3 values), 3 raw H
+	double* out;                 // [nvalues] (+ slot offset by the caller)
+	unsigned nprobes;
+};
+__global__ void k_probes(const __grid_constant__ ProbeParams p)
+{
+	const unsigned pr = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+	const unsigned lane = threadIdx.x % 32;
+	if (pr >= p.nprobes) return;
+	const unsigned t0 = p.pstart[pr], t1 = p.pstart[pr + 1];
+	const unsigned kind = p.pkind[pr];
+	double* out = p.out + p.pvalue[pr];
+	if (kind >= 2) {
+		if (lane < 3 && t0 + lane < t1) {
+			const float* F = kind == 2 ? p.V : p.I;
+			out[lane] = (double)F[p.term_off[t0 + lane]];
+		}
+		return;
+	}
+	const float* F = kind == 0 ? p.V : p.I;
+	double acc64 = 0.0;
+	float acc32 = 0.0f;
+	for (unsigned base = t0; base < t1; base += 32) {
+		float v = 0.0f;
+		if (base + lane < t1) v = (float)p.term_sign[base + lane] * F[p.term_off[base + lane]];
+		const unsigned cnt = min(32u, t1 - base);
+		for (unsigned q = 0; q < cnt; ++q) {
+			const float x = __shfl_sync(0xffffffffu, v, q);
+			if (kind == 0) acc64 = __dadd_rn(acc64, (double)x);
+			else acc32 = fadd(acc32, x);
+		}
+	}
+	if (lane == 0) out[0] = kind == 0 ? acc64 : (double)acc32;
+}
+
+// ---------------------------------------------------------------------------------------
+// Energy estimate: Engine_Interface_FDTD::CalcFastEnergy engine_interface_fdtd.cpp:302-347,
+// fp32 products accumulated in fp64, warp-shuffle + block reduction, one atomic per block.
+// ---------------------------------------------------------------------------------------
+struct EnergyParams {
+	const float* V; const float* I;
+	int nx, ny;          // loop bounds are nx-1, ny-1
+	int k0, k1;          // local plane range (owned, global k < nz-1)
+	int pitch; long long plane, comp;
+	double* acc;         // [2]: sum V^2, sum I^2
+};
+__global__ void k_energy(const __grid_constant__ EnergyParams p)
+{
+	double e = 0.0, h = 0.0;
+	const long long rows = (long long)(p.k1 - p.k0) * (p.ny - 1);
+	for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y) {
+		const int k = p.k0 + (int)(r / (p.ny - 1));
+		const int j = (int)(r % (p.ny - 1));
+		const long long o = (long long)k * p.plane + (long long)j * p.pitch;
+		for (int i = threadIdx.x; i < p.nx - 1; i += blockDim.x)
+#pragma unroll
+			for (int n = 0; n < 3; ++n) {
+				const float v = p.V[n * p.comp + o + i], c = p.I[n * p.comp + o + i];
+				e += (double)fmul(v, v);
+				h += (double)fmul(c, c);
+			}
+	}
+	for (int s = 16; s > 0; s >>= 1) {
+		e += __shfl_down_sync(0xffffffffu, e, s);
+		h += __shfl_down_sync(0xffffffffu, h, s);
+	}
+	__shared__ double se[32], sh[32];
+	const int w = threadIdx.y;
+	if (threadIdx.x == 0) { se[w] = e; sh[w] = h; }
+	__syncthreads();
+	if (threadIdx.y == 0 && threadIdx.x == 0) {
+		double E = 0, H = 0;
+		for (int q = 0; q < (int)blockDim.y; ++q) { E += se[q]; H += sh[q]; }
+		atomicAdd(p.acc, E);
+		atomicAdd(p.acc + 1, H);
+	}
+}
+
+// ---------------------------------------------------------------------------------------
+// Field dump: ProcessFields::CalcField processfields.cpp:283-409 + interpolation
+// engine_interface_fdtd.cpp:63-124 (E) / :150-204 (H), evaluated in fp64 like the reference
+// and stored as fp32 in {3,nz,ny,nx} order, x fastest.
+// ---------------------------------------------------------------------------------------
+struct DumpParams {
+	const float* V; const float* I;
+	const unsigned *px, *py, *pz;
+	const double* el[3];   // primal edge length per line
+	const double* del[3];  // dual edge length per line
+	float* out;
+	int is_H, interp;
+	unsigned onx, ony, onz;
+	int nx, ny, gnz, z0;
+	int pitch; long long plane, comp;
+};
+__device__ __forceinline__ double dump_raw(const DumpParams& p, int is_H, int n, const int pos[3])
+{
+	const long long o = n * p.comp + (long long)(pos[2] - p.z0) * p.plane + (long long)pos[1] * p.pitch + pos[0];
+	const double value = is_H ? (double)p.I[o] : (double)p.V[o];
+	const double delta = is_H ? p.del[n][pos[n]] : p.el[n][pos[n]];
+	if (delta != 0.0) return __ddiv_rn(value, delta);
+	return 0.0;
+}
+__global__ void k_dump(const __grid_constant__ DumpParams p)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long cnt = (long long)p.onx * p.ony * p.onz;
+	if (t >= cnt) return;
+	const unsigned ox = (unsigned)(t % p.onx), oy = (unsigned)((t / p.onx) % p.ony), oz = (unsigned)(t / ((long long)p.onx * p.ony));
+	const int pos[3] = {(int)p.px[ox], (int)p.py[oy], (int)p.pz[oz]};
+	const int N[3] = {p.nx, p.ny, p.gnz};
+	double out[3];
+	int ip[3] = {pos[0], pos[1], pos[2]};
+	if (!p.is_H) {
+		if (p.interp == 1) {
+			for (int n = 0; n < 3; ++n) {
+				if (pos[n] == N[n] - 1) { --ip[n]; out[n] = dump_raw(p, 0, n, ip); ++ip[n]; continue; }
+				const double delta = p.el[n][ip[n]];
+				out[n] = dump_raw(p, 0, n, ip);
+				if (delta == 0) { out[n] = 0; continue; }
+				if (pos[n] == 0) continue;
+				--ip[n];
+				const double dDown = p.el[n][ip[n]];
+				const double dRel = __ddiv_rn(delta, __dadd_rn(delta, dDown));
+				out[n] = __dadd_rn(__dmul_rn(out[n], __dsub_rn(1.0, dRel)), __dmul_rn(dump_raw(p, 0, n, ip), dRel));
+				++ip[n];
+			}
+		} else if (p.interp == 2) {
+			for (int n = 0; n < 3; ++n) {
+				const int nP = (n + 1) % 3, nPP = (n + 2) % 3;
+				if (pos[0] == N[0] - 1 || pos[1] == N[1] - 1 || pos[2] == N[2] - 1) { out[n] = 0; continue; }
+				double a = dump_raw(p, 0, n, ip);
+				++ip[nP]; a = __dadd_rn(a, dump_raw(p, 0, n, ip));
+				++ip[nPP]; a = __dadd_rn(a, dump_raw(p, 0, n, ip));
+				--ip[nP]; a = __dadd_rn(a, dump_raw(p, 0, n, ip));
+				--ip[nPP];
+				out[n] = __ddiv_rn(a, 4.0);
+			}
+		} else {
+			for (int n = 0; n < 3; ++n) out[n] = dump_raw(p, 0, n, pos);
+		}
+	} else {
+		if (p.interp == 1) {
+			for (int n = 0; n < 3; ++n) {
+				const int nP = (n + 1) % 3, nPP = (n + 2) % 3;
+				if (pos[0] == N[0] - 1 || pos[1] == N[1] - 1 || pos[2] == N[2] - 1 || pos[nP] == 0 || pos[nPP] == 0) { out[n] = 0; continue; }
+				double a = dump_raw(p, 1, n, ip);
+				--ip[nP]; a = __dadd_rn(a, dump_raw(p, 1, n, ip));
+				--ip[nPP]; a = __dadd_rn(a, dump_raw(p, 1, n, ip));
+				++ip[nP]; a = __dadd_rn(a, dump_raw(p, 1, n, ip));
+				++ip[nPP];
+				out[n] = __ddiv_rn(a, 4.0);
+			}
+		} else if (p.interp == 2) {
+			for (int n = 0; n < 3; ++n) {
+				const double delta = p.del[n][ip[n]];
+				out[n] = dump_raw(p, 1, n, ip);
+				if (pos[n] >= N[n] - 1) { out[n] = 0; continue; }
+				++ip[n];
+				const double dUp = p.del[n][ip[n]];
+				const double dRel = __ddiv_rn(delta, __dadd_rn(delta, dUp));
+				out[n] = __dadd_rn(__dmul_rn(out[n], __dsub_rn(1.0, dRel)), __dmul_rn(dump_raw(p, 1, n, ip), dRel));
+				--ip[n];
+			}
+		} else {
+			for (int n = 0; n < 3; ++n) out[n] = dump_raw(p, 1, n, pos);
+		}
+	}
+	p.out[t] = (float)out[0];
+	p.out[cnt + t] = (float)out[1];
+	p.out[2 * cnt + t] = (float)out[2];
+}
+
+// ---------------------------------------------------------------------------------------
+// Multi-GPU halo: copy the two tangential components of one xy plane into the neighbour's
+// ghost plane through an NVLink peer mapping, then publish the step number in the neighbour's
+// flag.  Template: Engine_MPI::SendReceiveVoltages/Currents engine_mpi.cpp:84-182 (which
+// packs into a host buffer and MPI_Isend/Irecv's it).
+// ---------------------------------------------------------------------------------------
+struct HaloParams {
+	const float* src;       // local field base (V or I)
+	float* dst;             // peer field base (mapped)
+	long long src_plane_off, dst_plane_off; // k*plane offsets
+	long long src_comp, dst_comp;
+	long long n;            // floats per plane (pitch*ny), multiple of 4
+	unsigned* done_counter; // local scratch
+	volatile unsigned* peer_flag;
+	const unsigned* numTS;
+	unsigned flag_add;      // value published = numTS + flag_add
+};
+__global__ void k_halo_push(const __grid_constant__ HaloParams p)
+{
+	const long long n4 = p.n / 4;
+	for (int c = 0; c < 2; ++c) {
+		const float4* s = reinterpret_cast<const float4*>(p.src + c * p.src_comp + p.src_plane_off);
+		float4* d = reinterpret_cast<float4*>(p.dst + c * p.dst_comp + p.dst_plane_off);
+		for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x)
+			d[q] = s[q];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const unsigned prev = atomicAdd(p.done_counter, 1u);
+		if (prev == gridDim.x - 1) {
+			*p.done_counter = 0;
+			__threadfence_system();
+			*p.peer_flag = *p.numTS + p.flag_add;
+			__threadfence_system();
+		}
+	}
+}
+struct WaitParams {
+	volatile unsigned* flag;
+	const unsigned* numTS;
+	unsigned flag_add;
+	unsigned* error;
+	long long timeout_cycles;
+};
+__global__ void k_halo_wait(const __grid_constant__ WaitParams p)
+{
+	const unsigned want = *p.numTS + p.flag_add;
+	const long long t0 = clock64();
+	while ((int)(*p.flag - want) < 0) {
+		if (clock64() - t0 > p.timeout_cycles) { *p.error = 1; break; }
+		__nanosleep(200);
+	}
+	__threadfence_system();
+}

@@ -1,0 +1,69 @@
+"""GPU parity tests: the CUDA engine, driven through the C ABI, against the CPU oracle on the
+same operator.  Bar: bit-exact E/H fields (the reference's own cross-engine rule,
+TESTSUITE/enginetests/cavity.m:155), which implies rel-L2 0 <= 1e-5 on every probe series."""
+import numpy as np
+import pytest
+
+from oracle.pyoracle import BC_PEC, BC_PMC, BC_MUR, BC_PML
+from tests import cases
+from tests.gpu_util import operator_from_oracle, assert_fields_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(s, steps=(1, 2, 17, 80), what="", **kw):
+    op = operator_from_oracle(s)
+    eng = op.CreateEngine()
+    for k, v in kw.items():
+        if k == "tuning":
+            eng.SetTuning(*v)
+    total = 0
+    for n in steps:
+        s.iterate(n)
+        eng.IterateTS(n)
+        total += n
+        assert eng.GetNumberOfTimesteps() == s.num_ts == total
+        mv, mc = assert_fields_equal(eng, s, "%s after %d steps" % (what, total))
+    assert mv > 0 and mc > 0, "fields stayed zero: the comparison would be vacuous"
+    return eng
+
+
+def test_stencil_pec_box():
+    s = cases.uniform_box(n=(27, 11, 33), bc=(BC_PEC,) * 6)
+    run_both(s, what="PEC box")
+
+
+def test_engine_cavity_mur_pml_pmc():
+    """the reference's engine test case: BC {MUR, PML_8, PMC, PEC, PEC, PEC}, dielectric box"""
+    s = cases.engine_cavity()
+    eng = run_both(s, steps=(1, 3, 50, 446), what="enginetests/cavity")
+    for b, box in enumerate(s.upml_boxes()):
+        for w in (0, 1):
+            got = eng.GetUPMLFlux(b, w, box["n"])
+            ref = s.upml_flux(b, w)
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [(23, 26, 21), (40, 36, 44), (130, 9, 7), (5, 5, 200)])
+def test_all_pml_odd_sizes(n):
+    pml = 4 if min(n) >= 12 else 1
+    s = cases.uniform_box(n=n, bc=(BC_PML,) * 6, pml=pml)
+    run_both(s, steps=(1, 5, 60), what="all-PML %s" % (n,))
+
+
+def test_all_mur():
+    s = cases.uniform_box(n=(31, 30, 29), bc=(BC_MUR,) * 6)
+    run_both(s, steps=(1, 9, 120), what="all-Mur")
+
+
+def test_no_graph_and_small_blocks():
+    s = cases.engine_cavity()
+    run_both(s, steps=(2, 41), what="tuned", tuning=(4, 5, 0))
+
+
+def test_materials_and_metal():
+    mats = [dict(start=(0.004, 0.003, 0.005), stop=(0.012, 0.010, 0.017), epsR=4.2, mueR=1.5, kappa=0.05, sigma=10.0)]
+    metals = [dict(start=(0.015, 0.0, 0.010), stop=(0.020, 0.012, 0.010))]
+    s = cases.uniform_box(n=(30, 24, 36), bc=(BC_PML, BC_PML, BC_MUR, BC_PEC, BC_PMC, BC_PML), pml=6,
+                          materials=mats, metals=metals)
+    run_both(s, steps=(1, 30, 150), what="materials")
