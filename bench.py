@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- FDTD MCells/s of the B200 engine on BASELINE.json's headline config.
+
+Workload (config C5 of BASELINE.md): synthetic uniform Cartesian vacuum mesh 1024^3, unit 1 mm,
+PML_8 on all six faces, centre E_z soft Gauss source, 3 voltage + 3 current + 6 field probes.
+A "step" is one FDTD timestep (E half-step + H half-step + all extension hooks) over the whole
+mesh.  MCells/s = Nx*Ny*Nz*timesteps / seconds / 1e6 (openems.cpp:1485 definition).
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                   the reference algorithm on the host cores
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fdtd_mcells_per_s"
+UNIT = "MCells/s"
+PML = 8
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """samples SM clock + throttle reasons with nvidia-smi while the timed region runs"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_c5(n, with_probes=True, slab=None, device=-1):
+    """host side: build the compressed operator of the C5 mesh and create the engine"""
+    from openems_b200 import SyntheticOperator
+    from openems_b200.synthetic import BC_PML, EXC_E_SOFT
+    C0 = 299792458.0
+    nx, ny, nz = n
+    lines = tuple(np.arange(m, dtype=np.float64) for m in (nx, ny, nz))  # drawing unit mm
+    so = SyntheticOperator(*lines, 1e-3)
+    so.set_bc([BC_PML] * 6, (PML,) * 6)
+    fc = C0 / (20 * 1e-3)
+    so.set_excite_gauss(fc / 2, fc / 2)
+    c = (nx // 2, ny // 2, nz // 2)
+    so.add_excitation((c[0], c[1], c[2] + 0.5), (c[0], c[1], c[2] + 0.5), EXC_E_SOFT, (0, 0, 1))
+    t0 = time.time()
+    so.build()
+    t_build = time.time() - t0
+    return so, t_build
+
+
+def add_c5_probes(eng, n):
+    nx, ny, nz = n
+    c = (nx // 2, ny // 2, nz // 2)
+    q = (nx // 4, ny // 4, nz // 4)
+    for a in range(3):  # 3 voltage probes: 16-edge lines through the quarter point
+        stop = list(q)
+        stop[a] += 16
+        eng.AddVoltageProbe(q, stop)
+    for a in range(3):  # 3 current probes: 16x16 loops around the centre
+        start, stop = list(c), list(c)
+        for b in range(3):
+            if b != a:
+                start[b] -= 8
+                stop[b] += 8
+        eng.AddCurrentProbe(start, stop, a)
+    for k in range(3):  # 6 field probes
+        p = (q[0] + 5 * k, q[1] + 3 * k, q[2] + 7 * k)
+        eng.AddFieldProbe(0, p)
+        eng.AddFieldProbe(1, p)
+
+
+def algorithmic_bytes(n, pml_cells, index_bytes):
+    """per half-step 36 B field traffic + index per cell, + 24 B per PML cell (flux r/w)"""
+    cells = n[0] * n[1] * n[2]
+    per_half = cells * (36 + index_bytes) + pml_cells * 24
+    return per_half, 2 * per_half
+
+
+def cpu_baseline(sample_n, steps, threads):
+    """the reference algorithm restated (oracle/fdtd_oracle_sse.c: sse-compressed layout, x-slab
+    threads, one barrier per phase) on a bounded sample of the same workload"""
+    from oracle.pyoracle import OracleSim, OracleSSE, BC_PML, EXC_E_SOFT
+    C0 = 299792458.0
+    lines = tuple(np.arange(m, dtype=np.float64) for m in sample_n)
+    s = OracleSim(*lines, 1e-3)
+    s.set_bc([BC_PML] * 6, (PML,) * 6)
+    fc = C0 / (20 * 1e-3)
+    s.set_excite_gauss(fc / 2, fc / 2)
+    c = tuple(m // 2 for m in sample_n)
+    s.add_excitation((c[0], c[1], c[2] + 0.5), (c[0], c[1], c[2] + 0.5), EXC_E_SOFT, (0, 0, 1))
+    s.build()
+    eng = OracleSSE(s, threads=threads)
+    eng.iterate(3)
+    t0 = time.time()
+    eng.iterate(steps)
+    dt = time.time() - t0
+    cells = sample_n[0] * sample_n[1] * sample_n[2]
+    return cells * steps / dt / 1e6, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = tuple(args.cpu_sample)
+    # each "step" of this arm = one timestep on the bounded sample mesh
+    steps = max(1, min(args.steps, 400))
+    cpu_baseline(sample, max(1, args.warmup), threads)
+    val, dt = cpu_baseline(sample, steps, threads)
+    n = tuple(args.n)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C5 uniform vacuum %dx%dx%d PML_8x6 centre Ez Gauss source" % n,
+                   "timed_on": "bounded sample %dx%dx%d of the same workload" % sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%dx%dx%d PML_8 mesh, %d timesteps, sse-compressed multithreaded restatement "
+                                   "(oracle/fdtd_oracle_sse.c)" % (sample + (steps,))},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def run_gpu(args):
+    import torch
+    from openems_b200 import load_library
+    load_library()  # fail loudly when the CUDA library is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = tuple(args.n)
+    nz = n[2]
+    slab = None
+    if world > 1:  # strong scaling: z-slabs of the same mesh
+        base, rem = divmod(nz, world)
+        zb = rank * base + min(rank, rem)
+        ze = zb + base + (1 if rank < rem else 0)
+        slab = (zb, ze)
+
+    so, t_build = build_c5(n)
+    op = so.operator()
+
+    # ---------------- e2e leg: engine creation from HOST buffers + K timesteps with probe readback
+    def make_engine():
+        eng = op.CreateEngine(device=local_rank, slab=slab)
+        add_c5_probes(eng, n)
+        return eng
+
+    burst = max(1, so.nyquist // 4)  # Processing interval: Nyquist / OverSampling(4), openems.cpp:568
+
+    def link(eng):
+        if world == 1:
+            return
+        blob = eng.ExportIPC()
+        blobs = [None] * world
+        dist.all_gather_object(blobs, blob)
+        eng.OpenPeers(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
+        dist.barrier()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    eng = make_engine()
+    link(eng)
+    stats0 = eng.GetStats()
+    pml_cells = stats0["pml_cells"]
+    index_bytes = stats0["index_bytes"]
+
+    # ---------------- device-resident leg
+    eng.IterateTS(args.warmup)
+    eng.Synchronize()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    k0 = eng.GetStats()["kernels_launched"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    eng.IterateTS(args.steps)
+    eng.Synchronize()
+    t_dev = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.GetStats()["kernels_launched"] - k0
+    if world > 1:
+        t = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev = float(t.item())
+    cells = n[0] * n[1] * n[2]
+    value = cells * args.steps / t_dev / 1e6
+
+    # ---------------- per-kernel timing (CUDA events on the engine's stream) for the roofline
+    sched = eng.TimeSchedule(min(10, max(3, args.steps // 10)))
+    local_cells = cells if slab is None else n[0] * n[1] * (slab[1] - slab[0])
+    per_half, per_step = algorithmic_bytes((n[0], n[1], local_cells // (n[0] * n[1])), pml_cells, index_bytes)
+    peak, peak_src = measured_peak()
+    kern = {}
+    for name, ms in sched:
+        kern[name] = kern.get(name, 0.0) + ms
+    t_E, t_H = kern.get("update_E", 0.0), kern.get("update_H", 0.0)
+    dom = "update_E" if t_E >= t_H else "update_H"
+    t_dom = max(t_E, t_H)
+    achieved = per_half / (t_dom * 1e-3) / 1e9 if t_dom > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tj = json.load(f)
+            key = "%dx%dx%d" % n
+            if world == 1 and key in tj and dom in tj[key]:
+                traffic = tj[key][dom]
+    except Exception:
+        pass
+    step_ms_sched = sum(ms for _, ms in sched)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None, "traffic": traffic,
+                "algorithmic_bytes_per_launch": per_half, "kernel_ms": t_dom, "peak_source": peak_src,
+                "kernels_ms": {k: round(v, 5) for k, v in kern.items()}, "step_ms_from_events": step_ms_sched,
+                "step_frac_of_peak": (per_step / (step_ms_sched * 1e-3) / 1e9 / peak) if step_ms_sched else None}
+
+    # ---------------- e2e: new engine from host buffers, K steps in bursts, probes read to host
+    eng.close()
+    del eng
+    barrier()
+    t0 = time.perf_counter()
+    eng = make_engine()
+    link(eng)
+    t_upload = time.perf_counter() - t0
+    h2d = eng.GetStats()["hbm_bytes"] - 2 * 3 * 4 * (cells if slab is None else n[0] * n[1] * (slab[1] - slab[0] + 2))
+    h2d = max(h2d, so.n_unique * 128 + cells * index_bytes // max(world, 1))
+    done, d2h = 0, 0
+    while done < args.steps:
+        m = min(burst, args.steps - done)
+        eng.IterateTS(m)
+        vals = eng.ReadProbes()  # D2H of the probe values, synchronises
+        d2h += vals.nbytes
+        done += m
+    eng.Synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_val = cells * args.steps / t_e2e / 1e6
+    probe_sample = [float(v) for v in vals[:4]]
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C5 uniform vacuum %dx%dx%d PML_8x6 centre Ez Gauss source, 12 probes" % n,
+                       "parallelism": "z-slabs x%d over NVLink peer memory" % world if world > 1 else "single GPU",
+                       "l2": "inputs (%.1f GB of fields+index per GPU) far larger than the 126 MB L2; no flush needed"
+                             % ((24 + index_bytes) * local_cells / 1e9),
+                       "n_unique_coeff_tuples": so.n_unique, "index_bytes": index_bytes, "pml_cells": pml_cells,
+                       "host_operator_build_s": round(t_build, 2), "burst_ts": burst},
+            "roofline": roofline,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+                    "includes": "engine creation from host buffers (operator H2D %.2f s) + %d timesteps in bursts of %d with "
+                                "probe read-back" % (t_upload, args.steps, burst), "probe_sample": probe_sample},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            sample = tuple(args.cpu_sample)
+            v, dt = cpu_baseline(sample, args.cpu_steps, threads)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": "%dx%dx%d PML_8 mesh, %d timesteps in %.1f s, sse-compressed multithreaded "
+                                             "restatement of the reference engine (oracle/fdtd_oracle_sse.c)"
+                                             % (sample + (args.cpu_steps, dt))}
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, nargs=3, default=[1024, 1024, 1024], help="mesh lines (default: the 1024^3 headline config)")
+    ap.add_argument("--cpu-sample", type=int, nargs=3, default=[192, 192, 192])
+    ap.add_argument("--cpu-steps", type=int, default=60)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

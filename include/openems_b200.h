@@ -185,6 +185,13 @@ int oems_cuda_get_stats(oems_cuda_engine* h, oems_cuda_stats* out);
 /* tuning knobs (0 keeps the default): block rows and z-chunk of the stencil kernels, graph on/off */
 int oems_cuda_set_tuning(oems_cuda_engine* h, int block_rows, int z_chunk, int use_graph);
 
+/* measurement aid: runs n_ts timesteps without the graph and returns the average duration in
+   ms of every kernel of the per-timestep schedule, timed with CUDA events on the engine's own
+   stream; oems_cuda_schedule_label(i) names entry i ("update_E", "update_H", "mur_pre", ...) */
+int oems_cuda_time_schedule(oems_cuda_engine* h, unsigned n_ts, double* ms_out, unsigned capacity,
+                            unsigned* n_entries);
+const char* oems_cuda_schedule_label(oems_cuda_engine* h, unsigned i);
+
 /* ---- multi-GPU halo exchange over NVLink peer memory (one process per GPU).
    Each rank exports IPC handles of its field buffers, gathers its neighbours' with
    torch.distributed / any host channel, and opens them here; the halo planes are then written

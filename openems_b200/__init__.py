@@ -8,6 +8,7 @@ behaviour).  Nothing here computes fields on the CPU and nothing imports oracle/
 """
 from ._lib import load_library, library_path, LibraryNotBuilt  # noqa: F401
 from .engine import Engine_CUDA, Operator_CUDA, Engine_Interface_CUDA, EngineError  # noqa: F401
+from .synthetic import SyntheticOperator  # noqa: F401
 
 __all__ = ["load_library", "library_path", "LibraryNotBuilt", "Engine_CUDA", "Operator_CUDA",
-           "Engine_Interface_CUDA", "EngineError"]
+           "Engine_Interface_CUDA", "EngineError", "SyntheticOperator"]

@@ -74,6 +74,8 @@ SIGNATURES = {
     "oems_cuda_get_upml_flux": (C.c_int, [_vp, C.c_int, C.c_int, _fp]),
     "oems_cuda_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "oems_cuda_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "oems_cuda_time_schedule": (C.c_int, [_vp, C.c_uint, _dp, C.c_uint, _up]),
+    "oems_cuda_schedule_label": (C.c_char_p, [_vp, C.c_uint]),
     "oems_cuda_export_ipc": (C.c_int, [_vp, C.POINTER(C.c_ubyte)]),
     "oems_cuda_open_peers": (C.c_int, [_vp, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte)]),
     "oems_cuda_link_peers": (C.c_int, [_vp, _vp, _vp]),
@@ -86,7 +88,9 @@ SIGNATURES = {
     "oems_synth_add_material": (C.c_int, [_vp, C.c_int, C.c_double * 3, C.c_double * 3] + [C.c_double] * 4),
     "oems_synth_add_metal": (C.c_int, [_vp, C.c_int, C.c_double * 3, C.c_double * 3]),
     "oems_synth_add_excitation": (C.c_int, [_vp, C.c_int, C.c_double * 3, C.c_double * 3, C.c_int, C.c_double * 3, C.c_double]),
+    "oems_synth_add_lorentz": (C.c_int, [_vp, C.c_int, C.c_double * 3, C.c_double * 3] + [C.c_double] * 4 + [C.c_int] + [_dp] * 6),
     "oems_synth_set_excite_gauss": (None, [_vp, C.c_double, C.c_double]),
+    "oems_synth_set_excite_sinus": (None, [_vp, C.c_double]),
     "oems_synth_build": (C.c_int, [_vp, C.c_uint]),
     "oems_synth_last_error": (C.c_char_p, [_vp]),
     "oems_synth_dT": (C.c_double, [_vp]),
@@ -95,6 +99,17 @@ SIGNATURES = {
     "oems_synth_index_bytes": (C.c_int, [_vp]),
     "oems_synth_table": (_vp, [_vp]),
     "oems_synth_index": (_vp, [_vp]),
+    "oems_synth_unique_planes": (C.c_uint, [_vp]),
+    "oems_synth_signal_length": (C.c_uint, [_vp]),
+    "oems_synth_signal": (_fp, [_vp, C.c_int]),
+    "oems_synth_exc_count": (C.c_uint, [_vp, C.c_int]),
+    "oems_synth_exc_get": (None, [_vp, C.c_int, _up, _up, _fp, _up]),
+    "oems_synth_mur_count": (C.c_int, [_vp]),
+    "oems_synth_mur_coeff": (_fp, [_vp, C.c_int, C.c_int, _ip, _up, _up, C.c_uint * 2, _up]),
+    "oems_synth_upml_count": (C.c_int, [_vp]),
+    "oems_synth_upml_box": (None, [_vp, C.c_int, _u3, _u3]),
+    "oems_synth_lorentz_order": (C.c_int, [_vp]),
+    "oems_synth_lorentz_count": (C.c_uint, [_vp, C.c_int]),
     "oems_synth_upload": (C.c_int, [_vp, _vp]),
 }
 
@@ -124,7 +139,6 @@ def load_library():
             continue
         f.restype = res
         f.argtypes = args
-    missing = [m for m in missing if not m.startswith('oems_synth_')]  # TEMP until the builder lands
     if missing:
         raise LibraryNotBuilt("libopenems_b200.so lacks symbols: " + ", ".join(missing))
     if L.oems_cuda_abi_version() != 1:

@@ -245,48 +245,7 @@ int Engine::add_rlc(unsigned count, const int* dir, const unsigned* pos3, const 
 // Re-keys the operator per cell: the 12 stencil coefficients plus, inside UPML
 // boxes, the 18 auxiliary coefficients form one 128-byte tuple; equal tuples (memcmp, like
 // SSE_coeff operator_sse_compressed.cpp:197-200) share an entry.
-namespace {
-struct EntrySet {
-	std::vector<oems_coeff_entry> items;
-	std::vector<int64_t> slots;
-	size_t mask;
-	EntrySet() : slots(1 << 12, -1), mask((1 << 12) - 1) {}
-	static uint64_t hash(const oems_coeff_entry& e)
-	{
-		const uint64_t* w = reinterpret_cast<const uint64_t*>(&e);
-		uint64_t h = 0x9E3779B97F4A7C15ull;
-		for (size_t i = 0; i < sizeof(oems_coeff_entry) / 8; ++i) {
-			h ^= w[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-			h *= 0xff51afd7ed558ccdull;
-		}
-		return h ^ (h >> 29);
-	}
-	void grow()
-	{
-		std::vector<int64_t> ns(slots.size() * 4, -1);
-		const size_t nm = ns.size() - 1;
-		for (size_t u = 0; u < items.size(); ++u) {
-			size_t s = hash(items[u]) & nm;
-			while (ns[s] >= 0) s = (s + 1) & nm;
-			ns[s] = (int64_t)u;
-		}
-		slots.swap(ns);
-		mask = nm;
-	}
-	uint32_t insert(const oems_coeff_entry& e)
-	{
-		size_t s = hash(e) & mask;
-		while (slots[s] >= 0) {
-			if (memcmp(&items[slots[s]], &e, sizeof(e)) == 0) return (uint32_t)slots[s];
-			s = (s + 1) & mask;
-		}
-		slots[s] = (int64_t)items.size();
-		items.push_back(e);
-		if (items.size() * 2 > slots.size()) grow();
-		return (uint32_t)(items.size() - 1);
-	}
-};
-} // namespace
+#include "entry_set.h"
 
 int Engine::compress_dense(std::vector<uint32_t>& index32)
 {
@@ -701,6 +660,7 @@ template <typename K, typename P> static void launch1d(K kern, const P& p, long 
 void Engine::build_schedule()
 {
 	step.clear();
+	labels.clear();
 	const bool i16 = index_bytes == 2;
 	const dim3 block(32, tune_rows);
 	auto stencil_grid = [&](const StencilParams& p, int rows_total) {
@@ -711,73 +671,73 @@ void Engine::build_schedule()
 
 	// ---- pre-voltage hooks, reverse priority order (engine.cpp:224-230):
 	//      Mur, Lorentz, RLC  (UPML pre is fused into the E kernel; Excitation has no pre hook)
-	if (pMur.nplanes) step.push_back([this](cudaStream_t s) { launch1d(k_mur_pre, pMur, pMur.total, s); });
+	if (pMur.nplanes) (labels.push_back("mur_pre"), step.push_back([this](cudaStream_t s) { launch1d(k_mur_pre, pMur, pMur.total, s); }));
 	// list order: [.., RLC, CondSheet, Lorentz, Mur, Excitation]; pre-hooks walk it
 	// back to front: Mur, Lorentz, RLC
 	for (size_t o = 0; o < lor_dev.size(); ++o)
-		if (lor_dev[o].v_on) step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_pre, lor_dev[o].v, lor_dev[o].v.count, s); });
+		if (lor_dev[o].v_on) (labels.push_back("lorentz_pre_V"), step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_pre, lor_dev[o].v, lor_dev[o].v.count, s); }));
 	for (size_t r = 0; r < rlc_dev.size(); ++r)
-		step.push_back([this, r](cudaStream_t s) { launch1d(k_rlc_pre, rlc_dev[r], rlc_dev[r].count, s); });
+		(labels.push_back("rlc_pre"), step.push_back([this, r](cudaStream_t s) { launch1d(k_rlc_pre, rlc_dev[r], rlc_dev[r].count, s); }));
 	// ---- multi-GPU: the ghost H plane of this step must have arrived
 	if (multi && peer_lo)
-		step.push_back([this](cudaStream_t s) {
+		(labels.push_back("halo_wait_H"), step.push_back([this](cudaStream_t s) {
 			WaitParams w{d_flagH, d_numTS, 0u, d_halo_err, 4000000000ll};
 			k_halo_wait<<<1, 1, 0, s>>>(w);
-		});
+		}));
 	// ---- E half-step with fused UPML
 	if (pE.k1 > pE.k0)
-		step.push_back([this, i16, block, stencil_grid](cudaStream_t s) {
+		(labels.push_back("update_E"), step.push_back([this, i16, block, stencil_grid](cudaStream_t s) {
 			const dim3 g = stencil_grid(pE, pE.ny);
 			if (i16) { if (has_pml) k_update_E<uint16_t, true><<<g, block, 0, s>>>(pE); else k_update_E<uint16_t, false><<<g, block, 0, s>>>(pE); }
 			else { if (has_pml) k_update_E<uint32_t, true><<<g, block, 0, s>>>(pE); else k_update_E<uint32_t, false><<<g, block, 0, s>>>(pE); }
-		});
+		}));
 	// ---- post-voltage hooks (UPML fused), then Mur post
-	if (pMur.nplanes) step.push_back([this](cudaStream_t s) { launch1d(k_mur_post, pMur, pMur.total, s); });
+	if (pMur.nplanes) (labels.push_back("mur_post"), step.push_back([this](cudaStream_t s) { launch1d(k_mur_post, pMur, pMur.total, s); }));
 	// ---- apply-voltage hooks in list order: RLC, Lorentz, Mur, Excitation
 	for (size_t r = rlc_dev.size(); r-- > 0;) // same priority: reversed insertion order
-		step.push_back([this, r](cudaStream_t s) { launch1d(k_rlc_apply, rlc_dev[r], rlc_dev[r].count, s); });
+		(labels.push_back("rlc_apply"), step.push_back([this, r](cudaStream_t s) { launch1d(k_rlc_apply, rlc_dev[r], rlc_dev[r].count, s); }));
 	for (size_t o = 0; o < lor_dev.size(); ++o)
-		if (lor_dev[o].v_on) step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_apply, lor_dev[o].v, lor_dev[o].v.count, s); });
-	if (pMur.nplanes) step.push_back([this](cudaStream_t s) { launch1d(k_mur_apply, pMur, pMur.total, s); });
-	if (pExc[0].groups) step.push_back([this](cudaStream_t s) { launch1d(k_excite, pExc[0], pExc[0].groups, s); });
+		if (lor_dev[o].v_on) (labels.push_back("lorentz_apply_V"), step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_apply, lor_dev[o].v, lor_dev[o].v.count, s); }));
+	if (pMur.nplanes) (labels.push_back("mur_apply"), step.push_back([this](cudaStream_t s) { launch1d(k_mur_apply, pMur, pMur.total, s); }));
+	if (pExc[0].groups) (labels.push_back("excite_V"), step.push_back([this](cudaStream_t s) { launch1d(k_excite, pExc[0], pExc[0].groups, s); }));
 	// ---- multi-GPU: tangential E of my lowest owned plane -> lower neighbour's ghost plane
 	if (multi && peer_lo)
-		step.push_back([this](cudaStream_t s) {
+		(labels.push_back("halo_push_E"), step.push_back([this](cudaStream_t s) {
 			HaloParams h{d_V, peer_lo_V, (long long)((int)zb - z0) * plane, peer_lo_ghostE_off, comp, peer_lo_comp, plane,
 			             d_halo_cnt, peer_lo_flagE, d_numTS, 1u};
 			k_halo_push<<<64, 256, 0, s>>>(h);
-		});
+		}));
 	// ---- pre-current hooks: Lorentz (UPML fused)
 	for (size_t o = 0; o < lor_dev.size(); ++o)
-		if (lor_dev[o].i_on) step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_pre, lor_dev[o].i, lor_dev[o].i.count, s); });
+		if (lor_dev[o].i_on) (labels.push_back("lorentz_pre_I"), step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_pre, lor_dev[o].i, lor_dev[o].i.count, s); }));
 	if (multi && peer_hi)
-		step.push_back([this](cudaStream_t s) {
+		(labels.push_back("halo_wait_E"), step.push_back([this](cudaStream_t s) {
 			WaitParams w{d_flagE, d_numTS, 1u, d_halo_err, 4000000000ll};
 			k_halo_wait<<<1, 1, 0, s>>>(w);
-		});
+		}));
 	// ---- H half-step with fused UPML, then the UPML cells the stencil never visits
 	if (pH.k1 > pH.k0)
-		step.push_back([this, i16, block, stencil_grid](cudaStream_t s) {
+		(labels.push_back("update_H"), step.push_back([this, i16, block, stencil_grid](cudaStream_t s) {
 			const dim3 g = stencil_grid(pH, pH.ny - 1);
 			if (i16) { if (has_pml) k_update_H<uint16_t, true><<<g, block, 0, s>>>(pH); else k_update_H<uint16_t, false><<<g, block, 0, s>>>(pH); }
 			else { if (has_pml) k_update_H<uint32_t, true><<<g, block, 0, s>>>(pH); else k_update_H<uint32_t, false><<<g, block, 0, s>>>(pH); }
-		});
+		}));
 	if (pEdge.count)
-		step.push_back([this, i16](cudaStream_t s) {
+		(labels.push_back("upml_untouched_H"), step.push_back([this, i16](cudaStream_t s) {
 			if (i16) launch1d(k_upml_untouched_H<uint16_t>, pEdge, pEdge.count, s);
 			else launch1d(k_upml_untouched_H<uint32_t>, pEdge, pEdge.count, s);
-		});
+		}));
 	// ---- apply-current hooks: Lorentz, Excitation
 	for (size_t o = 0; o < lor_dev.size(); ++o)
-		if (lor_dev[o].i_on) step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_apply, lor_dev[o].i, lor_dev[o].i.count, s); });
-	if (pExc[1].groups) step.push_back([this](cudaStream_t s) { launch1d(k_excite, pExc[1], pExc[1].groups, s); });
+		if (lor_dev[o].i_on) (labels.push_back("lorentz_apply_I"), step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_apply, lor_dev[o].i, lor_dev[o].i.count, s); }));
+	if (pExc[1].groups) (labels.push_back("excite_I"), step.push_back([this](cudaStream_t s) { launch1d(k_excite, pExc[1], pExc[1].groups, s); }));
 	if (multi && peer_hi)
-		step.push_back([this](cudaStream_t s) {
+		(labels.push_back("halo_push_H"), step.push_back([this](cudaStream_t s) {
 			HaloParams h{d_I, peer_hi_I, (long long)((int)ze - 1 - z0) * plane, peer_hi_ghostH_off, comp, peer_hi_comp, plane,
 			             d_halo_cnt + 1, peer_hi_flagH, d_numTS, 1u};
 			k_halo_push<<<64, 256, 0, s>>>(h);
-		});
-	step.push_back([this](cudaStream_t s) { k_tick<<<1, 1, 0, s>>>(d_numTS); });
+		}));
+	(labels.push_back("tick"), step.push_back([this](cudaStream_t s) { k_tick<<<1, 1, 0, s>>>(d_numTS); }));
 	kernels_per_step = (unsigned)step.size();
 
 	// ---- capture one timestep into a CUDA graph (launch-bound small meshes)
@@ -1210,6 +1170,39 @@ int Engine::set_tuning(int rows, int zchunk, int graph_on)
 		pE.zchunk = pH.zchunk = tune_zchunk;
 		build_schedule();
 	}
+	return 0;
+}
+
+
+// times every entry of the per-timestep schedule with CUDA events on the launch stream
+// (bench.py roofline: the kernels run on this engine's own stream, which torch events do not see)
+int Engine::time_schedule(unsigned n_ts, double* ms_out, unsigned cap, unsigned* n_entries)
+{
+	if (!finalized) return fail("time_schedule: engine not finalized");
+	CK(cudaSetDevice(device));
+	const size_t ne = step.size();
+	if (n_entries) *n_entries = (unsigned)ne;
+	if (cap < ne) return fail("time_schedule: output too small");
+	std::vector<cudaEvent_t> ev(ne + 1);
+	for (auto& e : ev) CK(cudaEventCreate(&e));
+	std::vector<double> acc(ne, 0.0);
+	for (unsigned it = 0; it < n_ts; ++it) {
+		for (size_t q = 0; q < ne; ++q) {
+			CK(cudaEventRecord(ev[q], stream));
+			step[q](stream);
+		}
+		CK(cudaEventRecord(ev[ne], stream));
+		CK(cudaStreamSynchronize(stream));
+		for (size_t q = 0; q < ne; ++q) {
+			float ms = 0;
+			CK(cudaEventElapsedTime(&ms, ev[q], ev[q + 1]));
+			acc[q] += ms;
+		}
+		kernels_launched += kernels_per_step;
+		++numTS_host;
+	}
+	for (auto& e : ev) cudaEventDestroy(e);
+	for (size_t q = 0; q < ne; ++q) ms_out[q] = n_ts ? acc[q] / n_ts : 0.0;
 	return 0;
 }
 

@@ -98,6 +98,8 @@ public:
 	int get_upml_flux(int box, int is_curr, float* out);
 	int get_stats(oems_cuda_stats* s);
 	int set_tuning(int rows, int zchunk, int use_graph);
+	int time_schedule(unsigned n_ts, double* ms_out, unsigned cap, unsigned* n_entries);
+	const char* schedule_label(unsigned i) const { return i < labels.size() ? labels[i].c_str() : ""; }
 	int export_ipc(unsigned char* out);
 	int open_peers(const unsigned char* lower, const unsigned char* upper);
 	int link_peers(Engine* lower, Engine* upper);
@@ -164,6 +166,7 @@ private:
 	// schedule
 	int tune_rows = 8, tune_zchunk = 32, tune_graph = -1;
 	std::vector<std::function<void(cudaStream_t)>> step;
+	std::vector<std::string> labels;
 	unsigned kernels_per_step = 0;
 	uint64_t kernels_launched = 0;
 	cudaGraph_t graph = nullptr;

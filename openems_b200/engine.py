@@ -350,6 +350,13 @@ class Engine_CUDA:
     def SetTuning(self, block_rows=0, z_chunk=0, use_graph=-1):
         self._ck(self._L.oems_cuda_set_tuning(self._h, block_rows, z_chunk, use_graph))
 
+    def TimeSchedule(self, n_ts):
+        """average ms of every kernel of the per-timestep schedule (CUDA events on the engine stream)"""
+        ms = np.zeros(64, np.float64)
+        n = C.c_uint()
+        self._ck(self._L.oems_cuda_time_schedule(self._h, int(n_ts), _ptr(ms, _dp), 64, C.byref(n)))
+        return [((self._L.oems_cuda_schedule_label(self._h, i) or b"").decode(), float(ms[i])) for i in range(n.value)]
+
     # ---- multi-GPU
     def ExportIPC(self):
         buf = (C.c_ubyte * _lib.OEMS_IPC_BYTES)()
