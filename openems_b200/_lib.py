@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_PATH = os.path.join(_HERE, "lib", "libopenems_b200.so")
+_PATH = os.environ.get("OPENEMS_B200_LIB") or os.path.join(_HERE, "lib", "libopenems_b200.so")
 
 OEMS_IPC_BYTES = 256
 

@@ -27,13 +27,25 @@ def needs_build():
     return any(os.path.exists(f) and os.path.getmtime(f) > t for f in files)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: tuning variants for sweeps (tools/sweep.py); the product build uses neither"""
+    global OUT
+    if out is not None:
+        saved, OUT = OUT, out
+        try:
+            return _build(True, verbose, defines)
+        finally:
+            OUT = saved
     if not force and not needs_build():
         return OUT
+    return _build(force, verbose, defines)
+
+
+def _build(force, verbose, defines):
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(SRC, s) for s in SOURCES if os.path.exists(os.path.join(SRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else [])
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]
     cmd += ["-I", os.path.join(HERE, "..", "include"), "-o", OUT] + srcs

@@ -120,20 +120,39 @@ int Engine::set_operator_compressed(unsigned nu, const oems_coeff_entry* table, 
 	allocs.push_back(p);
 	hbm_bytes += cells * ib;
 	d_idx = p;
-	if (ib == 2) {
-		std::vector<uint16_t> fill(pitch, (uint16_t)nu);
-		for (long long r = 0; r < (long long)gn[1] * nzl; ++r)
-			CK(cudaMemcpyAsync((uint16_t*)p + r * pitch, fill.data(), pitch * 2, cudaMemcpyHostToDevice, stream));
-	} else {
-		std::vector<uint32_t> fill(pitch, nu);
-		for (long long r = 0; r < (long long)gn[1] * nzl; ++r)
-			CK(cudaMemcpyAsync((uint32_t*)p + r * pitch, fill.data(), pitch * 4, cudaMemcpyHostToDevice, stream));
+	{
+		const long long rows = (long long)gn[1] * nzl;
+		const long long padn = rows * (pitch - (int)gn[0]);
+		if (padn > 0) {
+			const unsigned blocks = (unsigned)((padn + 255) / 256);
+			if (ib == 2) k_fill_index_padding<uint16_t><<<blocks, 256, 0, stream>>>((uint16_t*)p, rows, (int)gn[0], pitch, (uint16_t)nu);
+			else k_fill_index_padding<uint32_t><<<blocks, 256, 0, stream>>>((uint32_t*)p, rows, (int)gn[0], pitch, (uint32_t)nu);
+		}
 	}
-	CK(cudaStreamSynchronize(stream));
 	const char* src = (const char*)index + (size_t)z0 * gn[1] * gn[0] * ib;
-	CK(cudaMemcpy2DAsync(p, (size_t)pitch * ib, src, (size_t)gn[0] * ib, (size_t)gn[0] * ib, (size_t)gn[1] * nzl,
-	                     cudaMemcpyHostToDevice, stream));
-	CK(cudaStreamSynchronize(stream));
+	{
+		// double-buffered pinned staging: the caller's buffer is pageable, a direct copy would run
+		// at a fraction of the PCIe rate
+		const size_t row_bytes = (size_t)gn[0] * ib, total_rows = (size_t)gn[1] * nzl;
+		const size_t chunk_rows = std::max<size_t>(1, (size_t)(64u << 20) / row_bytes);
+		void* stage[2] = {nullptr, nullptr};
+		cudaEvent_t done[2];
+		for (int q = 0; q < 2; ++q) {
+			CK(cudaMallocHost(&stage[q], chunk_rows * row_bytes));
+			CK(cudaEventCreateWithFlags(&done[q], cudaEventDisableTiming));
+		}
+		int q = 0;
+		for (size_t r = 0; r < total_rows; r += chunk_rows, q ^= 1) {
+			const size_t nr = std::min(chunk_rows, total_rows - r);
+			CK(cudaEventSynchronize(done[q]));
+			memcpy(stage[q], src + r * row_bytes, nr * row_bytes);
+			CK(cudaMemcpy2DAsync((char*)p + r * (size_t)pitch * ib, (size_t)pitch * ib, stage[q], row_bytes, row_bytes, nr,
+			                     cudaMemcpyHostToDevice, stream));
+			CK(cudaEventRecord(done[q], stream));
+		}
+		CK(cudaStreamSynchronize(stream));
+		for (int k = 0; k < 2; ++k) { cudaFreeHost(stage[k]); cudaEventDestroy(done[k]); }
+	}
 	have_compressed = true;
 	have_dense = false;
 	return 0;

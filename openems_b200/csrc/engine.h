@@ -164,7 +164,7 @@ private:
 	std::vector<DumpHost> dumps;
 
 	// schedule
-	int tune_rows = 8, tune_zchunk = 32, tune_graph = -1;
+	int tune_rows = 4, tune_zchunk = 32, tune_graph = -1;
 	std::vector<std::function<void(cudaStream_t)>> step;
 	std::vector<std::string> labels;
 	unsigned kernels_per_step = 0;

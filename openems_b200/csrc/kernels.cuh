@@ -13,6 +13,16 @@
 #include <stdint.h>
 
 #define OEMS_MAX_PML_BOXES 8
+// tuning macros (overridable from the nvcc command line for sweeps)
+#ifndef OEMS_MIN_BLOCKS
+#define OEMS_MIN_BLOCKS 4
+#endif
+#ifndef OEMS_PREFETCH_DIST
+#define OEMS_PREFETCH_DIST 1   // planes ahead that are pulled into L2 (0 = off); 1 measured best (profiles/)
+#endif
+#ifndef OEMS_PREFETCH_LANES
+#define OEMS_PREFETCH_LANES 7  // lane mask: (lane & mask)==0 issues the prefetch of its 128 B line
+#endif
 #define OEMS_MAX_MUR 6
 
 struct PmlBox {
@@ -49,6 +59,16 @@ __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b)
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+// streaming variants for data touched once per half-step (the field being updated)
+#ifdef OEMS_STREAM_RW
+__device__ __forceinline__ float4 ld4s(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4s(float* p, const float4& v) { __stcs(reinterpret_cast<float4*>(p), v); }
+#else
+__device__ __forceinline__ float4 ld4s(const float* p) { return ld4(p); }
+__device__ __forceinline__ void st4s(float* p, const float4& v) { st4(p, v); }
+#endif
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <typename IdxT> struct Idx4;
 template <> struct Idx4<uint16_t> {
@@ -115,7 +135,7 @@ __device__ __forceinline__ float leap_pml(float X, float m_vv, float m_vi, float
 // through L1/L2 (it is the row the warp above just loaded), the i-1 element by warp shuffle.
 // ---------------------------------------------------------------------------------------
 template <typename IdxT, bool HAS_PML>
-__global__ void __launch_bounds__(256) k_update_E(const __grid_constant__ StencilParams p)
+__global__ void __launch_bounds__(256, OEMS_MIN_BLOCKS) k_update_E(const __grid_constant__ StencilParams p)
 {
 	const int lane = threadIdx.x;
 	const int i0 = (blockIdx.x * 32 + lane) * 4;
@@ -147,9 +167,17 @@ __global__ void __launch_bounds__(256) k_update_E(const __grid_constant__ Stenci
 		const long long om = (long long)k * p.plane + rowm;
 		unsigned e[4];
 		Idx4<IdxT>::load(p.idx, o, e);
+#if OEMS_PREFETCH_DIST > 0
+		if (k + OEMS_PREFETCH_DIST < ke && (lane & OEMS_PREFETCH_LANES) == 0) {
+			const long long of = o + (long long)OEMS_PREFETCH_DIST * p.plane;
+			prefetch_l2(I0 + of); prefetch_l2(I1 + of); prefetch_l2(I2 + of);
+			prefetch_l2(V0 + of); prefetch_l2(V1 + of); prefetch_l2(V2 + of);
+			if ((lane & 15) == 0) prefetch_l2(reinterpret_cast<const IdxT*>(p.idx) + of);
+		}
+#endif
 		const float4 i0c = ld4(I0 + o), i1c = ld4(I1 + o), i2c = ld4(I2 + o);
 		const float4 i0jm = ld4(I0 + om), i2jm = ld4(I2 + om);
-		float4 v0 = ld4(V0 + o), v1 = ld4(V1 + o), v2 = ld4(V2 + o);
+		float4 v0 = ld4s(V0 + o), v1 = ld4s(V1 + o), v2 = ld4s(V2 + o);
 		// i-1 neighbours of I1, I2
 		float l1 = __shfl_up_sync(0xffffffffu, i1c.w, 1);
 		float l2 = __shfl_up_sync(0xffffffffu, i2c.w, 1);
@@ -184,9 +212,9 @@ __global__ void __launch_bounds__(256) k_update_E(const __grid_constant__ Stenci
 					setcomp(v2, c, leap(comp(v2, c), A.z, B.z, curl2));
 				}
 			}
-			st4(V0 + o, v0);
-			st4(V1 + o, v1);
-			st4(V2 + o, v2);
+			st4s(V0 + o, v0);
+			st4s(V1 + o, v1);
+			st4s(V2 + o, v2);
 		}
 		i0km = i0c;
 		i1km = i1c;
@@ -198,7 +226,7 @@ __global__ void __launch_bounds__(256) k_update_E(const __grid_constant__ Stenci
 // i < nx-1, j < ny-1, global k < nz-1 only.  Marches z upward carrying plane k+1 of V0/V1.
 // ---------------------------------------------------------------------------------------
 template <typename IdxT, bool HAS_PML>
-__global__ void __launch_bounds__(256) k_update_H(const __grid_constant__ StencilParams p)
+__global__ void __launch_bounds__(256, OEMS_MIN_BLOCKS) k_update_H(const __grid_constant__ StencilParams p)
 {
 	const int lane = threadIdx.x;
 	const int i0 = (blockIdx.x * 32 + lane) * 4;
@@ -230,10 +258,18 @@ __global__ void __launch_bounds__(256) k_update_H(const __grid_constant__ Stenci
 		const long long on = o + p.plane;
 		unsigned e[4];
 		Idx4<IdxT>::load(p.idx, o, e);
+#if OEMS_PREFETCH_DIST > 0
+		if (k + OEMS_PREFETCH_DIST < ke && (lane & OEMS_PREFETCH_LANES) == 0) {
+			const long long of = on + (long long)OEMS_PREFETCH_DIST * p.plane;
+			prefetch_l2(V0 + of); prefetch_l2(V1 + of); prefetch_l2(V2 + of - p.plane);
+			prefetch_l2(I0 + of - p.plane); prefetch_l2(I1 + of - p.plane); prefetch_l2(I2 + of - p.plane);
+			if ((lane & 15) == 0) prefetch_l2(reinterpret_cast<const IdxT*>(p.idx) + of - p.plane);
+		}
+#endif
 		const float4 v2c = ld4(V2 + o);
 		const float4 v0n = ld4(V0 + on), v1n = ld4(V1 + on);
 		const float4 v0jp = ld4(V0 + op), v2jp = ld4(V2 + op);
-		float4 c0 = ld4(I0 + o), c1 = ld4(I1 + o), c2 = ld4(I2 + o);
+		float4 c0 = ld4s(I0 + o), c1 = ld4s(I1 + o), c2 = ld4s(I2 + o);
 		float r1 = __shfl_down_sync(0xffffffffu, v1c.x, 1);
 		float r2 = __shfl_down_sync(0xffffffffu, v2c.x, 1);
 		if (lane == 31) {
@@ -268,9 +304,9 @@ __global__ void __launch_bounds__(256) k_update_H(const __grid_constant__ Stenci
 					}
 				}
 			}
-			st4(I0 + o, c0);
-			st4(I1 + o, c1);
-			st4(I2 + o, c2);
+			st4s(I0 + o, c0);
+			st4s(I1 + o, c1);
+			st4s(I2 + o, c2);
 		}
 		v0c = v0n;
 		v1c = v1n;
@@ -516,6 +552,16 @@ __global__ void k_rlc_apply(const __grid_constant__ RlcParams p)
 }
 
 __global__ void k_tick(unsigned* numTS) { *numTS += 1; }
+
+// upload helper: operator index of the padding cells (i >= nx) points at the all-zero entry
+template <typename IdxT>
+__global__ void k_fill_index_padding(IdxT* idx, long long rows, int nx, int pitch, IdxT value)
+{
+	const int pad = pitch - nx;
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (pad <= 0 || t >= rows * pad) return;
+	idx[(t / pad) * pitch + nx + (int)(t % pad)] = value;
+}
 
 // ---------------------------------------------------------------------------------------
 // Probes: ordered signed sums.  One warp per probe: lanes gather 32 terms at a time, then every

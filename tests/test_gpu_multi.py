@@ -1,0 +1,56 @@
+"""z-slab engines with halo exchange through peer memory, against the single-domain oracle.
+Runs with several slabs on ONE GPU (always) and across two GPUs when the box has them."""
+import numpy as np
+import pytest
+
+from oracle.pyoracle import BC_PEC, BC_PMC, BC_MUR, BC_PML
+from tests import cases
+from tests.gpu_util import operator_from_oracle
+from openems_b200.slabs import slab_range, held_range, link_engines_in_process
+
+pytestmark = pytest.mark.gpu
+
+
+def run_slabs(s, bounds, devices, steps=(1, 2, 40), probes=False):
+    op = operator_from_oracle(s)
+    nz = s.N[2]
+    engines = [op.CreateEngine(device=devices[r], slab=(bounds[r], bounds[r + 1])) for r in range(len(bounds) - 1)]
+    link_engines_in_process(engines)
+    total = 0
+    for n in steps:
+        s.iterate(n)
+        for _ in range(n):
+            for e in engines:
+                e.IterateTS(1)
+        total += n
+        for e in engines:
+            e.Synchronize()
+        for w, ref in ((0, s.volt), (1, s.curr)):
+            got = np.zeros_like(ref)
+            for r, e in enumerate(engines):
+                zb, ze = bounds[r], bounds[r + 1]
+                h0, h1 = held_range(nz, zb, ze)
+                f = e.GetFields(w)
+                got[..., zb:ze] = f[..., zb - h0: ze - h0]
+            bad = int((got.view(np.uint32) != ref.view(np.uint32)).sum())
+            assert bad == 0, "%d values differ after %d steps (field %d)" % (bad, total, w)
+    assert np.abs(s.volt).max() > 0
+    return engines
+
+
+def test_two_slabs_one_gpu_pml():
+    s = cases.uniform_box(n=(24, 20, 36), bc=(BC_PML,) * 6, pml=5)
+    run_slabs(s, [0, 18, 36], [0, 0])
+
+
+def test_three_uneven_slabs_one_gpu_mixed_bc():
+    s = cases.engine_cavity()
+    run_slabs(s, [0, 9, 20, 33], [0, 0, 0], steps=(1, 3, 60))
+
+
+def test_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = cases.uniform_box(n=(40, 36, 44), bc=(BC_PML,) * 6, pml=8)
+    run_slabs(s, [0, 22, 44], [0, 1], steps=(1, 5, 80))

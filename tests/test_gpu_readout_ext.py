@@ -1,0 +1,205 @@
+"""GPU parity: probes, energy, dumps, Lorentz/Drude, lumped RLC, the compressed-operator path
+and the slow per-cell accessors, all through the C ABI against the oracle."""
+import numpy as np
+import pytest
+
+from oracle.pyoracle import OracleSim, BC_PEC, BC_PMC, BC_MUR, BC_PML, EXC_E_SOFT
+from tests import cases
+from tests.gpu_util import operator_from_oracle, assert_fields_equal
+from openems_b200 import SyntheticOperator, Engine_Interface_CUDA, EngineError, Operator_CUDA
+
+pytestmark = pytest.mark.gpu
+C0 = 299792458.0
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    d = np.sqrt(((a - b) ** 2).sum())
+    n = np.sqrt((b ** 2).sum())
+    return d / n if n else d
+
+
+def test_probe_series_voltage_current_field_energy():
+    """port voltage/current and probe series: north_star bar 1e-5 rel-L2, achieved: identical"""
+    s = cases.engine_cavity()
+    op = operator_from_oracle(s)
+    eng = op.CreateEngine()
+    vp = [((5, 4, 5), (9, 4, 5)), ((5, 8, 5), (5, 3, 5)), ((12, 4, 5), (12, 4, 17))]
+    cp = [(((4, 3, 10), (12, 8, 10)), 2, (1, 1, 1), (1, 1, 1)), (((8, 2, 6), (8, 8, 20)), 0, (1, 1, 1), (1, 0, 1)),
+          (((3, 5, 4), (20, 5, 25)), 1, (1, 1, 0), (1, 1, 1))]
+    fp = [(0, (16, 6, 20)), (1, (16, 6, 20)), (0, (0, 0, 0)), (1, (25, 9, 31))]
+    for a, b in vp:
+        eng.AddVoltageProbe(a, b)
+    for (a, b), nd, si, ei in cp:
+        eng.AddCurrentProbe(a, b, nd, si, ei)
+    for h, p in fp:
+        eng.AddFieldProbe(h, p)
+    interval = max(1, s.nyquist // 4)
+    eng.RecordProbes(interval, 200)
+    ref = []
+    for it in range(60):
+        s.iterate(interval)
+        eng.IterateTS(interval)
+        row = [s.voltage_integral(a, b) for a, b in vp]
+        row += [s.current_integral(a, b, nd, si, ei) for (a, b), nd, si, ei in cp]
+        for h, p in fp:
+            v = (s.curr if h else s.volt)[:, p[0], p[1], p[2]]
+            row += [float(x) for x in v]
+        ref.append(row)
+        if it % 20 == 7:
+            now = eng.ReadProbes()
+            assert np.array_equal(now, np.array(row))
+            e_gpu, e_ref = eng.CalcFastEnergy(), s.energy()
+            assert e_ref > 0 and abs(e_gpu - e_ref) <= 1e-12 * e_ref
+    ts, series = eng.ReadProbeSeries()
+    ref = np.array(ref)
+    assert series.shape == ref.shape
+    assert list(ts) == [interval * (i + 1) for i in range(60)]
+    assert np.abs(ref).max(axis=0).min() >= 0
+    for col in range(ref.shape[1]):
+        assert rel_l2(series[:, col], ref[:, col]) <= 1e-5
+    assert np.array_equal(series, ref)  # in fact identical
+    assert np.abs(ref[:, :6]).max() > 0
+
+
+def test_engine_interface_mirror():
+    s = cases.uniform_box(n=(20, 18, 22), bc=(BC_MUR,) * 6)
+    op = operator_from_oracle(s)
+    eng = op.CreateEngine()
+    ei = Engine_Interface_CUDA(op, eng)
+    s.iterate(60)
+    eng.IterateTS(60)
+    assert ei.GetNumberOfTimesteps() == 60
+    assert ei.GetTime() == pytest.approx(60 * s.dT)
+    assert ei.CalcVoltageIntegral((8, 9, 11), (12, 9, 11)) == s.voltage_integral((8, 9, 11), (12, 9, 11))
+    pos = (11, 9, 12)
+    assert np.array_equal(ei.GetEField(pos), s.raw_field(0, pos))
+    assert np.array_equal(ei.GetHField(pos), s.raw_field(1, pos))
+    # per-cell slow path, Engine::GetVolt/SetVolt
+    assert eng.GetVolt(2, 10, 9, 11) == s.volt[2, 10, 9, 11]
+    assert eng.GetCurr(1, (10, 9, 11)) == s.curr[1, 10, 9, 11]
+    eng.SetVolt(0, 3, 4, 5, 1.25)
+    assert eng.GetVolt(0, (3, 4, 5)) == 1.25
+
+
+@pytest.mark.parametrize("interp", [0, 1, 2])
+@pytest.mark.parametrize("is_H", [0, 1])
+def test_field_dump(is_H, interp):
+    """probe==dump rule and bit-equal dumps (fieldprobes.m:34, enginetests/cavity.m:155) on a
+    non-uniform mesh, including the faces where the interpolation degenerates"""
+    x = np.cumsum(np.r_[0, np.linspace(1, 2, 17)]) * 1e-3
+    y = np.arange(16) * 1.5e-3
+    z = np.cumsum(np.r_[0, np.linspace(2, 1, 19)]) * 1e-3
+    s = OracleSim(x, y, z, 1.0)
+    s.set_bc([BC_MUR, BC_MUR, BC_PEC, BC_PMC, BC_MUR, BC_MUR])
+    s.set_excite_gauss(5e9, 5e9)
+    c = cases.edge_center((x, y, z), 2, (9, 8, 10))
+    s.add_excitation(c, c, EXC_E_SOFT, (0, 0, 1))
+    s.build()
+    op = operator_from_oracle(s)
+    eng = op.CreateEngine()
+    s.iterate(70)
+    eng.IterateTS(70)
+    start, stop = (0, 0, 0), (17, 15, 19)
+    el = [[s.edge_length(n, [p if a == n else 0 for a in range(3)], False) for p in range(s.N[n])] for n in range(3)]
+    dl = [[s.edge_length(n, [p if a == n else 0 for a in range(3)], True) for p in range(s.N[n])] for n in range(3)]
+    d = eng.AddDump(is_H, interp, np.arange(18), np.arange(16), np.arange(20), el, dl)
+    got = eng.ReadDump(d)
+    ref = s.dump_field(is_H, interp, start, stop)
+    assert np.abs(ref).max() > 0
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # sub-sampled position lists
+    px, py, pz = [2, 5, 9, 17], [0, 8, 15], [3, 10, 19]
+    d2 = eng.AddDump(is_H, interp, px, py, pz, el, dl)
+    sub = eng.ReadDump(d2)
+    assert np.array_equal(sub, ref[:, pz][:, :, py][:, :, :, px])
+
+
+def test_lorentz_drude_block():
+    """config C4 in small: Drude eps+mue block (f_p 5 GHz, tau 5 ns) and a 2-pole Lorentz block"""
+    n = (34, 30, 38)
+    lor = [dict(start=(0.010, 0.008, 0.012), stop=(0.022, 0.020, 0.026), eps_fp=(5e9,), eps_tau=(5e-9,),
+                mue_fp=(5e9,), mue_tau=(5e-9,)),
+           dict(start=(0.004, 0.004, 0.004), stop=(0.008, 0.012, 0.010), epsR=2.0, eps_fp=(3e9, 6e9), eps_tau=(2e-9, 0.0),
+                eps_flor=(0.0, 9e9), prio=3)]
+    fc = C0 / (20 * 1e-3) / 2
+    s = cases.uniform_box(n=n, bc=(BC_PML,) * 6, pml=6, f0=fc, fc=fc, lorentz=lor, src_pos=(6, 15, 19))
+    L = s.lorentz()
+    assert len(L) == 2 and L[0]["count"] > 1000 and (L[0]["flags"] & 3) == 3 and (L[1]["flags"] & 4)
+    op = operator_from_oracle(s)
+    eng = op.CreateEngine()
+    for nsteps in (1, 40, 200):
+        s.iterate(nsteps)
+        eng.IterateTS(nsteps)
+        mv, mc = assert_fields_equal(eng, s, "lorentz")
+    assert mv > 0
+
+
+def test_lumped_rlc_raw():
+    rng = np.random.default_rng(7)
+    n = (24, 22, 26)
+
+    def extra(s, lines):
+        cnt = 5
+        pos = np.array([[8, 9, 10, 11, 12], [10, 10, 11, 11, 12], [12, 13, 12, 13, 14]], np.uint32)
+        d = np.array([0, 1, 2, 2, 1], np.int32)
+        co = {k: (rng.uniform(-0.3, 0.3, cnt)).astype(np.float32) for k in ("ilv", "i2v", "vv2", "vj1", "vj2", "ib0", "b1", "b2")}
+        co["vvd"] = rng.uniform(0.5, 1.0, cnt).astype(np.float32)
+        s._rlc = (d, pos, co)
+        s.add_rlc_raw(d, pos, co)
+    s = cases.uniform_box(n=n, bc=(BC_MUR,) * 6, extra=extra, src_pos=(9, 10, 12))
+    op = operator_from_oracle(s)
+    op.AddLumpedRLC(*s._rlc)
+    eng = op.CreateEngine()
+    for nsteps in (1, 2, 3, 4, 50):
+        s.iterate(nsteps)
+        eng.IterateTS(nsteps)
+        assert_fields_equal(eng, s, "rlc")
+
+
+def test_compressed_operator_path_matches_oracle():
+    """host builder -> compressed upload -> kernels, against the oracle's dense pipeline"""
+    lines = (np.arange(40, dtype=np.float64), np.arange(33, dtype=np.float64), np.arange(45, dtype=np.float64))
+
+    def setup(q):
+        q.set_bc([BC_PML, BC_PML, BC_MUR, BC_PML, BC_PMC, BC_PML], (8, 8, 8, 6, 8, 7))
+        q.set_excite_gauss(6e9, 6e9)
+        q.add_material((10, 5, 8), (25, 20, 30), epsR=2.5, kappa=0.01)
+        q.add_metal((12, 10, 20), (30, 18, 20))
+        q.add_excitation((20, 16, 10.5), (20, 16, 10.5), EXC_E_SOFT, (0, 0, 1))
+    o = OracleSim(*lines, 1e-3)
+    p = SyntheticOperator(*lines, 1e-3)
+    setup(o)
+    setup(p)
+    o.build()
+    p.build()
+    eng = p.CreateEngine()
+    for nsteps in (1, 30, 170):
+        o.iterate(nsteps)
+        eng.IterateTS(nsteps)
+        mv, mc = assert_fields_equal(eng, o, "compressed path")
+    assert mv > 0 and mc > 0
+    st = eng.GetStats()
+    assert st["n_unique"] == p.n_unique and st["index_bytes"] == 2 and st["uses_graph"]
+
+
+def test_reset_and_error_behaviour():
+    s = cases.uniform_box(n=(16, 16, 16), bc=(BC_PEC,) * 6)
+    op = operator_from_oracle(s)
+    eng = op.CreateEngine()
+    eng.IterateTS(20)
+    assert np.abs(eng.GetFields(0)).max() > 0
+    eng.Reset()
+    assert eng.GetNumberOfTimesteps() == 0 and np.abs(eng.GetFields(0)).max() == 0
+    s.iterate(25)
+    eng.IterateTS(25)
+    assert_fields_equal(eng, s, "after reset")
+    with pytest.raises(EngineError):
+        eng.GetVolt(0, 99, 0, 0)
+    with pytest.raises(EngineError):
+        eng.AddVoltageProbe((0, 0, 0), (0, 0, 99))
+    with pytest.raises(EngineError):
+        Operator_CUDA((2, 5, 5)).CreateEngine()
+    bad = Operator_CUDA((8, 8, 8))
+    with pytest.raises(EngineError):
+        bad.CreateEngine()  # no coefficients
