@@ -351,8 +351,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, nargs=3, default=[1024, 1024, 1024], help="mesh lines (default: the 1024^3 headline config)")
-    ap.add_argument("--cpu-sample", type=int, nargs=3, default=[192, 192, 192])
-    ap.add_argument("--cpu-steps", type=int, default=60)
+    ap.add_argument("--cpu-sample", type=int, nargs=3, default=[256, 256, 256])
+    ap.add_argument("--cpu-steps", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

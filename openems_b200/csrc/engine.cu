@@ -145,7 +145,14 @@ int Engine::set_operator_compressed(unsigned nu, const oems_coeff_entry* table, 
 		for (size_t r = 0; r < total_rows; r += chunk_rows, q ^= 1) {
 			const size_t nr = std::min(chunk_rows, total_rows - r);
 			CK(cudaEventSynchronize(done[q]));
-			memcpy(stage[q], src + r * row_bytes, nr * row_bytes);
+			{
+				const size_t bytes = nr * row_bytes, nt = 8, per = (bytes + nt - 1) / nt;
+#pragma omp parallel for schedule(static) num_threads(8)
+				for (long long t = 0; t < (long long)nt; ++t) {
+					const size_t b0 = (size_t)t * per, b1 = std::min(bytes, b0 + per);
+					if (b1 > b0) memcpy((char*)stage[q] + b0, src + r * row_bytes + b0, b1 - b0);
+				}
+			}
 			CK(cudaMemcpy2DAsync((char*)p + r * (size_t)pitch * ib, (size_t)pitch * ib, stage[q], row_bytes, row_bytes, nr,
 			                     cudaMemcpyHostToDevice, stream));
 			CK(cudaEventRecord(done[q], stream));
@@ -402,16 +409,24 @@ int Engine::build_pml()
 		pH.box[nb] = pb;
 		++nb;
 		// cells of the box the H stencil never visits (last line of a direction)
-		for (int lk = 0; lk < B.ln[2]; ++lk)
+		auto add_edge = [&](int li, int lj, int lk) {
+			e_cell.push_back(cell_off(B.ls[0] + li, B.ls[1] + lj, bz0 + lk));
+			e_fo.push_back(B.flux_off + ((long long)lk * B.ln[1] + lj) * B.ln[0] + li);
+			e_cs.push_back(cs);
+		};
+		const int lx = (int)gn[0] - 1 - B.ls[0], ly = (int)gn[1] - 1 - B.ls[1], lz = (int)gn[2] - 1 - (int)bz0;
+		const bool hx = lx >= 0 && lx < B.ln[0], hy = ly >= 0 && ly < B.ln[1], hz = lz >= 0 && lz < B.ln[2];
+		if (hx)
+			for (int lk = 0; lk < B.ln[2]; ++lk)
+				for (int lj = 0; lj < B.ln[1]; ++lj) add_edge(lx, lj, lk);
+		if (hy)
+			for (int lk = 0; lk < B.ln[2]; ++lk)
+				for (int li = 0; li < B.ln[0]; ++li)
+					if (!(hx && li == lx)) add_edge(li, ly, lk);
+		if (hz)
 			for (int lj = 0; lj < B.ln[1]; ++lj)
-				for (int li = 0; li < B.ln[0]; ++li) {
-					const unsigned x = B.ls[0] + li, y = B.ls[1] + lj, gz = bz0 + lk;
-					if (x == gn[0] - 1 || y == gn[1] - 1 || gz == gn[2] - 1) {
-						e_cell.push_back(cell_off(x, y, gz));
-						e_fo.push_back(B.flux_off + ((long long)lk * B.ln[1] + lj) * B.ln[0] + li);
-						e_cs.push_back(cs);
-					}
-				}
+				for (int li = 0; li < B.ln[0]; ++li)
+					if (!(hx && li == lx) && !(hy && lj == ly)) add_edge(li, lj, lz);
 	}
 	pE.nboxes = pH.nboxes = nb;
 	has_pml = nb > 0;
@@ -741,7 +756,7 @@ void Engine::build_schedule()
 			if (i16) { if (has_pml) k_update_H<uint16_t, true><<<g, block, 0, s>>>(pH); else k_update_H<uint16_t, false><<<g, block, 0, s>>>(pH); }
 			else { if (has_pml) k_update_H<uint32_t, true><<<g, block, 0, s>>>(pH); else k_update_H<uint32_t, false><<<g, block, 0, s>>>(pH); }
 		}));
-	if (pEdge.count)
+	if (pEdge.count && edge_dirty)
 		(labels.push_back("upml_untouched_H"), step.push_back([this, i16](cudaStream_t s) {
 			if (i16) launch1d(k_upml_untouched_H<uint16_t>, pEdge, pEdge.count, s);
 			else launch1d(k_upml_untouched_H<uint32_t>, pEdge, pEdge.count, s);
@@ -1102,6 +1117,7 @@ int Engine::set_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned 
 	float* base = is_curr ? d_I : d_V;
 	CK(cudaMemcpyAsync(base + n * comp + cell_off(x, y, z), &v, sizeof(float), cudaMemcpyHostToDevice, stream));
 	CK(cudaStreamSynchronize(stream));
+	if (is_curr && (x == gn[0] - 1 || y == gn[1] - 1 || z == gn[2] - 1)) mark_edge_dirty();
 	return 0;
 }
 
@@ -1135,7 +1151,19 @@ int Engine::set_fields(int is_curr, const float* in)
 					h[n * comp + (long long)k * plane + (long long)j * pitch + i] = in[(((size_t)n * nx + i) * ny + j) * nzl + k];
 	CK(cudaMemcpyAsync(is_curr ? d_I : d_V, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
 	CK(cudaStreamSynchronize(stream));
+	if (is_curr) mark_edge_dirty();
 	return 0;
+}
+
+// The currents on the last line of each direction are never written by the engine (engine.cpp:179-183)
+// and start at +0; with a +0 flux the UPML pre/post pair maps +0 to +0, so k_upml_untouched_H is
+// only scheduled once the caller has poked a current there (SetCurr / set_fields).
+void Engine::mark_edge_dirty()
+{
+	if (edge_dirty || !pEdge.count) return;
+	edge_dirty = true;
+	cudaStreamSynchronize(stream);
+	build_schedule();
 }
 
 int Engine::get_upml_flux(int box, int is_curr, float* out)

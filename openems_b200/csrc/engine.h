@@ -194,6 +194,8 @@ private:
 	int build_probes();
 	void build_schedule();
 	void launch_probes(double* dst);
+	void mark_edge_dirty();
+	bool edge_dirty = false;
 	bool owned(unsigned z) const { return z >= zb && z < ze; }
 	bool held(unsigned z) const { return (int)z >= z0 && (int)z < z0 + nzl; }
 	long long cell_off(unsigned x, unsigned y, unsigned z) const

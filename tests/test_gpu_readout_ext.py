@@ -203,3 +203,20 @@ def test_reset_and_error_behaviour():
     bad = Operator_CUDA((8, 8, 8))
     with pytest.raises(EngineError):
         bad.CreateEngine()  # no coefficients
+
+
+def test_upml_cells_outside_h_update_follow_reference():
+    """Engine_Ext_UPML touches every cell of its box, also the last H line the stencil skips
+    (engine_ext_upml.cpp:63-90 vs engine.cpp:179-183): poke a current there and compare"""
+    s = cases.uniform_box(n=(20, 18, 22), bc=(BC_PML,) * 6, pml=4)
+    op = operator_from_oracle(s)
+    eng = op.CreateEngine()
+    k0 = eng.GetStats()["kernels_per_step"]
+    for n, pos in ((1, (19, 5, 6)), (0, (7, 17, 3)), (2, (4, 9, 21))):
+        s.curr[n, pos[0], pos[1], pos[2]] = 0.37
+        eng.SetCurr(n, pos, 0.37)
+    assert eng.GetStats()["kernels_per_step"] == k0 + 1  # the edge kernel is now scheduled
+    for nsteps in (1, 1, 10):
+        s.iterate(nsteps)
+        eng.IterateTS(nsteps)
+        assert_fields_equal(eng, s, "poked last-line currents")
