@@ -1,0 +1,229 @@
+/*
+ * engine_cuda.cpp -- see engine_cuda.h.  Goes to openEMS/FDTD/engine_cuda.cpp.
+ *
+ * The stock Engine_Ext_* objects cannot be reused: they go through ENG_DISPATCH, which throws
+ * for any engine type other than BASIC/SSE (extensions/engine_extension_dispatcher.h:58-72).
+ * InitExtensions therefore reads the OPERATOR extensions' tables (one `friend class
+ * Engine_CUDA;` line per operator_ext header) and hands them to the library.
+ */
+#include "engine_cuda.h"
+#include "operator_cuda.h"
+#include "extensions/operator_ext_excitation.h"
+#include "extensions/operator_ext_upml.h"
+#include "extensions/operator_ext_mur_abc.h"
+#include "extensions/operator_ext_lorentzmaterial.h"
+#include "extensions/operator_ext_conductingsheet.h"
+#include "extensions/operator_ext_lumpedRLC.h"
+#include "extensions/operator_ext_steadystate.h"
+#include "extensions/engine_extension.h"
+#include "excitation.h"
+
+#include <cstdlib>
+#include <vector>
+
+using namespace std;
+
+Engine_CUDA* Engine_CUDA::New(const Operator_CUDA* op)
+{
+	cout << "Create FDTD engine (B200 CUDA)" << endl;
+	Engine_CUDA* e = new Engine_CUDA(op);
+	e->Init();
+	return e;
+}
+
+Engine_CUDA::Engine_CUDA(const Operator_CUDA* op) : Engine(op), m_Op_CUDA(op), m_h(NULL)
+{
+	m_type = UNKNOWN; // neither BASIC nor SSE: stock extensions must not dispatch on this engine
+}
+
+Engine_CUDA::~Engine_CUDA()
+{
+	Reset();
+}
+
+void Engine_CUDA::Check(int rc, const char* what) const
+{
+	if (rc==0) return;
+	cerr << "Engine_CUDA::" << what << ": " << oems_cuda_last_error(m_h) << endl;
+	exit(2); // the reference's convention for unrecoverable engine errors (openems.cpp:803-807)
+}
+
+void Engine_CUDA::Reset()
+{
+	if (m_h) oems_cuda_destroy(m_h);
+	m_h = NULL;
+	Engine::Reset();
+}
+
+void Engine_CUDA::Init()
+{
+	numTS = 0;
+	// no host field arrays: volt_ptr / curr_ptr stay NULL (all accessors are overridden)
+	Check( oems_cuda_create(numLines[0], numLines[1], numLines[2], m_Op_CUDA->GetDevice(), &m_h), "Init" );
+
+	// dense coefficients in ArrayNIJK order, as the C ABI wants them
+	const size_t N = (size_t)numLines[0]*numLines[1]*numLines[2];
+	std::vector<FDTD_FLOAT> vv(3*N), vi(3*N), ii(3*N), iv(3*N);
+	size_t p=0;
+	for (unsigned int n=0; n<3; ++n)
+		for (unsigned int x=0; x<numLines[0]; ++x)
+			for (unsigned int y=0; y<numLines[1]; ++y)
+				for (unsigned int z=0; z<numLines[2]; ++z, ++p)
+				{
+					vv[p] = Op->GetVV(n,x,y,z); vi[p] = Op->GetVI(n,x,y,z);
+					ii[p] = Op->GetII(n,x,y,z); iv[p] = Op->GetIV(n,x,y,z);
+				}
+	Check( oems_cuda_set_operator_dense(m_h, vv.data(), vi.data(), ii.data(), iv.data()), "set_operator" );
+
+	InitExtensions();
+	Check( oems_cuda_finalize(m_h), "finalize" );
+}
+
+void Engine_CUDA::InitExtensions()
+{
+	Excitation* exc = Op->GetExcitationSignal();
+	unsigned int period_ts = 0;
+	if (exc->GetSignalPeriod()>0)
+		period_ts = (unsigned int)int(exc->GetSignalPeriod()/exc->GetTimestep());
+	Check( oems_cuda_set_signal(m_h, exc->GetVoltageSignal(), exc->GetCurrentSignal(), exc->GetLength(), period_ts), "set_signal" );
+
+	for (size_t n=0; n<Op->GetNumberOfExtentions(); ++n)
+	{
+		Operator_Extension* op_ext = Op->GetExtension(n);
+
+		if (Operator_Ext_Excitation* e = dynamic_cast<Operator_Ext_Excitation*>(op_ext))
+		{
+			for (int w=0; w<2; ++w)
+			{
+				unsigned int cnt = w ? e->Curr_Count : e->Volt_Count;
+				if (cnt==0) continue;
+				unsigned int** idx = w ? e->Curr_index : e->Volt_index;
+				unsigned short* d16 = w ? e->Curr_dir : e->Volt_dir;
+				std::vector<unsigned int> idx3(3*(size_t)cnt), dir(cnt);
+				for (unsigned int i=0; i<cnt; ++i)
+				{
+					for (int a=0; a<3; ++a) idx3[(size_t)a*cnt+i] = idx[a][i];
+					dir[i] = d16[i];
+				}
+				Check( oems_cuda_add_excitation(m_h, w, cnt, idx3.data(), dir.data(),
+					w ? e->Curr_amp : e->Volt_amp, w ? e->Curr_delay : e->Volt_delay), "add_excitation" );
+			}
+			continue;
+		}
+		if (Operator_Ext_UPML* u = dynamic_cast<Operator_Ext_UPML*>(op_ext))
+		{
+			Check( oems_cuda_add_upml(m_h, u->m_StartPos, u->m_numLines, u->vv.data(), u->vvfn.data(), u->vvfo.data(),
+				u->ii.data(), u->iifn.data(), u->iifo.data()), "add_upml" );
+			continue;
+		}
+		if (Operator_Ext_Mur_ABC* m = dynamic_cast<Operator_Ext_Mur_ABC*>(op_ext))
+		{
+			// delayed start, Engine_Ext_Mur_ABC ctor engine_ext_mur_abc.cpp:44-60
+			int maxDelay=-1;
+			Operator_Ext_Excitation* Exc_ext = Op->GetExcitationExtension();
+			for (unsigned int i=0; i<Exc_ext->GetVoltCount(); ++i)
+				if ( ((Exc_ext->Volt_dir[i]==m->m_nyP) || (Exc_ext->Volt_dir[i]==m->m_nyPP)) && (Exc_ext->Volt_index[m->m_ny][i]==m->m_LineNr) )
+					if ((int)Exc_ext->Volt_delay[i]>maxDelay) maxDelay = (int)Exc_ext->Volt_delay[i];
+			unsigned int start_ts = (maxDelay>=0) ? maxDelay + exc->GetLength() + 10 : 0;
+			Check( oems_cuda_add_mur(m_h, m->m_ny, m->m_LineNr, m->m_LineNr_Shift, m->m_numLines,
+				m->m_Mur_Coeff_nyP.data(), m->m_Mur_Coeff_nyPP.data(), start_ts), "add_mur" );
+			continue;
+		}
+		// Operator_Ext_ConductingSheet derives from Operator_Ext_LorentzMaterial: same tables
+		if (Operator_Ext_LorentzMaterial* l = dynamic_cast<Operator_Ext_LorentzMaterial*>(op_ext))
+		{
+			for (int o=0; o<l->m_Order; ++o)
+			{
+				unsigned int cnt = l->m_LM_Count.at(o);
+				std::vector<unsigned int> pos3(3*(size_t)cnt);
+				std::vector<FDTD_FLOAT> c[6];
+				FDTD_FLOAT*** src[6] = {l->v_int_ADE, l->v_ext_ADE, l->v_Lor_ADE, l->i_int_ADE, l->i_ext_ADE, l->i_Lor_ADE};
+				bool on[6] = {l->m_volt_ADE_On[o], l->m_volt_ADE_On[o], l->m_volt_Lor_ADE_On[o],
+				              l->m_curr_ADE_On[o], l->m_curr_ADE_On[o], l->m_curr_Lor_ADE_On[o]};
+				for (int a=0; a<3; ++a)
+					for (unsigned int i=0; i<cnt; ++i) pos3[(size_t)a*cnt+i] = l->m_LM_pos[o][a][i];
+				for (int w=0; w<6; ++w)
+					if (on[w])
+					{
+						c[w].resize(3*(size_t)cnt);
+						for (int a=0; a<3; ++a)
+							for (unsigned int i=0; i<cnt; ++i) c[w][(size_t)a*cnt+i] = src[w][o][a][i];
+					}
+				Check( oems_cuda_add_lorentz(m_h, cnt, pos3.data(), on[0]?c[0].data():NULL, on[1]?c[1].data():NULL, on[2]?c[2].data():NULL,
+					on[3]?c[3].data():NULL, on[4]?c[4].data():NULL, on[5]?c[5].data():NULL), "add_lorentz" );
+			}
+			continue;
+		}
+		if (Operator_Ext_LumpedRLC* r = dynamic_cast<Operator_Ext_LumpedRLC*>(op_ext))
+		{
+			unsigned int cnt = r->RLC_count;
+			if (cnt==0) continue;
+			std::vector<unsigned int> pos3(3*(size_t)cnt);
+			for (int a=0; a<3; ++a)
+				for (unsigned int i=0; i<cnt; ++i) pos3[(size_t)a*cnt+i] = r->v_RLC_pos[a][i];
+			Check( oems_cuda_add_rlc(m_h, cnt, r->v_RLC_dir, pos3.data(), r->v_RLC_ilv, r->v_RLC_i2v, r->v_RLC_vvd, r->v_RLC_vv2,
+				r->v_RLC_vj1, r->v_RLC_vj2, r->v_RLC_ib0, r->v_RLC_b1, r->v_RLC_b2), "add_rlc" );
+			continue;
+		}
+		if (dynamic_cast<Operator_Ext_SteadyState*>(op_ext))
+		{
+			// engine-agnostic stock extension (virtual GetVolt only, engine_ext_steadystate.cpp:50-61);
+			// the driver dereferences it without a NULL check (openems.cpp:1318-1322), so create it.
+			Engine_Extension* eng_ext = op_ext->CreateEngineExtention();
+			if (eng_ext)
+			{
+				eng_ext->SetEngine(this);
+				m_Eng_exts.push_back(eng_ext);
+			}
+			continue;
+		}
+		cerr << "Engine_CUDA::InitExtensions: extension \"" << op_ext->GetExtensionName()
+		     << "\" has no device implementation yet (TFSF, local absorbing BC, cylinder: see DESIGN.md), aborting" << endl;
+		exit(2);
+	}
+}
+
+bool Engine_CUDA::IterateTS(unsigned int iterTS)
+{
+	if (m_Eng_exts.empty())
+	{
+		Check( oems_cuda_iterate(m_h, iterTS), "IterateTS" );
+		numTS += iterTS;
+		return true;
+	}
+	// steady-state detection samples voltages every timestep: step one by one
+	for (unsigned int iter=0; iter<iterTS; ++iter)
+	{
+		Check( oems_cuda_iterate(m_h, 1), "IterateTS" );
+		for (size_t n=0; n<m_Eng_exts.size(); ++n)
+			m_Eng_exts.at(n)->Apply2Voltages();
+		++numTS;
+	}
+	return true;
+}
+
+unsigned int Engine_CUDA::GetNumberOfTimesteps()
+{
+	return numTS;
+}
+
+FDTD_FLOAT Engine_CUDA::GetVolt(unsigned int n, unsigned int x, unsigned int y, unsigned int z) const
+{
+	float v=0;
+	Check( oems_cuda_get_field(m_h, 0, n, x, y, z, &v), "GetVolt" );
+	return v;
+}
+FDTD_FLOAT Engine_CUDA::GetCurr(unsigned int n, unsigned int x, unsigned int y, unsigned int z) const
+{
+	float v=0;
+	Check( oems_cuda_get_field(m_h, 1, n, x, y, z, &v), "GetCurr" );
+	return v;
+}
+void Engine_CUDA::SetVolt(unsigned int n, unsigned int x, unsigned int y, unsigned int z, FDTD_FLOAT value)
+{
+	Check( oems_cuda_set_field(m_h, 0, n, x, y, z, value), "SetVolt" );
+}
+void Engine_CUDA::SetCurr(unsigned int n, unsigned int x, unsigned int y, unsigned int z, FDTD_FLOAT value)
+{
+	Check( oems_cuda_set_field(m_h, 1, n, x, y, z, value), "SetCurr" );
+}
