@@ -115,6 +115,8 @@ int oems_cuda_finalize(oems_cuda_engine* h);
 /* ---- time stepping: Engine::IterateTS / GetNumberOfTimesteps (FDTD/engine.h:48-50).
    iterate() only enqueues; reads synchronise. */
 int oems_cuda_iterate(oems_cuda_engine* h, unsigned n_ts);
+/* iterate + device time of the burst in ms (CUDA events on the engine's stream), synchronises */
+int oems_cuda_iterate_timed(oems_cuda_engine* h, unsigned n_ts, double* elapsed_ms);
 int oems_cuda_sync(oems_cuda_engine* h);
 int oems_cuda_num_ts(oems_cuda_engine* h, unsigned* ts);
 int oems_cuda_reset(oems_cuda_engine* h); /* fields, extension state and numTS back to 0 */
@@ -184,6 +186,9 @@ typedef struct oems_cuda_stats {
 int oems_cuda_get_stats(oems_cuda_engine* h, oems_cuda_stats* out);
 /* tuning knobs (0 keeps the default): block rows and z-chunk of the stencil kernels, graph on/off */
 int oems_cuda_set_tuning(oems_cuda_engine* h, int block_rows, int z_chunk, int use_graph);
+
+/* named integer options (none at present; reserved so that tuning switches do not change the ABI) */
+int oems_cuda_set_option(oems_cuda_engine* h, const char* key, long long value);
 
 /* measurement aid: runs n_ts timesteps without the graph and returns the average duration in
    ms of every kernel of the per-timestep schedule, timed with CUDA events on the engine's own

@@ -53,6 +53,7 @@ SIGNATURES = {
     "oems_cuda_add_rlc": (C.c_int, [_vp, C.c_uint, _ip, _up] + [_fp] * 9),
     "oems_cuda_finalize": (C.c_int, [_vp]),
     "oems_cuda_iterate": (C.c_int, [_vp, C.c_uint]),
+    "oems_cuda_iterate_timed": (C.c_int, [_vp, C.c_uint, _dp]),
     "oems_cuda_sync": (C.c_int, [_vp]),
     "oems_cuda_num_ts": (C.c_int, [_vp, _up]),
     "oems_cuda_reset": (C.c_int, [_vp]),
@@ -74,6 +75,7 @@ SIGNATURES = {
     "oems_cuda_get_upml_flux": (C.c_int, [_vp, C.c_int, C.c_int, _fp]),
     "oems_cuda_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "oems_cuda_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "oems_cuda_set_option": (C.c_int, [_vp, C.c_char_p, C.c_longlong]),
     "oems_cuda_time_schedule": (C.c_int, [_vp, C.c_uint, _dp, C.c_uint, _up]),
     "oems_cuda_schedule_label": (C.c_char_p, [_vp, C.c_uint]),
     "oems_cuda_export_ipc": (C.c_int, [_vp, C.POINTER(C.c_ubyte)]),

@@ -827,6 +827,38 @@ int Engine::iterate(unsigned n)
 	return 0;
 }
 
+int Engine::set_option(const char* key, long long value)
+{
+	const std::string k = key ? key : "";
+	(void)value;
+	// no options at present.  (An "L2-blocked" launch order -- E kernel on a few planes, then the
+	// H kernel one plane behind so that it reads from L2 -- was measured in round 1 and was 1.7x
+	// SLOWER at 1024^3: see profiles/experiments_r01.md.)
+	return fail("set_option: unknown key " + k);
+}
+
+// iterate(n) bracketed by CUDA events on the engine's stream; returns the device time in ms
+int Engine::iterate_timed(unsigned n, double* ms)
+{
+	if (!finalized) return fail("iterate_timed: engine not finalized");
+	CK(cudaSetDevice(device));
+	cudaEvent_t a, b;
+	CK(cudaEventCreate(&a));
+	CK(cudaEventCreate(&b));
+	CK(cudaStreamSynchronize(stream));
+	CK(cudaEventRecord(a, stream));
+	int rc = iterate(n);
+	if (rc) return rc;
+	CK(cudaEventRecord(b, stream));
+	CK(cudaEventSynchronize(b));
+	float t = 0;
+	CK(cudaEventElapsedTime(&t, a, b));
+	cudaEventDestroy(a);
+	cudaEventDestroy(b);
+	if (ms) *ms = t;
+	return sync();
+}
+
 int Engine::sync()
 {
 	CK(cudaSetDevice(device));

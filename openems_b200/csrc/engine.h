@@ -76,6 +76,7 @@ public:
 	int finalize();
 
 	int iterate(unsigned n);
+	int iterate_timed(unsigned n, double* ms);
 	int sync();
 	int reset();
 	unsigned num_ts() const { return numTS_host; }
@@ -195,6 +196,9 @@ private:
 	void build_schedule();
 	void launch_probes(double* dst);
 	void mark_edge_dirty();
+public:
+	int set_option(const char* key, long long value);
+private:
 	bool edge_dirty = false;
 	bool owned(unsigned z) const { return z >= zb && z < ze; }
 	bool held(unsigned z) const { return (int)z >= z0 && (int)z < z0 + nzl; }

@@ -212,6 +212,12 @@ class Engine_CUDA:
         self._ck(self._L.oems_cuda_iterate(self._h, int(iterTS)))
         return True
 
+    def IterateTimed(self, iterTS):
+        """IterateTS + the burst's device time in ms (CUDA events on the engine's own stream)"""
+        ms = C.c_double()
+        self._ck(self._L.oems_cuda_iterate_timed(self._h, int(iterTS), C.byref(ms)))
+        return ms.value
+
     def Synchronize(self):
         self._ck(self._L.oems_cuda_sync(self._h))
 
@@ -349,6 +355,9 @@ class Engine_CUDA:
 
     def SetTuning(self, block_rows=0, z_chunk=0, use_graph=-1):
         self._ck(self._L.oems_cuda_set_tuning(self._h, block_rows, z_chunk, use_graph))
+
+    def SetOption(self, key, value):
+        self._ck(self._L.oems_cuda_set_option(self._h, key.encode(), int(value)))
 
     def TimeSchedule(self, n_ts):
         """average ms of every kernel of the per-timestep schedule (CUDA events on the engine stream)"""
