@@ -198,11 +198,9 @@ def run_gpu(args):
     n = tuple(args.n)
     nz = n[2]
     slab = None
-    if world > 1:  # strong scaling: z-slabs of the same mesh
-        base, rem = divmod(nz, world)
-        zb = rank * base + min(rank, rem)
-        ze = zb + base + (1 if rank < rem else 0)
-        slab = (zb, ze)
+    if world > 1:  # strong scaling: z-slabs of the same mesh (full z-PML planes cost about the same as plain planes: profiles/experiments_r01.md)
+        from openems_b200.slabs import slab_range
+        slab = slab_range(nz, world, rank, pml_lo=PML, pml_hi=PML, pml_weight=0.0)
 
     so, t_build = build_c5(n)
     op = so.operator()

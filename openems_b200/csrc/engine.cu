@@ -658,7 +658,7 @@ int Engine::finalize()
 	base.V = d_V; base.I = d_I; base.idx = d_idx;
 	base.nx = (int)gn[0]; base.ny = (int)gn[1]; base.nz = nzl;
 	base.pitch = pitch; base.plane = plane; base.comp = comp;
-	base.zchunk = tune_zchunk;
+	base.zchunk = tune_zchunk > 0 ? tune_zchunk : auto_zchunk();
 	pE = base; pH = base;
 	pE.tA = d_tab[0]; pE.tB = d_tab[1]; pE.tP0 = d_tab[2]; pE.tP1 = d_tab[3]; pE.tP2 = d_tab[4];
 	pH.tA = d_tab[5]; pH.tB = d_tab[6]; pH.tP0 = d_tab[7]; pH.tP1 = d_tab[8]; pH.tP2 = d_tab[9];
@@ -1235,6 +1235,14 @@ int Engine::get_stats(oems_cuda_stats* s)
 	return 0;
 }
 
+// planes marched per block: long chunks amortise the k-1 plane reload, short chunks give the
+// block scheduler enough blocks to hide the tail on thin slabs (profiles/experiments_r01.md #5)
+int Engine::auto_zchunk() const
+{
+	const int planes = (int)(ze - zb);
+	return planes >= 512 ? 32 : planes >= 256 ? 16 : 8;
+}
+
 int Engine::set_tuning(int rows, int zchunk, int graph_on)
 {
 	if (rows > 0) {
@@ -1246,7 +1254,7 @@ int Engine::set_tuning(int rows, int zchunk, int graph_on)
 	if (finalized) {
 		CK(cudaSetDevice(device));
 		CK(cudaStreamSynchronize(stream));
-		pE.zchunk = pH.zchunk = tune_zchunk;
+		pE.zchunk = pH.zchunk = tune_zchunk > 0 ? tune_zchunk : auto_zchunk();
 		build_schedule();
 	}
 	return 0;

@@ -165,7 +165,8 @@ private:
 	std::vector<DumpHost> dumps;
 
 	// schedule
-	int tune_rows = 4, tune_zchunk = 32, tune_graph = -1;
+	int tune_rows = 4, tune_zchunk = 0 /* 0 = auto */, tune_graph = -1;
+	int auto_zchunk() const;
 	std::vector<std::function<void(cudaStream_t)>> step;
 	std::vector<std::string> labels;
 	unsigned kernels_per_step = 0;
