@@ -1239,8 +1239,12 @@ int Engine::get_stats(oems_cuda_stats* s)
 // block scheduler enough blocks to hide the tail on thin slabs (profiles/experiments_r01.md #5)
 int Engine::auto_zchunk() const
 {
-	const int planes = (int)(ze - zb);
-	return planes >= 512 ? 32 : planes >= 256 ? 16 : 8;
+	const long long planes = (long long)(ze - zb);
+	const long long blocks_xy = (long long)((pitch / 4 + 31) / 32) * ((gn[1] + tune_rows - 1) / tune_rows);
+	const long long want = 16LL * 1184; // ~16 waves of resident 128-thread blocks on 148 SMs
+	for (int zc = 32; zc > 1; zc /= 2)
+		if (blocks_xy * ((planes + zc - 1) / zc) >= want) return zc;
+	return 1; // small meshes: one plane per block, maximum parallelism, shortest dependency chain
 }
 
 int Engine::set_tuning(int rows, int zchunk, int graph_on)
