@@ -167,8 +167,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C5 uniform vacuum %dx%dx%d PML_8x6 centre Ez Gauss source" % n,
-                   "timed_on": "bounded sample %dx%dx%d of the same workload" % sample},
+        "config": {"workload": "C5 uniform vacuum %dx%dx%d PML_8x6 centre Ez Gauss source, 12 probes" % n,
+                   "timed_on": "bounded sample %dx%dx%d of the same workload (same BC, source, dT), all host cores" % sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%dx%dx%d PML_8 mesh, %d timesteps, sse-compressed multithreaded restatement "
                                    "(oracle/fdtd_oracle_sse.c)" % (sample + (steps,))},
@@ -290,8 +290,10 @@ def run_gpu(args):
     eng = make_engine()
     link(eng)
     t_upload = time.perf_counter() - t0
-    h2d = eng.GetStats()["hbm_bytes"] - 2 * 3 * 4 * (cells if slab is None else n[0] * n[1] * (slab[1] - slab[0] + 2))
-    h2d = max(h2d, so.n_unique * 128 + cells * index_bytes // max(world, 1))
+    # bytes copied host->device while creating the engine: coefficient tuples + the per-cell index of
+    # the planes this rank holds (+ a few KB of signal / excitation / probe lists, ignored)
+    held = n[2] if slab is None else (slab[1] - slab[0] + (1 if slab[0] > 0 else 0) + (1 if slab[1] < n[2] else 0))
+    h2d = (so.n_unique * 128 + n[0] * n[1] * held * index_bytes) * world
     done, d2h = 0, 0
     while done < args.steps:
         m = min(burst, args.steps - done)
