@@ -187,7 +187,10 @@ int oems_cuda_get_stats(oems_cuda_engine* h, oems_cuda_stats* out);
 /* tuning knobs (0 keeps the default): block rows and z-chunk of the stencil kernels, graph on/off */
 int oems_cuda_set_tuning(oems_cuda_engine* h, int block_rows, int z_chunk, int use_graph);
 
-/* named integer options (none at present; reserved so that tuning switches do not change the ABI) */
+/* named integer options.  "fused" = 0 / 1 / -1: two-pass (in place), one-pass (E and H in one
+   kernel, ping-pong buffers) or automatic choice of the timestep schedule.  Both give identical
+   results.  One-pass needs a hook set without Lorentz/RLC and memory for the second field set;
+   automatic picks it for meshes without UPML (measured faster there, slower with UPML). */
 int oems_cuda_set_option(oems_cuda_engine* h, const char* key, long long value);
 
 /* measurement aid: runs n_ts timesteps without the graph and returns the average duration in
@@ -202,7 +205,7 @@ const char* oems_cuda_schedule_label(oems_cuda_engine* h, unsigned i);
    torch.distributed / any host channel, and opens them here; the halo planes are then written
    straight into the neighbour's ghost plane by the boundary kernels (no host staging, no
    collective), with device-side flags ordering the steps.  See DESIGN.md "multi-GPU". */
-#define OEMS_IPC_BYTES 256
+#define OEMS_IPC_BYTES 512
 int oems_cuda_export_ipc(oems_cuda_engine* h, unsigned char out[OEMS_IPC_BYTES]);
 int oems_cuda_open_peers(oems_cuda_engine* h, const unsigned char* lower /*OEMS_IPC_BYTES or NULL*/,
                          const unsigned char* upper);

@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATH = os.environ.get("OPENEMS_B200_LIB") or os.path.join(_HERE, "lib", "libopenems_b200.so")
 
-OEMS_IPC_BYTES = 256
+OEMS_IPC_BYTES = 512
 
 
 class LibraryNotBuilt(RuntimeError):

@@ -56,6 +56,10 @@ Engine::~Engine()
 	if (stream) cudaStreamSynchronize(stream);
 	if (graph_exec) cudaGraphExecDestroy(graph_exec);
 	if (graph) cudaGraphDestroy(graph);
+	for (int q = 0; q < 2; ++q) {
+		if (graphf_exec[q]) cudaGraphExecDestroy(graphf_exec[q]);
+		if (graphf[q]) cudaGraphDestroy(graphf[q]);
+	}
 	for (auto& d : dumps) {
 		if (d.h_pinned) cudaFreeHost(d.h_pinned);
 	}
@@ -668,10 +672,23 @@ int Engine::finalize()
 
 	if (build_pml()) return 1;
 	pE.flux = d_flux_v; pH.flux = d_flux_i;
+	sV[0] = d_V; sI[0] = d_I; sFv[0] = d_flux_v; sFi[0] = d_flux_i;
+	// the one-pass schedule needs a second field/flux set and no volume hooks between the half-steps
+	fused_possible = fused_req != 0 && h_lor.empty() && h_rlc.empty();
+	if (fused_possible) {
+		sV[1] = dalloc<float>(nfield);
+		sI[1] = dalloc<float>(nfield);
+		if (has_pml) { sFv[1] = dalloc<float>((size_t)flux_floats); sFi[1] = dalloc<float>((size_t)flux_floats); }
+		if (!sV[1] || !sI[1] || (has_pml && (!sFv[1] || !sFi[1]))) {
+			cudaGetLastError();
+			fused_possible = false; // not enough memory for the ping-pong set: stay with two passes
+		}
+	}
 	if (build_mur()) return 1;
 	if (build_exc()) return 1;
 	if (build_lorentz()) return 1;
 	if (build_rlc()) return 1;
+	if (fused_possible && build_fix_list()) return 1;
 	CK(cudaStreamSynchronize(stream));
 	CK(cudaGetLastError());
 
@@ -695,6 +712,10 @@ void Engine::build_schedule()
 {
 	step.clear();
 	labels.clear();
+	// one-pass schedule: on request, or by default for meshes without UPML -- with UPML the fused
+	// kernel's rare path (3 divergent lanes at both ends of every row in the x slabs) makes it slower
+	// than the two-pass schedule (profiles/experiments_r01.md #9)
+	fused_active = fused_possible && !edge_dirty && (fused_req == 1 || (fused_req < 0 && !has_pml));
 	const bool i16 = index_bytes == 2;
 	const dim3 block(32, tune_rows);
 	auto stencil_grid = [&](const StencilParams& p, int rows_total) {
@@ -773,30 +794,232 @@ void Engine::build_schedule()
 		}));
 	(labels.push_back("tick"), step.push_back([this](cudaStream_t s) { k_tick<<<1, 1, 0, s>>>(d_numTS); }));
 	kernels_per_step = (unsigned)step.size();
+	if (fused_active) build_schedule_fused();
 
 	// ---- capture one timestep into a CUDA graph (launch-bound small meshes)
 	if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
 	if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
-	use_graph = tune_graph != 0;
-	if (use_graph) {
-		if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-			for (auto& f : step) f(stream);
-			if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || !graph ||
-			    cudaGraphInstantiate(&graph_exec, graph, 0) != cudaSuccess) {
-				use_graph = false;
-				cudaGetLastError();
-			}
-		} else {
-			use_graph = false;
-			cudaGetLastError();
-		}
+	for (int q = 0; q < 2; ++q) {
+		if (graphf_exec[q]) { cudaGraphExecDestroy(graphf_exec[q]); graphf_exec[q] = nullptr; }
+		if (graphf[q]) { cudaGraphDestroy(graphf[q]); graphf[q] = nullptr; }
 	}
+	use_graph = tune_graph != 0;
+	auto capture = [&](std::vector<std::function<void(cudaStream_t)>>& list, cudaGraph_t& g, cudaGraphExec_t& ge) {
+		if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+		for (auto& f : list) f(stream);
+		if (cudaStreamEndCapture(stream, &g) != cudaSuccess || !g || cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) {
+			cudaGetLastError();
+			return false;
+		}
+		return true;
+	};
+	if (use_graph) {
+		if (fused_active) use_graph = capture(stepf[0], graphf[0], graphf_exec[0]) && capture(stepf[1], graphf[1], graphf_exec[1]);
+		else use_graph = capture(step, graph, graph_exec);
+	}
+}
+
+// ---------------------------------------------------------------------------- fused schedule
+// H cells whose curl reads an E value that a hook changes after the fused kernel ran:
+// Mur planes (Apply2Voltages overwrites the boundary cells) and soft/hard E sources.
+int Engine::build_fix_list()
+{
+	std::vector<long long> keys; // ((z*ny)+y)*nx+x, global
+	const long long nx = gn[0], ny = gn[1];
+	auto add = [&](int n, long long x, long long y, long long z) {
+		// H cells that read V_n(x,y,z): engine.cpp:179-221
+		const int d1[3][3] = {{0, 0, 1}, {1, 0, 0}, {0, 1, 0}}; // V0: p-z, V1: p-x, V2: p-y  (first partner)
+		const int d2[3][3] = {{0, 1, 0}, {0, 0, 1}, {1, 0, 0}}; // V0: p-y, V1: p-z, V2: p-x  (second partner)
+		const long long c[3][3] = {{x, y, z}, {x - d1[n][0], y - d1[n][1], z - d1[n][2]}, {x - d2[n][0], y - d2[n][1], z - d2[n][2]}};
+		for (int q = 0; q < 3; ++q) {
+			const long long cx = c[q][0], cy = c[q][1], cz = c[q][2];
+			if (cx < 0 || cy < 0 || cz < 0 || cx >= nx - 1 || cy >= ny - 1 || cz >= (long long)gn[2] - 1) continue;
+			if (!owned((unsigned)cz)) continue;
+			keys.push_back((cz * ny + cy) * nx + cx);
+		}
+	};
+	for (const MurHost& M : h_mur) {
+		const int nyP = (M.ny + 1) % 3, nyPP = (M.ny + 2) % 3;
+		for (unsigned a = 0; a < M.n[0]; ++a)
+			for (unsigned b = 0; b < M.n[1]; ++b) {
+				long long pos[3];
+				pos[M.ny] = M.line; pos[nyP] = a; pos[nyPP] = b;
+				add(nyP, pos[0], pos[1], pos[2]);
+				add(nyPP, pos[0], pos[1], pos[2]);
+			}
+	}
+	const ExcHost& E = h_exc[0];
+	for (size_t n = 0; n < E.dir.size(); ++n) add((int)E.dir[n], E.idx[0][n], E.idx[1][n], E.idx[2][n]);
+	std::sort(keys.begin(), keys.end());
+	keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+	fix_count = (long long)keys.size();
+	std::vector<int> cells((size_t)3 * keys.size());
+	for (size_t q = 0; q < keys.size(); ++q) {
+		const long long k = keys[q];
+		cells[3 * q] = (int)(k % nx);
+		cells[3 * q + 1] = (int)((k / nx) % ny);
+		cells[3 * q + 2] = (int)(k / (nx * ny)) - z0;
+	}
+	d_fix_cells = fix_count ? upload(cells) : nullptr;
+	if (fix_count && !d_fix_cells) return fail("out of device memory (fix-up list)");
+	return 0;
+}
+
+void Engine::build_schedule_fused()
+{
+	const bool i16 = index_bytes == 2;
+	const bool multi = peers_linked;
+	labelsf.clear();
+	for (int par = 0; par < 2; ++par) {
+		const int S = par, D = par ^ 1;
+		auto& L = stepf[par];
+		L.clear();
+		auto lab = [&](const char* name) { if (par == 0) labelsf.push_back(name); };
+		// ---- parameter blocks of this parity
+		FusedParams& F = pF[par];
+		memset(&F, 0, sizeof(F));
+		F.Vs = sV[S]; F.Is = sI[S]; F.Vd = sV[D]; F.Id = sI[D];
+		F.fVs = sFv[S]; F.fVd = sFv[D]; F.fIs = sFi[S]; F.fId = sFi[D];
+		F.idx = d_idx;
+		F.eA = d_tab[0]; F.eB = d_tab[1]; F.eP0 = d_tab[2]; F.eP1 = d_tab[3]; F.eP2 = d_tab[4];
+		F.hA = d_tab[5]; F.hB = d_tab[6]; F.hP0 = d_tab[7]; F.hP1 = d_tab[8]; F.hP2 = d_tab[9];
+		F.nx = (int)gn[0]; F.ny = (int)gn[1]; F.nz = nzl;
+		F.pitch = pitch; F.plane = plane; F.comp = comp;
+		F.kE0 = pE.k0; F.kE1 = pE.k1;
+		F.kH0 = pH.k0;
+		F.kH1 = (multi && peer_hi) ? pE.k1 - 1 : pH.k1;   // the slab's top plane waits for the ghost E plane
+		F.kHc1 = (multi && peer_hi) ? F.kH1 : pE.k1;       // planes above kH1 are copied through (top of the domain)
+		F.zchunk = pE.zchunk;
+		F.nboxes = pE.nboxes;
+		for (int b = 0; b < pE.nboxes; ++b) F.box[b] = pE.box[b];
+		FixParams& X = pFix[par];
+		memset(&X, 0, sizeof(X));
+		X.Is = sI[S]; X.Id = sI[D]; X.Vd = sV[D]; X.fIs = sFi[S]; X.fId = sFi[D];
+		X.idx = d_idx;
+		X.hA = d_tab[5]; X.hB = d_tab[6]; X.hP0 = d_tab[7]; X.hP1 = d_tab[8]; X.hP2 = d_tab[9];
+		X.cell = d_fix_cells; X.count = fix_count;
+		X.nx = (int)gn[0]; X.ny = (int)gn[1];
+		X.pitch = pitch; X.plane = plane; X.comp = comp;
+		X.nboxes = pE.nboxes;
+		for (int b = 0; b < pE.nboxes; ++b) X.box[b] = pE.box[b];
+		pMurS[par] = pMur; pMurS[par].V = sV[S];
+		pMurD[par] = pMur; pMurD[par].V = sV[D];
+		pExcD[par][0] = pExc[0]; pExcD[par][0].X = sV[D];
+		pExcD[par][1] = pExc[1]; pExcD[par][1].X = sI[D];
+		StencilParams& T = pHtop[par];
+		T = pH;
+		T.V = sV[D]; T.I = sI[S]; T.Iout = sI[D]; T.flux = sFi[S]; T.flux_out = sFi[D];
+		T.k0 = pE.k1 - 1; T.k1 = pE.k1; T.zchunk = 1;
+
+		// ---- pre-voltage hooks on the source set
+		if (pMur.nplanes) { lab("mur_pre"); L.push_back([this, par](cudaStream_t s) { launch1d(k_mur_pre, pMurS[par], pMurS[par].total, s); }); }
+		if (multi && peer_lo) {
+			lab("halo_wait_H");
+			L.push_back([this](cudaStream_t s) {
+				WaitParams w{d_flagH, d_numTS, 0u, d_halo_err, 4000000000ll};
+				k_halo_wait<<<1, 1, 0, s>>>(w);
+			});
+		}
+		// ---- E and H in one pass (UPML fused)
+		lab("fused_EH");
+		L.push_back([this, par, i16](cudaStream_t s) {
+			const FusedParams& q = pF[par];
+			const dim3 block(32, FUSED_TY + 1);
+			const dim3 g((unsigned)((pitch / 4 + 31) / 32), (unsigned)((q.ny + FUSED_TY - 1) / FUSED_TY),
+			             (unsigned)std::max(1, (q.kE1 - q.kE0 + q.zchunk - 1) / q.zchunk));
+			if (i16) { if (has_pml) k_fused_EH<uint16_t, true><<<g, block, 0, s>>>(q); else k_fused_EH<uint16_t, false><<<g, block, 0, s>>>(q); }
+			else { if (has_pml) k_fused_EH<uint32_t, true><<<g, block, 0, s>>>(q); else k_fused_EH<uint32_t, false><<<g, block, 0, s>>>(q); }
+		});
+		// ---- post / apply voltage hooks on the destination set
+		if (pMur.nplanes) {
+			lab("mur_post"); L.push_back([this, par](cudaStream_t s) { launch1d(k_mur_post, pMurD[par], pMurD[par].total, s); });
+			lab("mur_apply"); L.push_back([this, par](cudaStream_t s) { launch1d(k_mur_apply, pMurD[par], pMurD[par].total, s); });
+		}
+		if (pExc[0].groups) { lab("excite_V"); L.push_back([this, par](cudaStream_t s) { launch1d(k_excite, pExcD[par][0], pExcD[par][0].groups, s); }); }
+		if (multi && peer_lo) {
+			lab("halo_push_E");
+			L.push_back([this, D](cudaStream_t s) {
+				HaloParams h{sV[D], peer_lo_Vs[D], (long long)((int)zb - z0) * plane, peer_lo_ghostE_off, comp, peer_lo_comp, plane,
+				             d_halo_cnt, peer_lo_flagE, d_numTS, 1u};
+				k_halo_push<<<64, 256, 0, s>>>(h);
+			});
+		}
+		// ---- H cells that depend on E values changed by the hooks
+		if (fix_count) {
+			lab("fix_H");
+			L.push_back([this, par, i16](cudaStream_t s) {
+				if (i16) { if (has_pml) launch1d(k_fix_H<uint16_t, true>, pFix[par], pFix[par].count, s); else launch1d(k_fix_H<uint16_t, false>, pFix[par], pFix[par].count, s); }
+				else { if (has_pml) launch1d(k_fix_H<uint32_t, true>, pFix[par], pFix[par].count, s); else launch1d(k_fix_H<uint32_t, false>, pFix[par], pFix[par].count, s); }
+			});
+		}
+		// ---- slab top plane: needs the neighbour's E plane
+		if (multi && peer_hi) {
+			lab("halo_wait_E");
+			L.push_back([this](cudaStream_t s) {
+				WaitParams w{d_flagE, d_numTS, 1u, d_halo_err, 4000000000ll};
+				k_halo_wait<<<1, 1, 0, s>>>(w);
+			});
+			lab("update_H_top");
+			L.push_back([this, par, i16](cudaStream_t s) {
+				const StencilParams& q = pHtop[par];
+				const dim3 block(32, tune_rows);
+				const dim3 g((unsigned)((pitch / 4 + 31) / 32), (unsigned)((q.ny + tune_rows - 1) / tune_rows), 1);
+				if (i16) { if (has_pml) k_update_H<uint16_t, true><<<g, block, 0, s>>>(q); else k_update_H<uint16_t, false><<<g, block, 0, s>>>(q); }
+				else { if (has_pml) k_update_H<uint32_t, true><<<g, block, 0, s>>>(q); else k_update_H<uint32_t, false><<<g, block, 0, s>>>(q); }
+			});
+		}
+		if (pExc[1].groups) { lab("excite_I"); L.push_back([this, par](cudaStream_t s) { launch1d(k_excite, pExcD[par][1], pExcD[par][1].groups, s); }); }
+		if (multi && peer_hi) {
+			lab("halo_push_H");
+			L.push_back([this, D](cudaStream_t s) {
+				HaloParams h{sI[D], peer_hi_Is[D], (long long)((int)ze - 1 - z0) * plane, peer_hi_ghostH_off, comp, peer_hi_comp, plane,
+				             d_halo_cnt + 1, peer_hi_flagH, d_numTS, 1u};
+				k_halo_push<<<64, 256, 0, s>>>(h);
+			});
+		}
+		lab("tick");
+		L.push_back([this](cudaStream_t s) { k_tick<<<1, 1, 0, s>>>(d_numTS); });
+	}
+	kernels_per_step = (unsigned)stepf[0].size();
+}
+
+// switching between the one-pass and the two-pass schedule keeps the current fields: the two-pass
+// kernels work in place on set 0
+int Engine::set_fused_active(int req)
+{
+	const bool on = fused_possible && !edge_dirty && (req == 1 || (req < 0 && !has_pml));
+	CK(cudaStreamSynchronize(stream));
+	if (fused_active && !on && (numTS_host & 1u)) {
+		const size_t nfield = (size_t)3 * comp;
+		CK(cudaMemcpyAsync(sV[0], sV[1], nfield * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+		CK(cudaMemcpyAsync(sI[0], sI[1], nfield * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+		if (has_pml) {
+			CK(cudaMemcpyAsync(sFv[0], sFv[1], (size_t)flux_floats * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+			CK(cudaMemcpyAsync(sFi[0], sFi[1], (size_t)flux_floats * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+		}
+		CK(cudaStreamSynchronize(stream));
+	}
+	if (!fused_active && on && fused_possible && (numTS_host & 1u)) {
+		// odd timestep count: the current state must sit in set 1
+		const size_t nfield = (size_t)3 * comp;
+		CK(cudaMemcpyAsync(sV[1], sV[0], nfield * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+		CK(cudaMemcpyAsync(sI[1], sI[0], nfield * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+		if (has_pml) {
+			CK(cudaMemcpyAsync(sFv[1], sFv[0], (size_t)flux_floats * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+			CK(cudaMemcpyAsync(sFi[1], sFi[0], (size_t)flux_floats * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+		}
+		CK(cudaStreamSynchronize(stream));
+	}
+	fused_req = req;
+	build_schedule();
+	return 0;
 }
 
 void Engine::launch_probes(double* dst)
 {
 	if (!n_values) return;
 	ProbeParams p = pProbe;
+	p.V = sV[cur()]; p.I = sI[cur()];
 	p.out = dst;
 	const unsigned wpb = 4;
 	k_probes<<<(p.nprobes + wpb - 1) / wpb, wpb * 32, 0, stream>>>(p);
@@ -810,7 +1033,11 @@ int Engine::iterate(unsigned n)
 	if (!probes_built && !h_probes.empty())
 		if (build_probes()) return 1;
 	for (unsigned it = 0; it < n; ++it) {
-		if (use_graph) {
+		if (fused_active) {
+			const int par = (int)(numTS_host & 1u);
+			if (use_graph) CK(cudaGraphLaunch(graphf_exec[par], stream));
+			else for (auto& f : stepf[par]) f(stream);
+		} else if (use_graph) {
 			CK(cudaGraphLaunch(graph_exec, stream));
 		} else {
 			for (auto& f : step) f(stream);
@@ -830,7 +1057,12 @@ int Engine::iterate(unsigned n)
 int Engine::set_option(const char* key, long long value)
 {
 	const std::string k = key ? key : "";
-	(void)value;
+	if (k == "fused") {
+		// 0: two-pass, 1: one-pass (if the hook set allows it), -1: automatic
+		if (!finalized) { fused_req = value < 0 ? -1 : (value != 0); return 0; }
+		if (value > 0 && edge_dirty) return 0;
+		return set_fused_active(value < 0 ? -1 : (value != 0));
+	}
 	// no options at present.  (An "L2-blocked" launch order -- E kernel on a few planes, then the
 	// H kernel one plane behind so that it reads from L2 -- was measured in round 1 and was 1.7x
 	// SLOWER at 1024^3: see profiles/experiments_r01.md.)
@@ -877,11 +1109,14 @@ int Engine::reset()
 	CK(cudaSetDevice(device));
 	CK(cudaStreamSynchronize(stream));
 	const size_t nfield = (size_t)3 * comp;
-	CK(cudaMemsetAsync(d_V, 0, nfield * sizeof(float), stream));
-	CK(cudaMemsetAsync(d_I, 0, nfield * sizeof(float), stream));
-	if (has_pml) {
-		CK(cudaMemsetAsync(d_flux_v, 0, (size_t)flux_floats * sizeof(float), stream));
-		CK(cudaMemsetAsync(d_flux_i, 0, (size_t)flux_floats * sizeof(float), stream));
+	for (int q = 0; q < 2; ++q) {
+		if (!sV[q]) continue;
+		CK(cudaMemsetAsync(sV[q], 0, nfield * sizeof(float), stream));
+		CK(cudaMemsetAsync(sI[q], 0, nfield * sizeof(float), stream));
+		if (has_pml && sFv[q]) {
+			CK(cudaMemsetAsync(sFv[q], 0, (size_t)flux_floats * sizeof(float), stream));
+			CK(cudaMemsetAsync(sFi[q], 0, (size_t)flux_floats * sizeof(float), stream));
+		}
 	}
 	if (pMur.nplanes) {
 		CK(cudaMemsetAsync(pMur.vP, 0, (size_t)pMur.total * sizeof(float), stream));
@@ -1063,7 +1298,7 @@ int Engine::energy(double* e)
 	if (!finalized) return fail("energy: engine not finalized");
 	CK(cudaSetDevice(device));
 	EnergyParams p;
-	p.V = d_V; p.I = d_I;
+	p.V = sV[cur()]; p.I = sI[cur()];
 	p.nx = (int)gn[0]; p.ny = (int)gn[1];
 	p.k0 = (int)zb - z0; p.k1 = (int)std::min(ze, gn[2] - 1) - z0;
 	p.pitch = pitch; p.plane = plane; p.comp = comp;
@@ -1122,6 +1357,7 @@ int Engine::read_dump(int id, float* out)
 	if (id < 0 || id >= (int)dumps.size()) return fail("read_dump: bad id");
 	CK(cudaSetDevice(device));
 	DumpHost& D = dumps[id];
+	D.p.V = sV[cur()]; D.p.I = sI[cur()];
 	launch1d(k_dump, D.p, (long long)D.count, stream);
 	++kernels_launched;
 	CK(cudaMemcpyAsync(D.h_pinned, D.d_out, 3 * D.count * sizeof(float), cudaMemcpyDeviceToHost, stream));
@@ -1136,7 +1372,7 @@ int Engine::get_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned 
 	if (!finalized) return fail("get_field: engine not finalized");
 	if (n > 2 || x >= gn[0] || y >= gn[1] || !held(z)) return fail("get_field: position not on this engine");
 	CK(cudaSetDevice(device));
-	const float* base = is_curr ? d_I : d_V;
+	const float* base = is_curr ? sI[cur()] : sV[cur()];
 	CK(cudaMemcpyAsync(v, base + n * comp + cell_off(x, y, z), sizeof(float), cudaMemcpyDeviceToHost, stream));
 	CK(cudaStreamSynchronize(stream));
 	return 0;
@@ -1146,7 +1382,7 @@ int Engine::set_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned 
 	if (!finalized) return fail("set_field: engine not finalized");
 	if (n > 2 || x >= gn[0] || y >= gn[1] || !held(z)) return fail("set_field: position not on this engine");
 	CK(cudaSetDevice(device));
-	float* base = is_curr ? d_I : d_V;
+	float* base = is_curr ? sI[cur()] : sV[cur()];
 	CK(cudaMemcpyAsync(base + n * comp + cell_off(x, y, z), &v, sizeof(float), cudaMemcpyHostToDevice, stream));
 	CK(cudaStreamSynchronize(stream));
 	if (is_curr && (x == gn[0] - 1 || y == gn[1] - 1 || z == gn[2] - 1)) mark_edge_dirty();
@@ -1158,7 +1394,7 @@ int Engine::get_fields(int is_curr, float* out)
 	if (!finalized) return fail("get_fields: engine not finalized");
 	CK(cudaSetDevice(device));
 	std::vector<float> h((size_t)3 * comp);
-	CK(cudaMemcpyAsync(h.data(), is_curr ? d_I : d_V, h.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+	CK(cudaMemcpyAsync(h.data(), is_curr ? sI[cur()] : sV[cur()], h.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
 	CK(cudaStreamSynchronize(stream));
 	const unsigned nx = gn[0], ny = gn[1];
 #pragma omp parallel for collapse(2) schedule(static)
@@ -1181,7 +1417,7 @@ int Engine::set_fields(int is_curr, const float* in)
 			for (unsigned j = 0; j < ny; ++j)
 				for (int k = 0; k < nzl; ++k)
 					h[n * comp + (long long)k * plane + (long long)j * pitch + i] = in[(((size_t)n * nx + i) * ny + j) * nzl + k];
-	CK(cudaMemcpyAsync(is_curr ? d_I : d_V, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+	CK(cudaMemcpyAsync(is_curr ? sI[cur()] : sV[cur()], h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
 	CK(cudaStreamSynchronize(stream));
 	if (is_curr) mark_edge_dirty();
 	return 0;
@@ -1194,8 +1430,7 @@ void Engine::mark_edge_dirty()
 {
 	if (edge_dirty || !pEdge.count) return;
 	edge_dirty = true;
-	cudaStreamSynchronize(stream);
-	build_schedule();
+	set_fused_active(0); // the one-pass schedule does not carry this rare path; also rebuilds the schedule
 }
 
 int Engine::get_upml_flux(int box, int is_curr, float* out)
@@ -1209,7 +1444,7 @@ int Engine::get_upml_flux(int box, int is_curr, float* out)
 	if (B.ln[2] == 0) return 0;
 	const long long cs = (long long)B.ln[0] * B.ln[1] * B.ln[2];
 	std::vector<float> h((size_t)3 * cs);
-	CK(cudaMemcpyAsync(h.data(), (is_curr ? d_flux_i : d_flux_v) + B.flux_off, h.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+	CK(cudaMemcpyAsync(h.data(), (is_curr ? sFi[cur()] : sFv[cur()]) + B.flux_off, h.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
 	CK(cudaStreamSynchronize(stream));
 	for (int n = 0; n < 3; ++n)
 		for (int li = 0; li < B.ln[0]; ++li)
@@ -1271,7 +1506,7 @@ int Engine::time_schedule(unsigned n_ts, double* ms_out, unsigned cap, unsigned*
 {
 	if (!finalized) return fail("time_schedule: engine not finalized");
 	CK(cudaSetDevice(device));
-	const size_t ne = step.size();
+	const size_t ne = fused_active ? stepf[0].size() : step.size();
 	if (n_entries) *n_entries = (unsigned)ne;
 	if (cap < ne) return fail("time_schedule: output too small");
 	std::vector<cudaEvent_t> ev(ne + 1);
@@ -1280,7 +1515,8 @@ int Engine::time_schedule(unsigned n_ts, double* ms_out, unsigned cap, unsigned*
 	for (unsigned it = 0; it < n_ts; ++it) {
 		for (size_t q = 0; q < ne; ++q) {
 			CK(cudaEventRecord(ev[q], stream));
-			step[q](stream);
+			if (fused_active) stepf[numTS_host & 1u][q](stream);
+			else step[q](stream);
 		}
 		CK(cudaEventRecord(ev[ne], stream));
 		CK(cudaStreamSynchronize(stream));
@@ -1299,7 +1535,8 @@ int Engine::time_schedule(unsigned n_ts, double* ms_out, unsigned cap, unsigned*
 
 // ------------------------------------------------------------------------------ multi-GPU
 struct IpcBlob {
-	cudaIpcMemHandle_t hV, hI, hFlags;
+	cudaIpcMemHandle_t hV, hI, hFlags, hV1, hI1;
+	int has_set1;
 	long long comp, plane;
 	int z0, nzl, zb, ze, pitch, ny;
 	int device;
@@ -1315,6 +1552,11 @@ int Engine::export_ipc(unsigned char* out)
 	CK(cudaIpcGetMemHandle(&b.hV, d_V));
 	CK(cudaIpcGetMemHandle(&b.hI, d_I));
 	CK(cudaIpcGetMemHandle(&b.hFlags, d_flagE));
+	b.has_set1 = sV[1] != nullptr;
+	if (b.has_set1) {
+		CK(cudaIpcGetMemHandle(&b.hV1, sV[1]));
+		CK(cudaIpcGetMemHandle(&b.hI1, sI[1]));
+	}
 	b.comp = comp; b.plane = plane; b.z0 = z0; b.nzl = nzl; b.zb = (int)zb; b.ze = (int)ze; b.pitch = pitch; b.ny = (int)gn[1];
 	b.device = device;
 	memset(out, 0, OEMS_IPC_BYTES);
@@ -1337,6 +1579,13 @@ int Engine::open_peers(const unsigned char* lower, const unsigned char* upper)
 		CK(cudaIpcOpenMemHandle(&pF, b.hFlags, cudaIpcMemLazyEnablePeerAccess));
 		ipc_opened.push_back(pV); ipc_opened.push_back(pF);
 		peer_lo_V = (float*)pV;
+		peer_lo_Vs[0] = peer_lo_V;
+		if (b.has_set1) {
+			void* pV1 = nullptr;
+			CK(cudaIpcOpenMemHandle(&pV1, b.hV1, cudaIpcMemLazyEnablePeerAccess));
+			ipc_opened.push_back(pV1);
+			peer_lo_Vs[1] = (float*)pV1;
+		} else fused_possible = false;
 		peer_lo_flagE = (unsigned*)pF; // neighbour's flagE
 		peer_lo_comp = b.comp;
 		peer_lo_ghostE_off = (long long)((int)zb - b.z0) * plane;
@@ -1351,6 +1600,13 @@ int Engine::open_peers(const unsigned char* lower, const unsigned char* upper)
 		CK(cudaIpcOpenMemHandle(&pF, b.hFlags, cudaIpcMemLazyEnablePeerAccess));
 		ipc_opened.push_back(pI); ipc_opened.push_back(pF);
 		peer_hi_I = (float*)pI;
+		peer_hi_Is[0] = peer_hi_I;
+		if (b.has_set1) {
+			void* pI1 = nullptr;
+			CK(cudaIpcOpenMemHandle(&pI1, b.hI1, cudaIpcMemLazyEnablePeerAccess));
+			ipc_opened.push_back(pI1);
+			peer_hi_Is[1] = (float*)pI1;
+		} else fused_possible = false;
 		peer_hi_flagH = (unsigned*)pF + 1; // neighbour's flagH
 		peer_hi_comp = b.comp;
 		peer_hi_ghostH_off = (long long)((int)ze - 1 - b.z0) * plane;
@@ -1382,11 +1638,15 @@ int Engine::link_peers(Engine* lower, Engine* upper)
 	if (lower) {
 		if (lower->pitch != pitch || lower->ze != zb) return fail("link_peers: lower neighbour does not match");
 		peer_lo_V = lower->d_V; peer_lo_flagE = lower->d_flagE; peer_lo_comp = lower->comp;
+		peer_lo_Vs[0] = lower->sV[0]; peer_lo_Vs[1] = lower->sV[1];
+		if (!lower->sV[1] || !lower->fused_possible) fused_possible = false;
 		peer_lo_ghostE_off = (long long)((int)zb - lower->z0) * plane;
 	}
 	if (upper) {
 		if (upper->pitch != pitch || upper->zb != ze) return fail("link_peers: upper neighbour does not match");
 		peer_hi_I = upper->d_I; peer_hi_flagH = upper->d_flagH; peer_hi_comp = upper->comp;
+		peer_hi_Is[0] = upper->sI[0]; peer_hi_Is[1] = upper->sI[1];
+		if (!upper->sI[1] || !upper->fused_possible) fused_possible = false;
 		peer_hi_ghostH_off = (long long)((int)ze - 1 - upper->z0) * plane;
 	}
 	peers_linked = lower || upper;

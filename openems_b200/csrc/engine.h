@@ -10,6 +10,7 @@
 
 #include "../../include/openems_b200.h"
 #include "kernels.cuh"
+#include "kernels_fused.cuh"
 
 struct UpmlBoxHost {
 	unsigned start[3], n[3];          // global
@@ -100,7 +101,11 @@ public:
 	int get_stats(oems_cuda_stats* s);
 	int set_tuning(int rows, int zchunk, int use_graph);
 	int time_schedule(unsigned n_ts, double* ms_out, unsigned cap, unsigned* n_entries);
-	const char* schedule_label(unsigned i) const { return i < labels.size() ? labels[i].c_str() : ""; }
+	const char* schedule_label(unsigned i) const
+	{
+		const std::vector<std::string>& L = fused_active ? labelsf : labels;
+		return i < L.size() ? L[i].c_str() : "";
+	}
 	int export_ipc(unsigned char* out);
 	int open_peers(const unsigned char* lower, const unsigned char* upper);
 	int link_peers(Engine* lower, Engine* upper);
@@ -174,6 +179,27 @@ private:
 	cudaGraph_t graph = nullptr;
 	cudaGraphExec_t graph_exec = nullptr;
 	bool use_graph = false;
+
+	// fused one-pass timestep (kernels_fused.cuh): ping-pong field/flux sets, one schedule per parity
+	float *sV[2] = {nullptr, nullptr}, *sI[2] = {nullptr, nullptr}, *sFv[2] = {nullptr, nullptr}, *sFi[2] = {nullptr, nullptr};
+	int fused_req = -1; // -1 automatic, 0 two-pass, 1 one-pass
+	bool fused_possible = false, fused_active = false;
+	int cur() const { return fused_active ? (int)(numTS_host & 1u) : 0; }
+	std::vector<std::function<void(cudaStream_t)>> stepf[2];
+	std::vector<std::string> labelsf;
+	cudaGraph_t graphf[2] = {nullptr, nullptr};
+	cudaGraphExec_t graphf_exec[2] = {nullptr, nullptr};
+	FusedParams pF[2];
+	FixParams pFix[2];
+	StencilParams pHtop[2];
+	MurParams pMurS[2], pMurD[2];
+	ExcParams pExcD[2][2];
+	int* d_fix_cells = nullptr;
+	long long fix_count = 0;
+	int build_fix_list();
+	void build_schedule_fused();
+	int set_fused_active(int req);
+	float *peer_lo_Vs[2] = {nullptr, nullptr}, *peer_hi_Is[2] = {nullptr, nullptr};
 
 	// multi-GPU
 	Engine *peer_lo = nullptr, *peer_hi = nullptr;

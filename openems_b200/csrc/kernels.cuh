@@ -43,6 +43,10 @@ struct StencilParams {
 	const float4* tP1;
 	const float4* tP2;
 	float* flux;
+	// out-of-place mode of k_update_H (slab top plane of the fused schedule): results go to Iout /
+	// flux_out, every cell of the planes is written (cells outside the update range are copied)
+	float* Iout;
+	float* flux_out;
 	int nx, ny, nz;      // lines held by this GPU (nz = local planes incl. ghosts)
 	int pitch;
 	long long plane;     // pitch*ny
@@ -119,12 +123,12 @@ __device__ __forceinline__ float leap(float X, float m_vv, float m_vi, float cur
 	return fadd(fmul(X, m_vv), fmul(m_vi, curl));
 }
 __device__ __forceinline__ float leap_pml(float X, float m_vv, float m_vi, float curl, float a_vv,
-                                          float a_fn, float a_fo, float* fluxp)
+                                          float a_fn, float a_fo, const float* flux_in, float* flux_out)
 {
-	const float F = *fluxp;
+	const float F = *flux_in;
 	const float f = fsub(fmul(a_vv, X), fmul(a_fo, F));
 	const float Fn = fadd(fmul(F, m_vv), fmul(m_vi, curl));
-	*fluxp = Fn;
+	*flux_out = Fn;
 	return fadd(f, fmul(a_fn, Fn));
 }
 
@@ -202,9 +206,9 @@ __global__ void __launch_bounds__(256, OEMS_MIN_BLOCKS) k_update_E(const __grid_
 					const long long fo = pml_flux_offset(p, ic + c, j, k, cs);
 					const float4 P0 = __ldg(p.tP0 + e[c]), P1 = __ldg(p.tP1 + e[c]), P2 = __ldg(p.tP2 + e[c]);
 					if (fo >= 0) {
-						setcomp(v0, c, leap_pml(comp(v0, c), A.x, B.x, curl0, P0.x, P1.x, P2.x, p.flux + fo));
-						setcomp(v1, c, leap_pml(comp(v1, c), A.y, B.y, curl1, P0.y, P1.y, P2.y, p.flux + fo + cs));
-						setcomp(v2, c, leap_pml(comp(v2, c), A.z, B.z, curl2, P0.z, P1.z, P2.z, p.flux + fo + 2 * cs));
+						setcomp(v0, c, leap_pml(comp(v0, c), A.x, B.x, curl0, P0.x, P1.x, P2.x, p.flux + fo, p.flux + fo));
+						setcomp(v1, c, leap_pml(comp(v1, c), A.y, B.y, curl1, P0.y, P1.y, P2.y, p.flux + fo + cs, p.flux + fo + cs));
+						setcomp(v2, c, leap_pml(comp(v2, c), A.z, B.z, curl2, P0.z, P1.z, P2.z, p.flux + fo + 2 * cs, p.flux + fo + 2 * cs));
 					}
 				} else {
 					setcomp(v0, c, leap(comp(v0, c), A.x, B.x, curl0));
@@ -233,17 +237,23 @@ __global__ void __launch_bounds__(256, OEMS_MIN_BLOCKS) k_update_H(const __grid_
 	const int j = blockIdx.y * blockDim.y + threadIdx.y;
 	const int kb = p.k0 + blockIdx.z * p.zchunk;
 	const int ke = min(kb + p.zchunk, p.k1);
-	if (j >= p.ny - 1 || kb >= ke) return;
+	const bool oop = p.Iout != nullptr;
+	if (j >= p.ny - (oop ? 0 : 1) || kb >= ke) return;
+	const bool upd = j < p.ny - 1; // the last row is only copied (out-of-place mode)
 	const bool active = i0 < p.pitch;
 	const int ic = active ? i0 : 0;
 	const long long row = (long long)j * p.pitch + ic;
-	const long long rowp = (long long)(j + 1) * p.pitch + ic;
+	const long long rowp = (long long)(upd ? j + 1 : j) * p.pitch + ic;
 	const float* __restrict__ V0 = p.V;
 	const float* __restrict__ V1 = p.V + p.comp;
 	const float* __restrict__ V2 = p.V + 2 * p.comp;
-	float* I0 = p.I;
-	float* I1 = p.I + p.comp;
-	float* I2 = p.I + 2 * p.comp;
+	const float* I0 = p.I;
+	const float* I1 = p.I + p.comp;
+	const float* I2 = p.I + 2 * p.comp;
+	float* O0 = oop ? p.Iout : p.I;
+	float* O1 = O0 + p.comp;
+	float* O2 = O0 + 2 * p.comp;
+	float* fout = (oop && p.flux_out) ? p.flux_out : p.flux;
 	const bool has_right = ic + 4 < p.pitch;
 
 	float4 v0c, v1c;
@@ -284,7 +294,7 @@ __global__ void __launch_bounds__(256, OEMS_MIN_BLOCKS) k_update_H(const __grid_
 #pragma unroll
 			for (int c = 0; c < 4; ++c) {
 				if (c > 0 && !uni) { A = __ldg(p.tA + e[c]); B = __ldg(p.tB + e[c]); }
-				if (ic + c < p.nx - 1) {
+				if (upd && ic + c < p.nx - 1) {
 					const float curl0 = fadd(fsub(fsub(comp(v2c, c), comp(v2jp, c)), comp(v1c, c)), comp(v1n, c));
 					const float curl1 = fadd(fsub(fsub(comp(v0c, c), comp(v0n, c)), comp(v2c, c)), comp(v2xp, c));
 					const float curl2 = fadd(fsub(fsub(comp(v1c, c), comp(v1xp, c)), comp(v0c, c)), comp(v0jp, c));
@@ -293,9 +303,9 @@ __global__ void __launch_bounds__(256, OEMS_MIN_BLOCKS) k_update_H(const __grid_
 						const long long fo = pml_flux_offset(p, ic + c, j, k, cs);
 						const float4 P0 = __ldg(p.tP0 + e[c]), P1 = __ldg(p.tP1 + e[c]), P2 = __ldg(p.tP2 + e[c]);
 						if (fo >= 0) {
-							setcomp(c0, c, leap_pml(comp(c0, c), A.x, B.x, curl0, P0.x, P1.x, P2.x, p.flux + fo));
-							setcomp(c1, c, leap_pml(comp(c1, c), A.y, B.y, curl1, P0.y, P1.y, P2.y, p.flux + fo + cs));
-							setcomp(c2, c, leap_pml(comp(c2, c), A.z, B.z, curl2, P0.z, P1.z, P2.z, p.flux + fo + 2 * cs));
+							setcomp(c0, c, leap_pml(comp(c0, c), A.x, B.x, curl0, P0.x, P1.x, P2.x, p.flux + fo, fout + fo));
+							setcomp(c1, c, leap_pml(comp(c1, c), A.y, B.y, curl1, P0.y, P1.y, P2.y, p.flux + fo + cs, fout + fo + cs));
+							setcomp(c2, c, leap_pml(comp(c2, c), A.z, B.z, curl2, P0.z, P1.z, P2.z, p.flux + fo + 2 * cs, fout + fo + 2 * cs));
 						}
 					} else {
 						setcomp(c0, c, leap(comp(c0, c), A.x, B.x, curl0));
@@ -304,9 +314,9 @@ __global__ void __launch_bounds__(256, OEMS_MIN_BLOCKS) k_update_H(const __grid_
 					}
 				}
 			}
-			st4s(I0 + o, c0);
-			st4s(I1 + o, c1);
-			st4s(I2 + o, c2);
+			st4s(O0 + o, c0);
+			st4s(O1 + o, c1);
+			st4s(O2 + o, c2);
 		}
 		v0c = v0n;
 		v1c = v1n;

@@ -67,3 +67,28 @@ def test_materials_and_metal():
     s = cases.uniform_box(n=(30, 24, 36), bc=(BC_PML, BC_PML, BC_MUR, BC_PEC, BC_PMC, BC_PML), pml=6,
                           materials=mats, metals=metals)
     run_both(s, steps=(1, 30, 150), what="materials")
+
+
+def test_one_pass_and_two_pass_schedules_agree_and_are_used():
+    """the fused one-pass timestep is the default when the hook set allows it; switching it off
+    gives the two-pass schedule; both match the oracle bit for bit, also when toggled mid-run"""
+    s = cases.engine_cavity()
+    op = operator_from_oracle(s)
+    eng = op.CreateEngine()
+    # automatic choice: this mesh has UPML -> two-pass; a mesh without UPML -> one-pass
+    assert "fused_EH" not in [n for n, _ in eng.TimeSchedule(0)]
+    s2 = cases.uniform_box(n=(27, 11, 33), bc=(BC_MUR, BC_MUR, BC_PMC, BC_PEC, BC_PEC, BC_MUR))
+    e2 = operator_from_oracle(s2).CreateEngine()
+    assert "fused_EH" in [n for n, _ in e2.TimeSchedule(0)]
+    s2.iterate(90)
+    e2.IterateTS(90)
+    assert_fields_equal(e2, s2, "automatic one-pass, Mur/PMC/PEC")
+    total = 0
+    for n, fused in ((3, 1), (4, 0), (5, 1), (31, 1), (2, 0), (40, 1)):
+        eng.SetOption("fused", fused)
+        names = [x for x, _ in eng.TimeSchedule(0)]
+        assert ("fused_EH" in names) == bool(fused)
+        s.iterate(n)
+        eng.IterateTS(n)
+        total += n
+        assert_fields_equal(eng, s, "fused=%d after %d" % (fused, total))

@@ -14,11 +14,15 @@ for name, bc in (("PEC", [0] * 6), ("PML z", [0, 0, 0, 0, 3, 3]), ("PML y", [0, 
     so.add_excitation((n // 2, n // 2, n // 2 + 0.5), (n // 2, n // 2, n // 2 + 0.5), EXC_E_SOFT, (0, 0, 1))
     so.build()
     eng = so.CreateEngine()
-    eng.IterateTS(5)
-    t = {}
-    for k, ms in eng.TimeSchedule(8):
-        t[k] = t.get(k, 0) + ms
-    st = eng.GetStats()
-    print("%-8s pml_cells %10d  update_E %.3f ms  update_H %.3f ms  step %.3f ms  %.0f MC/s"
-          % (name, st["pml_cells"], t["update_E"], t["update_H"], sum(t.values()), n ** 3 / sum(t.values()) / 1e3), flush=True)
+    for fused in (1, 0):
+        eng.SetOption("fused", fused)
+        eng.IterateTS(6)
+        t = {}
+        for k, ms in eng.TimeSchedule(8):
+            t[k] = t.get(k, 0) + ms
+        st = eng.GetStats()
+        ms_graph = eng.IterateTimed(20) / 20
+        print("%-8s fused=%d pml_cells %10d  %s  step(events) %.3f ms  step(graph) %.3f ms  %.0f MC/s"
+              % (name, fused, st["pml_cells"], " ".join("%s %.3f" % (k, v) for k, v in t.items() if v > 0.02), sum(t.values()),
+                 ms_graph, n ** 3 / ms_graph / 1e3), flush=True)
     eng.close()
