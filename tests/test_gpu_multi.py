@@ -11,11 +11,16 @@ from openems_b200.slabs import slab_range, held_range, link_engines_in_process
 pytestmark = pytest.mark.gpu
 
 
-def run_slabs(s, bounds, devices, steps=(1, 2, 40), probes=False):
+def run_slabs(s, bounds, devices, steps=(1, 2, 40), fused=None):
     op = operator_from_oracle(s)
     nz = s.N[2]
     engines = [op.CreateEngine(device=devices[r], slab=(bounds[r], bounds[r + 1])) for r in range(len(bounds) - 1)]
+    if fused is not None:
+        for e in engines:
+            e.SetOption("fused", fused)
     link_engines_in_process(engines)
+    if fused:
+        assert all("fused_EH" in [n for n, _ in e.TimeSchedule(0)] for e in engines)
     total = 0
     for n in steps:
         s.iterate(n)
@@ -46,6 +51,16 @@ def test_two_slabs_one_gpu_pml():
 def test_three_uneven_slabs_one_gpu_mixed_bc():
     s = cases.engine_cavity()
     run_slabs(s, [0, 9, 20, 33], [0, 0, 0], steps=(1, 3, 60))
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_slabs_one_pass_and_two_pass(fused):
+    """both timestep schedules on z-slabs (the one-pass schedule does the slab's top plane after
+    the neighbour's E plane has arrived), UPML + Mur + PMC mix and a Mur-only mesh"""
+    s = cases.engine_cavity()
+    run_slabs(s, [0, 12, 21, 33], [0, 0, 0], steps=(1, 2, 45), fused=fused)
+    s = cases.uniform_box(n=(20, 22, 30), bc=(BC_MUR,) * 6)
+    run_slabs(s, [0, 15, 30], [0, 0], steps=(1, 3, 50), fused=fused)
 
 
 def test_two_gpus():
