@@ -107,6 +107,15 @@ int oems_cuda_add_rlc(oems_cuda_engine* h, unsigned count, const int* dir, const
                       const float* ilv, const float* i2v, const float* vvd, const float* vv2,
                       const float* vj1, const float* vj2, const float* ib0, const float* b1,
                       const float* b2);
+/* Operator_Ext_SteadyState (created by the driver for periodic excitations, openems.cpp:1206-1234):
+   m_TS_period and the E probe list m_E_probe_pos / m_E_probe_dir
+   (FDTD/extensions/operator_ext_steadystate.h).  The probe voltages are recorded on the device
+   every timestep; oems_cuda_steadystate_check evaluates Engine_Ext_SteadyState::Apply2Voltages
+   (engine_ext_steadystate.cpp:50-107) for the last completed period and returns what
+   GetLastDiff() would (1 until two periods have passed). */
+int oems_cuda_add_steadystate(oems_cuda_engine* h, unsigned period_ts, unsigned count,
+                              const unsigned* pos3, const unsigned* dir);
+int oems_cuda_steadystate_check(oems_cuda_engine* h, double* last_diff, unsigned* n_checks);
 /* ends the upload: compresses, moves everything to HBM, fixes the extension schedule in the
    order of Engine::SortExtensionByPriority (FDTD/engine.cpp:87-98) and captures the
    per-timestep CUDA graph.  Replaces Engine::Init (engine.cpp:51-59). */

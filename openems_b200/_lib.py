@@ -51,6 +51,8 @@ SIGNATURES = {
     "oems_cuda_add_mur": (C.c_int, [_vp, C.c_int, C.c_uint, C.c_uint, C.c_uint * 2, _fp, _fp, C.c_uint]),
     "oems_cuda_add_lorentz": (C.c_int, [_vp, C.c_uint, _up] + [_fp] * 6),
     "oems_cuda_add_rlc": (C.c_int, [_vp, C.c_uint, _ip, _up] + [_fp] * 9),
+    "oems_cuda_add_steadystate": (C.c_int, [_vp, C.c_uint, C.c_uint, _up, _up]),
+    "oems_cuda_steadystate_check": (C.c_int, [_vp, _dp, _up]),
     "oems_cuda_finalize": (C.c_int, [_vp]),
     "oems_cuda_iterate": (C.c_int, [_vp, C.c_uint]),
     "oems_cuda_iterate_timed": (C.c_int, [_vp, C.c_uint, _dp]),

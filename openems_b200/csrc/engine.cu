@@ -271,6 +271,63 @@ int Engine::add_rlc(unsigned count, const int* dir, const unsigned* pos3, const 
 	return 0;
 }
 
+int Engine::add_steadystate(unsigned period_ts, unsigned count, const unsigned* pos3, const unsigned* dir)
+{
+	if (finalized) return fail("engine already finalized");
+	if (slab_set) return fail("add_steadystate: not supported on a z-slab engine yet");
+	if (period_ts == 0 || count == 0) return fail("add_steadystate: empty");
+	for (unsigned n = 0; n < count; ++n) {
+		if (dir[n] > 2) return fail("add_steadystate: bad direction");
+		for (int a = 0; a < 3; ++a)
+			if (pos3[(size_t)a * count + n] >= gn[a]) return fail("add_steadystate: position outside the mesh");
+	}
+	ss_period = period_ts;
+	ss_pos.assign(pos3, pos3 + (size_t)3 * count);
+	ss_dir.assign(dir, dir + count);
+	return 0;
+}
+
+// Engine_Ext_SteadyState::Apply2Voltages (engine_ext_steadystate.cpp:62-106) evaluated on the host
+// from the device snapshot of the last completed period
+int Engine::steadystate_check(double* last_diff, unsigned* n_checks)
+{
+	if (!ss_on) return fail("steadystate_check: no steady-state detection set up");
+	CK(cudaSetDevice(device));
+	const unsigned p = ss_period, cnt = pSs.count;
+	unsigned info[2];
+	double en[4];
+	CK(cudaMemcpyAsync(info, pSs.info, sizeof(info), cudaMemcpyDeviceToHost, stream));
+	CK(cudaMemcpyAsync(en, pSs.energy, sizeof(en), cudaMemcpyDeviceToHost, stream));
+	std::vector<double> snap((size_t)2 * p * cnt);
+	CK(cudaMemcpyAsync(snap.data(), pSs.snap, snap.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	if (n_checks) *n_checks = info[0];
+	double diff = 1.0;
+	if (info[0] > 0) {
+		bool no_valid = true;
+		diff = 0;
+		if (en[2] > 0) { diff = std::fabs(en[3] - en[2]) / en[2]; no_valid = false; }
+		const unsigned rel_pos = info[1] % (2 * p);
+		unsigned old_pos = 0, new_pos = p;
+		if (rel_pos <= p) { new_pos = 0; old_pos = p; }
+		std::vector<double> curr_pow(cnt, 0.0), diff_pow(cnt, 0.0);
+		double max_pow = 0;
+		for (unsigned n = 0; n < cnt; ++n) {
+			for (unsigned nt = 0; nt < p; ++nt) {
+				const double a = snap[(size_t)(nt + new_pos) * cnt + n], b = snap[(size_t)(nt + old_pos) * cnt + n];
+				curr_pow[n] += a * a;
+				diff_pow[n] += (b - a) * (b - a);
+			}
+			max_pow = std::max(max_pow, curr_pow[n]);
+		}
+		for (unsigned n = 0; n < cnt; ++n)
+			if (curr_pow[n] > max_pow * 1e-2) { diff = std::max(diff, diff_pow[n] / curr_pow[n]); no_valid = false; }
+		if (no_valid || diff > 1) diff = 1;
+	}
+	if (last_diff) *last_diff = diff;
+	return 0;
+}
+
 // ------------------------------------------------------------------------------ compression
 // Re-keys the operator per cell: the 12 stencil coefficients plus, inside UPML
 // boxes, the 18 auxiliary coefficients form one 128-byte tuple; equal tuples (memcmp, like
@@ -688,6 +745,27 @@ int Engine::finalize()
 	if (build_exc()) return 1;
 	if (build_lorentz()) return 1;
 	if (build_rlc()) return 1;
+	ss_on = false;
+	if (ss_period) {
+		const unsigned cnt = (unsigned)ss_dir.size();
+		std::vector<long long> off(cnt);
+		for (unsigned n = 0; n < cnt; ++n)
+			off[n] = (long long)ss_dir[n] * comp + cell_off(ss_pos[n], ss_pos[(size_t)cnt + n], ss_pos[(size_t)2 * cnt + n]);
+		memset(&pSs, 0, sizeof(pSs));
+		pSs.V = d_V; pSs.I = d_I;
+		pSs.off = upload(off);
+		pSs.rec = dalloc<double>((size_t)2 * ss_period * cnt);
+		pSs.snap = dalloc<double>((size_t)2 * ss_period * cnt);
+		pSs.energy = dalloc<double>(4);
+		pSs.info = dalloc<unsigned>(2);
+		pSs.numTS = d_numTS;
+		pSs.period = ss_period; pSs.count = cnt;
+		pSs.nx = (int)gn[0]; pSs.ny = (int)gn[1];
+		pSs.k0 = (int)zb - z0; pSs.k1 = (int)std::min(ze, gn[2] - 1) - z0;
+		pSs.pitch = pitch; pSs.plane = plane; pSs.comp = comp;
+		if (!pSs.off || !pSs.rec || !pSs.snap || !pSs.energy || !pSs.info) return fail("out of device memory (steady state)");
+		ss_on = true;
+	}
 	if (fused_possible && build_fix_list()) return 1;
 	CK(cudaStreamSynchronize(stream));
 	CK(cudaGetLastError());
@@ -748,7 +826,13 @@ void Engine::build_schedule()
 		}));
 	// ---- post-voltage hooks (UPML fused), then Mur post
 	if (pMur.nplanes) (labels.push_back("mur_post"), step.push_back([this](cudaStream_t s) { launch1d(k_mur_post, pMur, pMur.total, s); }));
-	// ---- apply-voltage hooks in list order: RLC, Lorentz, Mur, Excitation
+	// ---- apply-voltage hooks in list order: SteadyState, RLC, Lorentz, Mur, Excitation
+	auto ss_launch = [this](const SsParams& q, cudaStream_t s) {
+		k_ss_record<<<(q.count + 63) / 64, 64, 0, s>>>(q);
+		k_ss_energy<<<148 * 2, dim3(32, 8), 0, s>>>(q);
+		k_ss_snapshot<<<8, 256, 0, s>>>(q);
+	};
+	if (ss_on) (labels.push_back("steadystate"), step.push_back([this, ss_launch](cudaStream_t s) { ss_launch(pSs, s); }));
 	for (size_t r = rlc_dev.size(); r-- > 0;) // same priority: reversed insertion order
 		(labels.push_back("rlc_apply"), step.push_back([this, r](cudaStream_t s) { launch1d(k_rlc_apply, rlc_dev[r], rlc_dev[r].count, s); }));
 	for (size_t o = 0; o < lor_dev.size(); ++o)
@@ -933,6 +1017,18 @@ void Engine::build_schedule_fused()
 		// ---- post / apply voltage hooks on the destination set
 		if (pMur.nplanes) {
 			lab("mur_post"); L.push_back([this, par](cudaStream_t s) { launch1d(k_mur_post, pMurD[par], pMurD[par].total, s); });
+		}
+		if (ss_on) {
+			pSsF[par] = pSs; pSsF[par].V = sV[D]; pSsF[par].I = sI[S];
+			lab("steadystate");
+			L.push_back([this, par](cudaStream_t s) {
+				const SsParams& q = pSsF[par];
+				k_ss_record<<<(q.count + 63) / 64, 64, 0, s>>>(q);
+				k_ss_energy<<<148 * 2, dim3(32, 8), 0, s>>>(q);
+				k_ss_snapshot<<<8, 256, 0, s>>>(q);
+			});
+		}
+		if (pMur.nplanes) {
 			lab("mur_apply"); L.push_back([this, par](cudaStream_t s) { launch1d(k_mur_apply, pMurD[par], pMurD[par].total, s); });
 		}
 		if (pExc[0].groups) { lab("excite_V"); L.push_back([this, par](cudaStream_t s) { launch1d(k_excite, pExcD[par][0], pExcD[par][0].groups, s); }); }
@@ -1132,6 +1228,12 @@ int Engine::reset()
 		CK(cudaMemsetAsync(R.Vd, 0, (size_t)3 * R.count * sizeof(float), stream));
 		CK(cudaMemsetAsync(R.J, 0, (size_t)3 * R.count * sizeof(float), stream));
 		CK(cudaMemsetAsync(R.Il, 0, (size_t)R.count * sizeof(float), stream));
+	}
+	if (ss_on) {
+		CK(cudaMemsetAsync(pSs.rec, 0, (size_t)2 * ss_period * pSs.count * sizeof(double), stream));
+		CK(cudaMemsetAsync(pSs.snap, 0, (size_t)2 * ss_period * pSs.count * sizeof(double), stream));
+		CK(cudaMemsetAsync(pSs.energy, 0, 4 * sizeof(double), stream));
+		CK(cudaMemsetAsync(pSs.info, 0, 2 * sizeof(unsigned), stream));
 	}
 	CK(cudaMemsetAsync(d_numTS, 0, sizeof(unsigned), stream));
 	CK(cudaMemsetAsync(d_flagE, 0, 8 * sizeof(unsigned), stream));

@@ -74,6 +74,8 @@ public:
 	int add_mur(int ny, unsigned line, unsigned shift, const unsigned n[2], const float* cP, const float* cPP, unsigned start_ts);
 	int add_lorentz(unsigned count, const unsigned* pos3, const float* const c[6]);
 	int add_rlc(unsigned count, const int* dir, const unsigned* pos3, const float* const c[9]);
+	int add_steadystate(unsigned period_ts, unsigned count, const unsigned* pos3, const unsigned* dir);
+	int steadystate_check(double* last_diff, unsigned* n_checks);
 	int finalize();
 
 	int iterate(unsigned n);
@@ -135,6 +137,10 @@ private:
 	std::vector<LorHost> h_lor;
 	std::vector<RlcHost> h_rlc;
 	std::vector<ProbeHost> h_probes;
+	unsigned ss_period = 0;
+	std::vector<unsigned> ss_pos, ss_dir;
+	SsParams pSs{}, pSsF[2];
+	bool ss_on = false;
 
 	// device
 	float *d_V = nullptr, *d_I = nullptr;

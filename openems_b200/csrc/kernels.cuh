@@ -664,6 +664,69 @@ __global__ void k_energy(const __grid_constant__ EnergyParams p)
 }
 
 // ---------------------------------------------------------------------------------------
+// Steady-state detection: Engine_Ext_SteadyState::Apply2Voltages engine_ext_steadystate.cpp:50-107.
+// Every timestep the probe voltages go into a 2-period ring; when a period completes
+// (TS % p == 0, TS >= 2p) the energy estimate of that instant (E after the stencil, H before its
+// update) is taken and ring + energies are snapshotted for the host, which evaluates the
+// criterion without per-step read-backs.
+// ---------------------------------------------------------------------------------------
+struct SsParams {
+	const float* V; const float* I;
+	const long long* off;   // [count] voltage offsets incl. component
+	double* rec;            // ring [2p][count]
+	double* snap;           // snapshot of the ring at the last completed period
+	double* energy;         // [0],[1] scratch sums V^2, I^2 ; [2] previous, [3] current period energy
+	unsigned* info;         // [0] number of completed checks, [1] TS of the last one
+	const unsigned* numTS;
+	unsigned period, count;
+	int nx, ny, k0, k1;
+	int pitch; long long plane, comp;
+};
+__device__ __forceinline__ bool ss_due(const SsParams& p) { const unsigned ts = *p.numTS; return ts % p.period == 0 && ts >= 2 * p.period; }
+__global__ void k_ss_record(const __grid_constant__ SsParams p)
+{
+	const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned ts = *p.numTS;
+	if (n < p.count) p.rec[(size_t)(ts % (2 * p.period)) * p.count + n] = (double)p.V[p.off[n]];
+	if (n == 0 && ss_due(p)) { p.energy[0] = 0.0; p.energy[1] = 0.0; }
+}
+__global__ void k_ss_energy(const __grid_constant__ SsParams p)
+{
+	if (!ss_due(p)) return;
+	double e = 0.0, h = 0.0;
+	const long long rows = (long long)(p.k1 - p.k0) * (p.ny - 1);
+	for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y) {
+		const int k = p.k0 + (int)(r / (p.ny - 1));
+		const int j = (int)(r % (p.ny - 1));
+		const long long o = (long long)k * p.plane + (long long)j * p.pitch;
+		for (int i = threadIdx.x; i < p.nx - 1; i += blockDim.x)
+#pragma unroll
+			for (int n = 0; n < 3; ++n) {
+				const float v = p.V[n * p.comp + o + i], c = p.I[n * p.comp + o + i];
+				e += (double)fmul(v, v);
+				h += (double)fmul(c, c);
+			}
+	}
+	for (int s = 16; s > 0; s >>= 1) {
+		e += __shfl_down_sync(0xffffffffu, e, s);
+		h += __shfl_down_sync(0xffffffffu, h, s);
+	}
+	if (threadIdx.x == 0) { atomicAdd(p.energy, e); atomicAdd(p.energy + 1, h); }
+}
+__global__ void k_ss_snapshot(const __grid_constant__ SsParams p)
+{
+	if (!ss_due(p)) return;
+	const size_t n = (size_t)2 * p.period * p.count;
+	for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) p.snap[q] = p.rec[q];
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		p.energy[2] = p.energy[3];
+		p.energy[3] = 8.85418781762e-12 * p.energy[0] + 1.256637062e-6 * p.energy[1];
+		p.info[0] += 1;
+		p.info[1] = *p.numTS;
+	}
+}
+
+// ---------------------------------------------------------------------------------------
 // Field dump: ProcessFields::CalcField processfields.cpp:283-409 + interpolation
 // engine_interface_fdtd.cpp:63-124 (E) / :150-204 (H), evaluated in fp64 like the reference
 // and stored as fp32 in {3,nz,ny,nx} order, x fastest.

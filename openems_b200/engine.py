@@ -60,6 +60,7 @@ class Operator_CUDA:
         self.mur = []
         self.lorentz = []
         self.rlc = []
+        self.steadystate = None
         self.mesh = None  # (x, y, z, gridDelta) for field probes / dumps
 
     # ---- Operator::GetNumberOfLines / SetVV.. / GetVV.. (FDTD/operator.h:215-218)
@@ -114,6 +115,21 @@ class Operator_CUDA:
 
     def AddLorentzOrder(self, pos3, v_int=None, v_ext=None, v_lor=None, i_int=None, i_ext=None, i_lor=None):
         self.lorentz.append((_u32(pos3), [None if a is None else _f32(a) for a in (v_int, v_ext, v_lor, i_int, i_ext, i_lor)]))
+
+    def SetSteadyStateDetection(self, period_ts, pos3=None, direction=None):
+        """Operator_Ext_SteadyState; without an explicit probe list the driver's default set is
+        used (openems.cpp:1206-1234: centre node plus, per axis, the node with that coordinate
+        set to 0 -- the `pos[n] *= 1/4` of the reference is integer arithmetic -- twice)"""
+        if pos3 is None:
+            c = [n // 2 for n in self.numLines]
+            pts = [tuple(c)]
+            for n in range(3):
+                q = list(c)
+                q[n] = 0
+                pts += [tuple(q), tuple(q)]
+            pos3 = np.array([[p[a] for p in pts for _ in range(3)] for a in range(3)], np.uint32)
+            direction = np.array([d for _ in pts for d in range(3)], np.uint32)
+        self.steadystate = (int(period_ts), _u32(pos3), _u32(direction))
 
     def AddLumpedRLC(self, direction, pos3, coeffs):
         names = ("ilv", "i2v", "vvd", "vv2", "vj1", "vj2", "ib0", "b1", "b2")
@@ -201,6 +217,9 @@ class Engine_CUDA:
                 self._ck(L.oems_cuda_add_lorentz(h, pos3.shape[1], _ptr(pos3, _up), *[_ptr(a, _fp) for a in co]))
             for d, pos3, co in op.rlc:
                 self._ck(L.oems_cuda_add_rlc(h, len(d), _ptr(d, _ip), _ptr(pos3, _up), *[_ptr(a, _fp) for a in co]))
+            if op.steadystate is not None:
+                per, pos3, d = op.steadystate
+                self._ck(L.oems_cuda_add_steadystate(h, per, len(d), _ptr(pos3, _up), _ptr(d, _up)))
             self._ck(L.oems_cuda_finalize(h))
         self._initialized = True
 
@@ -321,6 +340,12 @@ class Engine_CUDA:
         ts = np.zeros(max(cap, 1), np.uint32)
         self._ck(self._L.oems_cuda_read_probe_series(self._h, _ptr(out, _dp), _ptr(ts, _up), cap, C.byref(n)))
         return ts[: n.value].copy(), out[: n.value].copy()
+
+    def SteadyStateLastDiff(self):
+        """Engine_Ext_SteadyState::GetLastDiff(): (last_max_diff, number of completed period checks)"""
+        d, n = C.c_double(), C.c_uint()
+        self._ck(self._L.oems_cuda_steadystate_check(self._h, C.byref(d), C.byref(n)))
+        return d.value, n.value
 
     def CalcFastEnergy(self):
         e = C.c_double()

@@ -250,6 +250,7 @@ void orc_destroy(orc_sim* s)
 		free(R->ib0); free(R->b1); free(R->b2); free(R->Il);
 	}
 	free(s->rlc);
+	if (s->ss) { free(s->ss->dir); for (int n = 0; n < 3; ++n) free(s->ss->pos[n]); free(s->ss->rec); free(s->ss); }
 	free(s->volt); free(s->curr);
 	free(s);
 }
@@ -1301,6 +1302,67 @@ static void rlc_applyV(orc_sim* s, ext_t* e, int tid, int nth)
 	}
 }
 
+/* Engine_Ext_SteadyState::Apply2Voltages engine_ext_steadystate.cpp:50-107 */
+static void ss_applyV(orc_sim* s, ext_t* e, int tid, int nth)
+{
+	if (tid != 0) return;
+	(void)nth;
+	ss_t* S = e->data;
+	const unsigned p = S->period, TS = s->numTS, rel_pos = TS % (2 * p);
+	for (unsigned n = 0; n < S->count; ++n) {
+		unsigned pos[3] = {S->pos[0][n], S->pos[1][n], S->pos[2][n]};
+		S->rec[(size_t)n * 2 * p + rel_pos] = VOLT(s, S->dir[n], pos);
+	}
+	if ((TS % p == 0) && (TS >= 2 * p)) {
+		int no_valid = 1;
+		S->last_max_diff = 0;
+		double curr_total_energy = orc_energy(s);
+		if (S->last_total_energy > 0) {
+			S->last_max_diff = fabs(curr_total_energy - S->last_total_energy) / S->last_total_energy;
+			no_valid = 0;
+		}
+		S->last_total_energy = curr_total_energy;
+		unsigned old_pos = 0, new_pos = p;
+		if (rel_pos <= p) { new_pos = 0; old_pos = p; }
+		double max_pow = 0;
+		double* curr_pow = xcalloc(S->count, sizeof(double));
+		double* diff_pow = xcalloc(S->count, sizeof(double));
+		for (unsigned n = 0; n < S->count; ++n) {
+			const double* buf = S->rec + (size_t)n * 2 * p;
+			for (unsigned nt = 0; nt < p; ++nt) {
+				curr_pow[n] += buf[nt + new_pos] * buf[nt + new_pos];
+				diff_pow[n] += (buf[nt + old_pos] - buf[nt + new_pos]) * (buf[nt + old_pos] - buf[nt + new_pos]);
+			}
+			if (curr_pow[n] > max_pow) max_pow = curr_pow[n];
+		}
+		for (unsigned n = 0; n < S->count; ++n)
+			if (curr_pow[n] > max_pow * 1e-2) {
+				if (diff_pow[n] / curr_pow[n] > S->last_max_diff) S->last_max_diff = diff_pow[n] / curr_pow[n];
+				no_valid = 0;
+			}
+		if (no_valid || S->last_max_diff > 1) S->last_max_diff = 1;
+		free(curr_pow); free(diff_pow);
+	}
+}
+
+int orc_add_steadystate(orc_sim* s, unsigned period_ts, unsigned count, const unsigned* pos3, const int* dir)
+{
+	if (s->ss || period_ts == 0) return -1;
+	ss_t* S = xcalloc(1, sizeof(ss_t));
+	S->period = period_ts; S->count = count;
+	S->dir = xcalloc(count, sizeof(int));
+	memcpy(S->dir, dir, count * sizeof(int));
+	for (int n = 0; n < 3; ++n) {
+		S->pos[n] = xcalloc(count, sizeof(unsigned));
+		memcpy(S->pos[n], pos3 + (size_t)n * count, count * sizeof(unsigned));
+	}
+	S->rec = xcalloc((size_t)count * 2 * period_ts, sizeof(double));
+	S->last_max_diff = 1; S->last_total_energy = 0;
+	s->ss = S;
+	return 0;
+}
+double orc_steadystate_last_diff(const orc_sim* s) { return s->ss ? s->ss->last_max_diff : 1.0; }
+
 static void add_ext(orc_sim* s, int prio, void* data, hook_fn preV, hook_fn postV, hook_fn applyV,
                     hook_fn preI, hook_fn postI, hook_fn applyI)
 {
@@ -1390,6 +1452,8 @@ int orc_build(orc_sim* s, unsigned max_ts)
 		build_upml_box(s, &s->upml[b]);
 		add_ext(s, PRIO_UPML, &s->upml[b], upml_preV, upml_postV, NULL, upml_preI, upml_postI, NULL);
 	}
+	/* Operator_Ext_SteadyState is inserted after UPML and before Lorentz (openems.cpp:1206-1236) */
+	if (s->ss) add_ext(s, PRIO_STEADYSTATE, s->ss, NULL, NULL, ss_applyV, NULL, NULL, NULL);
 	build_lorentz(s);
 	if (s->lor_order > 0)
 		add_ext(s, PRIO_DEFAULT, NULL, lor_preV, NULL, lor_applyV, lor_preI, NULL, lor_applyI);

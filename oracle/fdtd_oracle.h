@@ -66,6 +66,11 @@ int orc_add_rlc_raw(orc_sim* s, unsigned count, const int* dir, const unsigned* 
                     const float* vj1, const float* vj2, const float* ib0, const float* b1,
                     const float* b2);
 
+/* steady-state detection: Engine_Ext_SteadyState engine_ext_steadystate.cpp:50-107 with the
+   probe set of openems.cpp:1206-1234; pos3 is [3][count]. */
+int    orc_add_steadystate(orc_sim* s, unsigned period_ts, unsigned count, const unsigned* pos3, const int* dir);
+double orc_steadystate_last_diff(const orc_sim* s);
+
 /* ---- excitation signal, FDTD/excitation.cpp:150-276 */
 void orc_set_excite_gauss(orc_sim* s, double f0, double fc);
 void orc_set_excite_sinus(orc_sim* s, double f0);

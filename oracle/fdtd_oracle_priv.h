@@ -61,6 +61,14 @@ typedef struct {
 	float *Vdn[3], *Jn[3], *Il;
 } rlc_t;
 
+typedef struct {
+	unsigned period, count;
+	int* dir;
+	unsigned* pos[3];
+	double* rec;          /* [count][2*period] */
+	double last_max_diff, last_total_energy;
+} ss_t;
+
 struct ext_s;
 typedef void (*hook_fn)(orc_sim*, struct ext_s*, int tid, int nth);
 typedef struct ext_s {
@@ -73,6 +81,7 @@ typedef struct ext_s {
 #define PRIO_DEFAULT 0
 #define PRIO_UPML 1000000
 #define PRIO_EXCITATION (-1000)
+#define PRIO_STEADYSTATE 2000000
 
 struct orc_sim {
 	unsigned N[3];
@@ -104,6 +113,7 @@ struct orc_sim {
 	mur_t mur[6]; int nmur;
 	int lor_order; lor_order_t lor[MAX_ORDER];
 	rlc_t* rlc; int nrlc;
+	ss_t* ss;
 
 	/* engine */
 	float *volt, *curr;

@@ -56,6 +56,8 @@ def lib():
         "orc_add_excitation": (C.c_int, [vp, C.c_int, _d3, _d3, C.c_int, _d3, C.c_double]),
         "orc_add_lumped_rc": (C.c_int, [vp, _d3, _d3, C.c_int, C.c_double, C.c_double, C.c_int]),
         "orc_add_rlc_raw": (C.c_int, [vp, C.c_uint, C.POINTER(C.c_int), _up] + [_fp] * 9),
+        "orc_add_steadystate": (C.c_int, [vp, C.c_uint, C.c_uint, _up, C.POINTER(C.c_int)]),
+        "orc_steadystate_last_diff": (C.c_double, [vp]),
         "orc_set_excite_gauss": (None, [vp, C.c_double, C.c_double]),
         "orc_set_excite_sinus": (None, [vp, C.c_double]),
         "orc_set_excite_dirac": (None, [vp, C.c_double]),
@@ -184,6 +186,14 @@ class OracleSim:
         arrs = [np.ascontiguousarray(coeffs[k], dtype=np.float32) for k in names]
         return lib().orc_add_rlc_raw(self._h, len(d), d.ctypes.data_as(C.POINTER(C.c_int)),
                                      p.ctypes.data_as(_up), *[a.ctypes.data_as(_fp) for a in arrs])
+
+    def add_steadystate(self, period_ts, pos3, direction):
+        p = np.ascontiguousarray(pos3, dtype=np.uint32)
+        d = np.ascontiguousarray(direction, dtype=np.int32)
+        return lib().orc_add_steadystate(self._h, int(period_ts), len(d), p.ctypes.data_as(_up), d.ctypes.data_as(C.POINTER(C.c_int)))
+
+    def steadystate_last_diff(self):
+        return lib().orc_steadystate_last_diff(self._h)
 
     def set_excite_gauss(self, f0, fc):
         lib().orc_set_excite_gauss(self._h, f0, fc)

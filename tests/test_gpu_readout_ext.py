@@ -220,3 +220,36 @@ def test_upml_cells_outside_h_update_follow_reference():
         s.iterate(nsteps)
         eng.IterateTS(nsteps)
         assert_fields_equal(eng, s, "poked last-line currents")
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_steady_state_detection_sinus(fused):
+    """Engine_Ext_SteadyState with the stock sinus-excited parallel plate
+    waveguide (C1): the device-recorded criterion equals the reference's, period by period"""
+    from tests import configs
+    s0, _ = configs.c1_parallel_plate_waveguide("sinus")
+    sv, si, period = s0.signal()
+    assert period > 0
+    op = operator_from_oracle(s0)
+    op.SetSteadyStateDetection(period)
+    per, pos3, d = op.steadystate
+    # the oracle with the same probe set (it must be added before build -> rebuild the case)
+    from oracle.pyoracle import OracleSim, BC_PEC, BC_PMC, BC_MUR, EXC_E_SOFT
+    s = OracleSim(s0.x, s0.y, s0.z, 1.0)
+    s.set_bc([BC_PMC, BC_PMC, BC_PEC, BC_PEC, BC_MUR, BC_MUR])
+    s.set_excite_sinus(10e6)
+    s.add_excitation((-10, -10, 0), (10, 10, 0), EXC_E_SOFT, (0, 1, 0))
+    s.add_steadystate(per, pos3, d.astype(np.int32))
+    s.build()
+    eng = op.CreateEngine()
+    eng.SetOption("fused", fused)
+    checks = 0
+    for it in range(9):
+        n = per if it else per + 1   # stop right after the timestep with TS % period == 0
+        s.iterate(n)
+        eng.IterateTS(n)
+        got, checks = eng.SteadyStateLastDiff()
+        ref = s.steadystate_last_diff()
+        assert got == pytest.approx(ref, rel=1e-9, abs=1e-300), (it, got, ref)
+    assert checks >= 7 and 0 < ref < 1
+    assert_fields_equal(eng, s, "steady state run")
