@@ -123,9 +123,14 @@ def add_c5_probes(eng, n):
         eng.AddFieldProbe(1, p)
 
 
-def algorithmic_bytes(n, pml_cells, index_bytes):
-    """per half-step 36 B field traffic + index per cell, + 24 B per PML cell (flux r/w)"""
+def algorithmic_bytes(n, pml_cells, index_bytes, one_pass=False):
+    """SURVEY 8(d).  Two-pass schedule: per half-step 36 B field traffic + index per cell, + 24 B
+    per PML cell (flux r/w).  One-pass schedule (k_fused_EH): E and H read once and written once
+    = 48 B + index per cell and launch; per step the UPML flux r/w of both half-steps on top."""
     cells = n[0] * n[1] * n[2]
+    if one_pass:
+        per_launch = cells * (48 + index_bytes)
+        return per_launch, per_launch + pml_cells * 48
     per_half = cells * (36 + index_bytes) + pml_cells * 24
     return per_half, 2 * per_half
 
@@ -257,14 +262,18 @@ def run_gpu(args):
     # ---------------- per-kernel timing (CUDA events on the engine's stream) for the roofline
     sched = eng.TimeSchedule(min(10, max(3, args.steps // 10)))
     local_cells = cells if slab is None else n[0] * n[1] * (slab[1] - slab[0])
-    per_half, per_step = algorithmic_bytes((n[0], n[1], local_cells // (n[0] * n[1])), pml_cells, index_bytes)
     peak, peak_src = measured_peak()
     kern = {}
     for name, ms in sched:
         kern[name] = kern.get(name, 0.0) + ms
-    t_E, t_H = kern.get("update_E", 0.0), kern.get("update_H", 0.0)
-    dom = "update_E" if t_E >= t_H else "update_H"
-    t_dom = max(t_E, t_H)
+    one_pass = "fused_EH" in kern
+    per_half, per_step = algorithmic_bytes((n[0], n[1], local_cells // (n[0] * n[1])), pml_cells, index_bytes, one_pass)
+    if one_pass:
+        dom, t_dom = "fused_EH", kern["fused_EH"]
+    else:
+        t_E, t_H = kern.get("update_E", 0.0), kern.get("update_H", 0.0)
+        dom = "update_E" if t_E >= t_H else "update_H"
+        t_dom = max(t_E, t_H)
     achieved = per_half / (t_dom * 1e-3) / 1e9 if t_dom > 0 else 0.0
     traffic = None
     try:
@@ -317,6 +326,7 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C5 uniform vacuum %dx%dx%d PML_8x6 centre Ez Gauss source, 12 probes" % n,
                        "parallelism": "z-slabs x%d over NVLink peer memory" % world if world > 1 else "single GPU",
+                       "schedule": "one-pass (k_fused_EH + UPML shell)" if one_pass else "two-pass (k_update_E, k_update_H)",
                        "l2": "inputs (%.1f GB of fields+index per GPU) far larger than the 126 MB L2; no flush needed"
                              % ((24 + index_bytes) * local_cells / 1e9),
                        "n_unique_coeff_tuples": so.n_unique, "index_bytes": index_bytes, "pml_cells": pml_cells,

@@ -198,8 +198,9 @@ int oems_cuda_set_tuning(oems_cuda_engine* h, int block_rows, int z_chunk, int u
 
 /* named integer options.  "fused" = 0 / 1 / -1: two-pass (in place), one-pass (E and H in one
    kernel, ping-pong buffers) or automatic choice of the timestep schedule.  Both give identical
-   results.  One-pass needs a hook set without Lorentz/RLC and memory for the second field set;
-   automatic picks it for meshes without UPML (measured faster there, slower with UPML). */
+   results.  One-pass needs a hook set without Lorentz/RLC, disjoint UPML boxes and memory for
+   the second field set; automatic picks it whenever that holds.  UPML cells stay on a two-pass
+   "shell" (k_shell_E / k_shell_H) around the one-pass interior. */
 int oems_cuda_set_option(oems_cuda_engine* h, const char* key, long long value);
 
 /* measurement aid: runs n_ts timesteps without the graph and returns the average duration in

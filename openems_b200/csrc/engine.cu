@@ -491,6 +491,14 @@ int Engine::build_pml()
 	}
 	pE.nboxes = pH.nboxes = nb;
 	has_pml = nb > 0;
+	pml_disjoint = true;
+	for (int a = 0; a < nb; ++a)
+		for (int b = a + 1; b < nb; ++b) {
+			bool overlap = true;
+			for (int d = 0; d < 3; ++d)
+				overlap &= pE.box[a].s[d] < pE.box[b].s[d] + pE.box[b].n[d] && pE.box[b].s[d] < pE.box[a].s[d] + pE.box[a].n[d];
+			if (overlap) pml_disjoint = false;
+		}
 	if (has_pml) {
 		d_flux_v = dalloc<float>((size_t)flux_floats);
 		d_flux_i = dalloc<float>((size_t)flux_floats);
@@ -729,14 +737,14 @@ int Engine::finalize()
 
 	if (build_pml()) return 1;
 	pE.flux = d_flux_v; pH.flux = d_flux_i;
-	sV[0] = d_V; sI[0] = d_I; sFv[0] = d_flux_v; sFi[0] = d_flux_i;
-	// the one-pass schedule needs a second field/flux set and no volume hooks between the half-steps
-	fused_possible = fused_req != 0 && h_lor.empty() && h_rlc.empty();
+	sV[0] = d_V; sI[0] = d_I;
+	// the one-pass schedule needs a second field set, no volume hooks between the half-steps and
+	// disjoint UPML boxes (each is updated by its own shell launch)
+	fused_possible = fused_req != 0 && h_lor.empty() && h_rlc.empty() && pml_disjoint;
 	if (fused_possible) {
 		sV[1] = dalloc<float>(nfield);
 		sI[1] = dalloc<float>(nfield);
-		if (has_pml) { sFv[1] = dalloc<float>((size_t)flux_floats); sFi[1] = dalloc<float>((size_t)flux_floats); }
-		if (!sV[1] || !sI[1] || (has_pml && (!sFv[1] || !sFi[1]))) {
+		if (!sV[1] || !sI[1]) {
 			cudaGetLastError();
 			fused_possible = false; // not enough memory for the ping-pong set: stay with two passes
 		}
@@ -790,10 +798,9 @@ void Engine::build_schedule()
 {
 	step.clear();
 	labels.clear();
-	// one-pass schedule: on request, or by default for meshes without UPML -- with UPML the fused
-	// kernel's rare path (3 divergent lanes at both ends of every row in the x slabs) makes it slower
-	// than the two-pass schedule (profiles/experiments_r01.md #9)
-	fused_active = fused_possible && !edge_dirty && (fused_req == 1 || (fused_req < 0 && !has_pml));
+	// one-pass schedule whenever it is possible (second field set allocated, no Lorentz/RLC hooks,
+	// UPML edge path not in use) unless the two-pass schedule was requested
+	fused_active = fused_possible && !edge_dirty && fused_req != 0;
 	const bool i16 = index_bytes == 2;
 	const dim3 block(32, tune_rows);
 	auto stencil_grid = [&](const StencilParams& p, int rows_total) {
@@ -963,36 +970,83 @@ void Engine::build_schedule_fused()
 		FusedParams& F = pF[par];
 		memset(&F, 0, sizeof(F));
 		F.Vs = sV[S]; F.Is = sI[S]; F.Vd = sV[D]; F.Id = sI[D];
-		F.fVs = sFv[S]; F.fVd = sFv[D]; F.fIs = sFi[S]; F.fId = sFi[D];
 		F.idx = d_idx;
-		F.eA = d_tab[0]; F.eB = d_tab[1]; F.eP0 = d_tab[2]; F.eP1 = d_tab[3]; F.eP2 = d_tab[4];
-		F.hA = d_tab[5]; F.hB = d_tab[6]; F.hP0 = d_tab[7]; F.hP1 = d_tab[8]; F.hP2 = d_tab[9];
+		F.eA = d_tab[0]; F.eB = d_tab[1];
+		F.hA = d_tab[5]; F.hB = d_tab[6];
 		F.nx = (int)gn[0]; F.ny = (int)gn[1]; F.nz = nzl;
 		F.pitch = pitch; F.plane = plane; F.comp = comp;
 		F.kE0 = pE.k0; F.kE1 = pE.k1;
 		F.kH0 = pH.k0;
 		F.kH1 = (multi && peer_hi) ? pE.k1 - 1 : pH.k1;   // the slab's top plane waits for the ghost E plane
 		F.kHc1 = (multi && peer_hi) ? F.kH1 : pE.k1;       // planes above kH1 are copied through (top of the domain)
-		F.zchunk = pE.zchunk;
-		F.nboxes = pE.nboxes;
-		for (int b = 0; b < pE.nboxes; ++b) F.box[b] = pE.box[b];
+		F.zchunk = has_pml ? std::min(pE.zchunk, 63) : pE.zchunk; // the kernel keeps one shell bit per plane of a chunk
+		// UPML shell: all boxes of a half-step in one launch (kernels_fused.cuh)
+		ShellParams& SE = pShE[par];
+		ShellParams& SH = pShH[par];
+		memset(&SE, 0, sizeof(SE));
+		SE.idx = d_idx;
+		SE.nx = (int)gn[0]; SE.ny = (int)gn[1]; SE.pitch = pitch; SE.plane = plane; SE.comp = comp;
+		SE.nboxes = pE.nboxes;
+		SH = SE;
+		SE.Xs = sV[S]; SE.Xd = sV[S]; SE.Y = sI[S]; // in place: see kernels_fused.cuh
+		SE.tA = d_tab[0]; SE.tB = d_tab[1]; SE.tP0 = d_tab[2]; SE.tP1 = d_tab[3]; SE.tP2 = d_tab[4];
+		SH.Xs = sI[S]; SH.Xd = sI[D]; SH.Y = sV[D];
+		SH.tA = d_tab[5]; SH.tB = d_tab[6]; SH.tP0 = d_tab[7]; SH.tP1 = d_tab[8]; SH.tP2 = d_tab[9];
+		F.nsh = pE.nboxes;
+		for (int b = 0; b < pE.nboxes; ++b) {
+			const PmlBox& B = pE.box[b];
+			F.sh[b].c0 = B.s[0] / 4; F.sh[b].cn = (B.s[0] + B.n[0] - 1) / 4 - F.sh[b].c0 + 1;
+			F.sh[b].j0 = B.s[1]; F.sh[b].jn = B.n[1];
+			F.sh[b].k0 = B.s[2]; F.sh[b].kn = B.n[2];
+			ShellBoxParams q;
+			memset(&q, 0, sizeof(q));
+			q.cs = (long long)B.n[0] * B.n[1] * B.n[2];
+			q.bs0 = B.s[0]; q.bs1 = B.s[1]; q.bs2 = B.s[2]; q.bn0 = B.n[0]; q.bn1 = B.n[1];
+			q.c0 = F.sh[b].c0; q.nchunk = F.sh[b].cn;
+			// lanes side by side in x: the smallest power of two that covers the box
+			q.xl = q.nchunk <= 4 ? 4 : q.nchunk <= 8 ? 8 : q.nchunk <= 16 ? 16 : 32;
+			const int rows = 8 * (32 / q.xl);
+			q.gx = (q.nchunk + q.xl - 1) / q.xl;
+			q.gy = (q.bn1 + rows - 1) / rows;
+			ShellBoxParams e = q, h = q;
+			e.flux = d_flux_v + B.off;
+			e.k0 = B.s[2]; e.k1 = B.s[2] + B.n[2];
+			h.flux = d_flux_i + B.off;
+			h.k0 = std::max(B.s[2], F.kH0); h.k1 = std::min(B.s[2] + B.n[2], F.kH1);
+			// z chunk: long marches save the re-read of the carried plane, short ones give more blocks
+			for (ShellBoxParams* w : {&e, &h}) {
+				const int nk = std::max(0, w->k1 - w->k0);
+				int zc = 16;
+				while (zc > 4 && (long long)w->gx * w->gy * ((nk + zc - 1) / zc) < 4 * 148) zc /= 2;
+				w->zchunk = std::max(1, std::min(zc, nk));
+			}
+			SE.box[b] = e;
+			SH.box[b] = h;
+		}
+		for (ShellParams* w : {&SE, &SH}) {
+			unsigned nb = 0;
+			for (int b = 0; b < w->nboxes; ++b) {
+				ShellBoxParams& q = w->box[b];
+				const int nk = std::max(0, q.k1 - q.k0);
+				q.blk0 = nb;
+				nb += (unsigned)q.gx * q.gy * ((nk + q.zchunk - 1) / q.zchunk);
+			}
+			w->nblocks = nb;
+		}
 		FixParams& X = pFix[par];
 		memset(&X, 0, sizeof(X));
-		X.Is = sI[S]; X.Id = sI[D]; X.Vd = sV[D]; X.fIs = sFi[S]; X.fId = sFi[D];
+		X.Is = sI[S]; X.Id = sI[D]; X.Vd = sV[D];
 		X.idx = d_idx;
-		X.hA = d_tab[5]; X.hB = d_tab[6]; X.hP0 = d_tab[7]; X.hP1 = d_tab[8]; X.hP2 = d_tab[9];
+		X.hA = d_tab[5]; X.hB = d_tab[6];
 		X.cell = d_fix_cells; X.count = fix_count;
-		X.nx = (int)gn[0]; X.ny = (int)gn[1];
 		X.pitch = pitch; X.plane = plane; X.comp = comp;
-		X.nboxes = pE.nboxes;
-		for (int b = 0; b < pE.nboxes; ++b) X.box[b] = pE.box[b];
 		pMurS[par] = pMur; pMurS[par].V = sV[S];
 		pMurD[par] = pMur; pMurD[par].V = sV[D];
 		pExcD[par][0] = pExc[0]; pExcD[par][0].X = sV[D];
 		pExcD[par][1] = pExc[1]; pExcD[par][1].X = sI[D];
 		StencilParams& T = pHtop[par];
 		T = pH;
-		T.V = sV[D]; T.I = sI[S]; T.Iout = sI[D]; T.flux = sFi[S]; T.flux_out = sFi[D];
+		T.V = sV[D]; T.I = sI[S]; T.Iout = sI[D]; T.flux = d_flux_i; T.flux_out = nullptr; // flux in place
 		T.k0 = pE.k1 - 1; T.k1 = pE.k1; T.zchunk = 1;
 
 		// ---- pre-voltage hooks on the source set
@@ -1004,7 +1058,15 @@ void Engine::build_schedule_fused()
 				k_halo_wait<<<1, 1, 0, s>>>(w);
 			});
 		}
-		// ---- E and H in one pass (UPML fused)
+		// ---- E of the UPML shell, then E and H of everything else in one pass
+		if (has_pml) {
+			lab("shell_E");
+			L.push_back([this, par, i16](cudaStream_t s) {
+				const ShellParams& q = pShE[par];
+				if (!q.nblocks) return;
+				if (i16) k_shell_E<uint16_t><<<q.nblocks, dim3(32, 8), 0, s>>>(q); else k_shell_E<uint32_t><<<q.nblocks, dim3(32, 8), 0, s>>>(q);
+			});
+		}
 		lab("fused_EH");
 		L.push_back([this, par, i16](cudaStream_t s) {
 			const FusedParams& q = pF[par];
@@ -1044,8 +1106,17 @@ void Engine::build_schedule_fused()
 		if (fix_count) {
 			lab("fix_H");
 			L.push_back([this, par, i16](cudaStream_t s) {
-				if (i16) { if (has_pml) launch1d(k_fix_H<uint16_t, true>, pFix[par], pFix[par].count, s); else launch1d(k_fix_H<uint16_t, false>, pFix[par], pFix[par].count, s); }
-				else { if (has_pml) launch1d(k_fix_H<uint32_t, true>, pFix[par], pFix[par].count, s); else launch1d(k_fix_H<uint32_t, false>, pFix[par], pFix[par].count, s); }
+				if (i16) launch1d(k_fix_H<uint16_t>, pFix[par], pFix[par].count, s);
+				else launch1d(k_fix_H<uint32_t>, pFix[par], pFix[par].count, s);
+			});
+		}
+		// ---- H of the UPML shell, from the final E
+		if (has_pml) {
+			lab("shell_H");
+			L.push_back([this, par, i16](cudaStream_t s) {
+				const ShellParams& q = pShH[par];
+				if (!q.nblocks) return;
+				if (i16) k_shell_H<uint16_t><<<q.nblocks, dim3(32, 8), 0, s>>>(q); else k_shell_H<uint32_t><<<q.nblocks, dim3(32, 8), 0, s>>>(q);
 			});
 		}
 		// ---- slab top plane: needs the neighbour's E plane
@@ -1083,16 +1154,12 @@ void Engine::build_schedule_fused()
 // kernels work in place on set 0
 int Engine::set_fused_active(int req)
 {
-	const bool on = fused_possible && !edge_dirty && (req == 1 || (req < 0 && !has_pml));
+	const bool on = fused_possible && !edge_dirty && req != 0;
 	CK(cudaStreamSynchronize(stream));
 	if (fused_active && !on && (numTS_host & 1u)) {
 		const size_t nfield = (size_t)3 * comp;
 		CK(cudaMemcpyAsync(sV[0], sV[1], nfield * sizeof(float), cudaMemcpyDeviceToDevice, stream));
 		CK(cudaMemcpyAsync(sI[0], sI[1], nfield * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-		if (has_pml) {
-			CK(cudaMemcpyAsync(sFv[0], sFv[1], (size_t)flux_floats * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-			CK(cudaMemcpyAsync(sFi[0], sFi[1], (size_t)flux_floats * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-		}
 		CK(cudaStreamSynchronize(stream));
 	}
 	if (!fused_active && on && fused_possible && (numTS_host & 1u)) {
@@ -1100,10 +1167,6 @@ int Engine::set_fused_active(int req)
 		const size_t nfield = (size_t)3 * comp;
 		CK(cudaMemcpyAsync(sV[1], sV[0], nfield * sizeof(float), cudaMemcpyDeviceToDevice, stream));
 		CK(cudaMemcpyAsync(sI[1], sI[0], nfield * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-		if (has_pml) {
-			CK(cudaMemcpyAsync(sFv[1], sFv[0], (size_t)flux_floats * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-			CK(cudaMemcpyAsync(sFi[1], sFi[0], (size_t)flux_floats * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-		}
 		CK(cudaStreamSynchronize(stream));
 	}
 	fused_req = req;
@@ -1209,10 +1272,10 @@ int Engine::reset()
 		if (!sV[q]) continue;
 		CK(cudaMemsetAsync(sV[q], 0, nfield * sizeof(float), stream));
 		CK(cudaMemsetAsync(sI[q], 0, nfield * sizeof(float), stream));
-		if (has_pml && sFv[q]) {
-			CK(cudaMemsetAsync(sFv[q], 0, (size_t)flux_floats * sizeof(float), stream));
-			CK(cudaMemsetAsync(sFi[q], 0, (size_t)flux_floats * sizeof(float), stream));
-		}
+	}
+	if (has_pml) {
+		CK(cudaMemsetAsync(d_flux_v, 0, (size_t)flux_floats * sizeof(float), stream));
+		CK(cudaMemsetAsync(d_flux_i, 0, (size_t)flux_floats * sizeof(float), stream));
 	}
 	if (pMur.nplanes) {
 		CK(cudaMemsetAsync(pMur.vP, 0, (size_t)pMur.total * sizeof(float), stream));
@@ -1546,7 +1609,7 @@ int Engine::get_upml_flux(int box, int is_curr, float* out)
 	if (B.ln[2] == 0) return 0;
 	const long long cs = (long long)B.ln[0] * B.ln[1] * B.ln[2];
 	std::vector<float> h((size_t)3 * cs);
-	CK(cudaMemcpyAsync(h.data(), (is_curr ? sFi[cur()] : sFv[cur()]) + B.flux_off, h.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+	CK(cudaMemcpyAsync(h.data(), (is_curr ? d_flux_i : d_flux_v) + B.flux_off, h.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
 	CK(cudaStreamSynchronize(stream));
 	for (int n = 0; n < 3; ++n)
 		for (int li = 0; li < B.ln[0]; ++li)

@@ -186,8 +186,10 @@ private:
 	cudaGraphExec_t graph_exec = nullptr;
 	bool use_graph = false;
 
-	// fused one-pass timestep (kernels_fused.cuh): ping-pong field/flux sets, one schedule per parity
-	float *sV[2] = {nullptr, nullptr}, *sI[2] = {nullptr, nullptr}, *sFv[2] = {nullptr, nullptr}, *sFi[2] = {nullptr, nullptr};
+	// fused one-pass timestep (kernels_fused.cuh): ping-pong field sets (UPML flux is updated in place), one schedule per parity
+	float *sV[2] = {nullptr, nullptr}, *sI[2] = {nullptr, nullptr};
+	bool pml_disjoint = true;
+	ShellParams pShE[2], pShH[2]; // UPML shell launches per parity
 	int fused_req = -1; // -1 automatic, 0 two-pass, 1 one-pass
 	bool fused_possible = false, fused_active = false;
 	int cur() const { return fused_active ? (int)(numTS_host & 1u) : 0; }

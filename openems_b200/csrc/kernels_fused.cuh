@@ -5,8 +5,8 @@
 // per cell is exactly that of k_update_E / k_update_H (same helpers, same roundings), only the
 // order in which cells are visited changes, so the results are bit-identical.
 //
-// Scheme (z-marching, out of place: fields and UPML flux are ping-pong buffers, the source set
-// is never written during a step):
+// Scheme (z-marching, out of place: the field sets are ping-pong buffers, the source set is
+// never written during a step):
 //   block = (32 lanes, TY+1 warps), tile = 128 x cells by TY rows, marching a z chunk upwards.
 //   iteration kk:  every warp computes E_new(kk) of its row (4 cells per lane) from E_old(kk),
 //                  H_old(kk), H_old(kk-1) [registers], stores it (rows of the tile) and publishes
@@ -19,6 +19,17 @@
 // cells that depend on an E value they changed are recomputed by k_fix_H from the untouched
 // source set (engine.cu builds that list at upload).  Lorentz/RLC switch the engine back to
 // the two-pass schedule.
+//
+// UPML (4.6 % of the cells of the 1024^3 PML_8 benchmark) stays on a two-pass "shell" around
+// the one-pass interior, so that the big kernel carries no UPML code at all:
+//   1. k_shell_E  all UPML boxes: E_new of the box cells IN PLACE in the source set (E_old of a cell
+//                                is read by nobody but the cell itself), flux in place
+//   2. k_fused_EH              : all other cells; shell cells are passed through (their E is
+//                                already E_new and is copied to the destination set, their H is
+//                                copied unchanged)
+//   3. (hooks, k_fix_H)
+//   4. k_shell_H  all UPML boxes: H_new of the box cells from the FINAL E of the destination set,
+//                                source set -> destination set
 #pragma once
 #include "kernels.cuh"
 
@@ -29,11 +40,9 @@
 struct FusedParams {
 	const float* Vs; const float* Is;   // source set (timestep n)
 	float* Vd; float* Id;               // destination set (timestep n+1)
-	const float* fVs; float* fVd;       // UPML voltage flux, source / destination
-	const float* fIs; float* fId;       // UPML current flux
 	const void* idx;
-	const float4 *eA, *eB, *eP0, *eP1, *eP2; // E tables (vv|flag, vi, aux vv, vvfn, vvfo)
-	const float4 *hA, *hB, *hP0, *hP1, *hP2; // H tables
+	const float4 *eA, *eB;              // E tables (vv|UPML flag, vi)
+	const float4 *hA, *hB;              // H tables (ii|UPML flag, iv)
 	int nx, ny, nz;      // nz = local planes held
 	int pitch;
 	long long plane, comp;
@@ -41,78 +50,10 @@ struct FusedParams {
 	int kH0, kH1;        // local planes whose H is UPDATED here; other owned planes are copied through
 	int kHc1;            // H planes [kH1, kHc1) are copied through (top of the domain); [kHc1, kE1) left to the slab kernel
 	int zchunk;
-	int nboxes;
-	PmlBox box[OEMS_MAX_PML_BOXES];
+	// UPML shell: regions (whole float4 chunks in x) whose E and H are produced by k_shell_E/H
+	int nsh;
+	struct ShellBox { int c0, cn, j0, jn, k0, kn; } sh[OEMS_MAX_PML_BOXES];
 };
-
-template <typename P>
-__device__ __forceinline__ long long pml_offset_any(const P& p, int i, int j, int k, long long& cs)
-{
-#pragma unroll 1
-	for (int b = 0; b < p.nboxes; ++b) {
-		const PmlBox& B = p.box[b];
-		const int li = i - B.s[0], lj = j - B.s[1], lk = k - B.s[2];
-		if ((unsigned)li < (unsigned)B.n[0] && (unsigned)lj < (unsigned)B.n[1] && (unsigned)lk < (unsigned)B.n[2]) {
-			cs = (long long)B.n[0] * B.n[1] * B.n[2];
-			return B.off + ((long long)lk * B.n[1] + lj) * B.n[0] + li;
-		}
-	}
-	return -1;
-}
-
-// out-of-place UPML update of one component: reads the flux of timestep n, returns the new
-// field value and the new flux (engine_ext_upml.cpp:52-137 / :144-229 around the leapfrog)
-__device__ __forceinline__ float leap_pml_oop(float X, float m_vv, float m_vi, float curl, float a_vv, float a_fn,
-                                              float a_fo, float F, float& Fn)
-{
-	const float f = fsub(fmul(a_vv, X), fmul(a_fo, F));
-	Fn = fadd(fmul(F, m_vv), fmul(m_vi, curl));
-	return fadd(f, fmul(a_fn, Fn));
-}
-
-// all three components of one cell; flux_out == nullptr: do not store the new flux (halo cells)
-template <bool HAS_PML, typename P>
-__device__ __forceinline__ void cell_update(const P& p, const float4* tP0, const float4* tP1, const float4* tP2,
-                                            const float* flux_in, float* flux_out, unsigned e, const float4& A,
-                                            const float4& B, int x, int j, int k, float curl0, float curl1, float curl2,
-                                            float& x0, float& x1, float& x2)
-{
-	if (HAS_PML && A.w != 0.0f) {
-		long long cs;
-		const long long fo = pml_offset_any(p, x, j, k, cs);
-		if (fo >= 0) {
-			const float4 P0 = __ldg(tP0 + e), P1 = __ldg(tP1 + e), P2 = __ldg(tP2 + e);
-			float f0, f1, f2;
-			x0 = leap_pml_oop(x0, A.x, B.x, curl0, P0.x, P1.x, P2.x, flux_in[fo], f0);
-			x1 = leap_pml_oop(x1, A.y, B.y, curl1, P0.y, P1.y, P2.y, flux_in[fo + cs], f1);
-			x2 = leap_pml_oop(x2, A.z, B.z, curl2, P0.z, P1.z, P2.z, flux_in[fo + 2 * cs], f2);
-			if (flux_out) { flux_out[fo] = f0; flux_out[fo + cs] = f1; flux_out[fo + 2 * cs] = f2; }
-		}
-		return;
-	}
-	x0 = leap(x0, A.x, B.x, curl0);
-	x1 = leap(x1, A.y, B.y, curl1);
-	x2 = leap(x2, A.z, B.z, curl2);
-}
-
-// flux offset like pml_offset_any, also returning the box's plane stride (for the L2 prefetch of
-// the next plane) -- used by the batched UPML pass of k_fused_EH
-template <typename P>
-__device__ __forceinline__ long long pml_offset_ps(const P& p, int i, int j, int k, long long& cs, long long& ps)
-{
-#pragma unroll 1
-	for (int b = 0; b < p.nboxes; ++b) {
-		const PmlBox& B = p.box[b];
-		const int li = i - B.s[0], lj = j - B.s[1], lk = k - B.s[2];
-		if ((unsigned)li < (unsigned)B.n[0] && (unsigned)lj < (unsigned)B.n[1] && (unsigned)lk < (unsigned)B.n[2]) {
-			ps = (long long)B.n[0] * B.n[1];
-			cs = ps * B.n[2];
-			if (lk + 1 >= B.n[2]) ps = 0;
-			return B.off + ((long long)lk * B.n[1] + lj) * B.n[0] + li;
-		}
-	}
-	return -1;
-}
 
 template <typename IdxT, bool HAS_PML>
 __global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_EH(const __grid_constant__ FusedParams p)
@@ -149,6 +90,25 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_EH(const __gri
 	const int xe = ic + 4;
 	const bool hcol = lane == 31 && !halo_row && active && xe < p.nx;
 
+	// shell membership of this thread's chunk (shb) and of the chunk to its right (shxb), one bit
+	// per plane of the z chunk (zchunk + 1 <= 64 planes, checked by the host)
+	unsigned long long shb = 0, shxb = 0;
+	if (HAS_PML) {
+		const int chunk = ic >> 2;
+		for (int b = 0; b < p.nsh; ++b) {
+			if ((unsigned)(jc - p.sh[b].j0) >= (unsigned)p.sh[b].jn) continue;
+			const bool mine = (unsigned)(chunk - p.sh[b].c0) < (unsigned)p.sh[b].cn;
+			const bool right = (unsigned)(chunk + 1 - p.sh[b].c0) < (unsigned)p.sh[b].cn;
+			if (!mine && !right) continue;
+			const int a = max(p.sh[b].k0, kb) - kb, z = min(p.sh[b].k0 + p.sh[b].kn, e_last + 1) - kb;
+			if (z <= a) continue;
+			const unsigned long long m = (z - a >= 64 ? ~0ull : ((1ull << (z - a)) - 1ull)) << a;
+			if (mine) shb |= m;
+			if (right) shxb |= m;
+		}
+	}
+	bool shk = false; // plane k (previous iteration) of this chunk belongs to the shell
+
 	// carried state: E_new(k) and H_old(k) of the own cells, operator indices of plane k
 	float4 ek0 = make_float4(0, 0, 0, 0), ek1 = ek0, ek2 = ek0;
 	float4 hk0, hk1, hk2 = make_float4(0, 0, 0, 0);
@@ -166,6 +126,8 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_EH(const __gri
 		// ------------------------------------------------------------ E_new(kk)
 		const long long o = (long long)kk * p.plane + row;
 		const long long om = (long long)kk * p.plane + rowm;
+		// shell cells: E_new was stored by k_shell_E before this kernel started
+		const bool sh = HAS_PML && (shb >> (kk - kb) & 1ull), shx = HAS_PML && (shxb >> (kk - kb) & 1ull);
 		unsigned e[4];
 		Idx4<IdxT>::load(p.idx, o, e);
 		if (kk + 1 <= e_last && (lane & 7) == 0) {
@@ -176,7 +138,7 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_EH(const __gri
 		}
 		const float4 i0c = ld4(I0 + o), i1c = ld4(I1 + o), i2c = ld4(I2 + o);
 		const float4 i0jm = ld4(I0 + om), i2jm = ld4(I2 + om);
-		float4 v0 = ld4(V0 + o), v1 = ld4(V1 + o), v2 = ld4(V2 + o);
+		float4 v0 = ld4(V0 + o), v1 = ld4(V1 + o), v2 = ld4(V2 + o); // shell cells: already E_new (k_shell_E works in place)
 		float l1 = __shfl_up_sync(0xffffffffu, i1c.w, 1);
 		float l2 = __shfl_up_sync(0xffffffffu, i2c.w, 1);
 		if (lane == 0) {
@@ -189,55 +151,19 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_EH(const __gri
 		if (active) {
 			const bool uni = (e[0] == e[1]) & (e[1] == e[2]) & (e[2] == e[3]);
 			float4 A = __ldg(p.eA + e[0]), B = __ldg(p.eB + e[0]);
-			const bool st = !halo_row && kk < ke;
-			unsigned pm = 0; // UPML cells of this thread
 #pragma unroll
 			for (int c = 0; c < 4; ++c) {
 				if (c > 0 && !uni) { A = __ldg(p.eA + e[c]); B = __ldg(p.eB + e[c]); }
-				if (HAS_PML && A.w != 0.0f) { pm |= 1u << c; continue; }
 				const float curl0 = fadd(fsub(fsub(comp(i2c, c), comp(i2jm, c)), comp(i1c, c)), comp(hk1, c));
 				const float curl1 = fadd(fsub(fsub(comp(i0c, c), comp(hk0, c)), comp(i2c, c)), comp(i2xm, c));
 				const float curl2 = fadd(fsub(fsub(comp(i1c, c), comp(i1xm, c)), comp(i0c, c)), comp(i0jm, c));
-				setcomp(v0, c, leap(comp(v0, c), A.x, B.x, curl0));
-				setcomp(v1, c, leap(comp(v1, c), A.y, B.y, curl1));
-				setcomp(v2, c, leap(comp(v2, c), A.z, B.z, curl2));
+				// branch-free: the shell keeps what it loaded
+				const float n0 = leap(comp(v0, c), A.x, B.x, curl0), n1 = leap(comp(v1, c), A.y, B.y, curl1), n2 = leap(comp(v2, c), A.z, B.z, curl2);
+				setcomp(v0, c, sh ? comp(v0, c) : n0);
+				setcomp(v1, c, sh ? comp(v1, c) : n1);
+				setcomp(v2, c, sh ? comp(v2, c) : n2);
 			}
-			if (HAS_PML && pm) {
-				// rare path: all flux loads of the thread's UPML cells are issued before the first use
-				long long fo[4], cs[4];
-				float F[4][3];
-#pragma unroll
-				for (int c = 0; c < 4; ++c) {
-					fo[c] = -1;
-					if (pm >> c & 1u) {
-						long long ps;
-						fo[c] = pml_offset_ps(p, ic + c, jc, kk, cs[c], ps);
-						if (fo[c] >= 0) {
-							F[c][0] = __ldg(p.fVs + fo[c]); F[c][1] = __ldg(p.fVs + fo[c] + cs[c]); F[c][2] = __ldg(p.fVs + fo[c] + 2 * cs[c]);
-							if (ps && (c == 0 || c == 3)) { prefetch_l2(p.fVs + fo[c] + ps); prefetch_l2(p.fVs + fo[c] + cs[c] + ps); prefetch_l2(p.fVs + fo[c] + 2 * cs[c] + ps); }
-						}
-					}
-				}
-#pragma unroll
-				for (int c = 0; c < 4; ++c) {
-					if (fo[c] < 0) continue;
-					const float4 Ac = __ldg(p.eA + e[c]), Bc = __ldg(p.eB + e[c]);
-					const float4 P0 = __ldg(p.eP0 + e[c]), P1 = __ldg(p.eP1 + e[c]), P2 = __ldg(p.eP2 + e[c]);
-					const float curl0 = fadd(fsub(fsub(comp(i2c, c), comp(i2jm, c)), comp(i1c, c)), comp(hk1, c));
-					const float curl1 = fadd(fsub(fsub(comp(i0c, c), comp(hk0, c)), comp(i2c, c)), comp(i2xm, c));
-					const float curl2 = fadd(fsub(fsub(comp(i1c, c), comp(i1xm, c)), comp(i0c, c)), comp(i0jm, c));
-					float f;
-					setcomp(v0, c, leap_pml_oop(comp(v0, c), Ac.x, Bc.x, curl0, P0.x, P1.x, P2.x, F[c][0], f)); F[c][0] = f;
-					setcomp(v1, c, leap_pml_oop(comp(v1, c), Ac.y, Bc.y, curl1, P0.y, P1.y, P2.y, F[c][1], f)); F[c][1] = f;
-					setcomp(v2, c, leap_pml_oop(comp(v2, c), Ac.z, Bc.z, curl2, P0.z, P1.z, P2.z, F[c][2], f)); F[c][2] = f;
-				}
-				if (st) {
-#pragma unroll
-					for (int c = 0; c < 4; ++c)
-						if (fo[c] >= 0) { p.fVd[fo[c]] = F[c][0]; p.fVd[fo[c] + cs[c]] = F[c][1]; p.fVd[fo[c] + 2 * cs[c]] = F[c][2]; }
-				}
-			}
-			if (st) {
+			if (!halo_row && kk < ke) {
 				st4(p.Vd + o, v0);
 				st4(p.Vd + p.comp + o, v1);
 				st4(p.Vd + 2 * p.comp + o, v2);
@@ -245,14 +171,15 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_EH(const __gri
 			if (hcol) {
 				// V1, V2 of cell (xe, j, kk): engine.cpp:148-166 with the x-1 neighbour = my last cell
 				const unsigned ex = reinterpret_cast<const IdxT*>(p.idx)[o + 4];
-				const float4 Ax = __ldg(p.eA + ex), Bx = __ldg(p.eB + ex);
-				const float xi0 = I0[o + 4], xi1 = I1[o + 4], xi2 = I2[o + 4], xi0jm = I0[om + 4], xi2jm = I2[om + 4];
-				const float c0x = fadd(fsub(fsub(xi2, xi2jm), xi1), 0.0f); // V0 of the halo cell is not needed
+				const float xi0 = I0[o + 4], xi1 = I1[o + 4], xi2 = I2[o + 4], xi0jm = I0[om + 4]; // V0 of the halo cell is not needed
 				const float c1x = fadd(fsub(fsub(xi0, hcI0), xi2), i2c.w);
 				const float c2x = fadd(fsub(fsub(xi1, i1c.w), xi0), xi0jm);
-				float a = 0.0f, b = V1[o + 4], d = V2[o + 4];
-				cell_update<HAS_PML>(p, p.eP0, p.eP1, p.eP2, p.fVs, (float*)nullptr, ex, Ax, Bx, xe, jc, kk, c0x, c1x, c2x, a, b, d);
-				nV1 = b; nV2 = d; nI0 = xi0;
+				const float4 Ax = __ldg(p.eA + ex), Bx = __ldg(p.eB + ex);
+				const float b1 = V1[o + 4], b2 = V2[o + 4];
+				const float n1 = leap(b1, Ax.y, Bx.y, c1x), n2 = leap(b2, Ax.z, Bx.z, c2x);
+				nV1 = shx ? b1 : n1;
+				nV2 = shx ? b2 : n2;
+				nI0 = xi0;
 			}
 		}
 		xV0[kk % 3][ty][lane] = v0;
@@ -268,18 +195,16 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_EH(const __gri
 		if (k >= kb && !halo_row && active) {
 			const long long oh = (long long)k * p.plane + row;
 			float4 c0 = hk0, c1 = hk1, c2 = hk2;
-			if (k < he && j < p.ny - 1) {
+			if (k < he && j < p.ny - 1 && !shk) { // H of shell cells: copied through here, updated by k_shell_H
 				const float4 v0jp = xV0[k % 3][ty + 1][lane], v2jp = xV2[k % 3][ty + 1][lane];
 				const float4 v1xp = make_float4(ek1.y, ek1.z, ek1.w, r1);
 				const float4 v2xp = make_float4(ek2.y, ek2.z, ek2.w, r2);
 				const bool uni = (ek_idx[0] == ek_idx[1]) & (ek_idx[1] == ek_idx[2]) & (ek_idx[2] == ek_idx[3]);
 				float4 A = __ldg(p.hA + ek_idx[0]), B = __ldg(p.hB + ek_idx[0]);
-				unsigned pm = 0;
 #pragma unroll
 				for (int c = 0; c < 4; ++c) {
 					if (c > 0 && !uni) { A = __ldg(p.hA + ek_idx[c]); B = __ldg(p.hB + ek_idx[c]); }
 					if (ic + c < p.nx - 1) {
-						if (HAS_PML && A.w != 0.0f) { pm |= 1u << c; continue; }
 						const float curl0 = fadd(fsub(fsub(comp(ek2, c), comp(v2jp, c)), comp(ek1, c)), comp(v1, c));
 						const float curl1 = fadd(fsub(fsub(comp(ek0, c), comp(v0, c)), comp(ek2, c)), comp(v2xp, c));
 						const float curl2 = fadd(fsub(fsub(comp(ek1, c), comp(v1xp, c)), comp(ek0, c)), comp(v0jp, c));
@@ -287,38 +212,6 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_EH(const __gri
 						setcomp(c1, c, leap(comp(c1, c), A.y, B.y, curl1));
 						setcomp(c2, c, leap(comp(c2, c), A.z, B.z, curl2));
 					}
-				}
-				if (HAS_PML && pm) {
-					long long fo[4], cs[4];
-					float F[4][3];
-#pragma unroll
-					for (int c = 0; c < 4; ++c) {
-						fo[c] = -1;
-						if (pm >> c & 1u) {
-							long long ps;
-							fo[c] = pml_offset_ps(p, ic + c, jc, k, cs[c], ps);
-							if (fo[c] >= 0) {
-								F[c][0] = __ldg(p.fIs + fo[c]); F[c][1] = __ldg(p.fIs + fo[c] + cs[c]); F[c][2] = __ldg(p.fIs + fo[c] + 2 * cs[c]);
-								if (ps && (c == 0 || c == 3)) { prefetch_l2(p.fIs + fo[c] + ps); prefetch_l2(p.fIs + fo[c] + cs[c] + ps); prefetch_l2(p.fIs + fo[c] + 2 * cs[c] + ps); }
-							}
-						}
-					}
-#pragma unroll
-					for (int c = 0; c < 4; ++c) {
-						if (fo[c] < 0) continue;
-						const float4 Ac = __ldg(p.hA + ek_idx[c]), Bc = __ldg(p.hB + ek_idx[c]);
-						const float4 P0 = __ldg(p.hP0 + ek_idx[c]), P1 = __ldg(p.hP1 + ek_idx[c]), P2 = __ldg(p.hP2 + ek_idx[c]);
-						const float curl0 = fadd(fsub(fsub(comp(ek2, c), comp(v2jp, c)), comp(ek1, c)), comp(v1, c));
-						const float curl1 = fadd(fsub(fsub(comp(ek0, c), comp(v0, c)), comp(ek2, c)), comp(v2xp, c));
-						const float curl2 = fadd(fsub(fsub(comp(ek1, c), comp(v1xp, c)), comp(ek0, c)), comp(v0jp, c));
-						float f;
-						setcomp(c0, c, leap_pml_oop(comp(c0, c), Ac.x, Bc.x, curl0, P0.x, P1.x, P2.x, F[c][0], f)); F[c][0] = f;
-						setcomp(c1, c, leap_pml_oop(comp(c1, c), Ac.y, Bc.y, curl1, P0.y, P1.y, P2.y, F[c][1], f)); F[c][1] = f;
-						setcomp(c2, c, leap_pml_oop(comp(c2, c), Ac.z, Bc.z, curl2, P0.z, P1.z, P2.z, F[c][2], f)); F[c][2] = f;
-					}
-#pragma unroll
-					for (int c = 0; c < 4; ++c)
-						if (fo[c] >= 0) { p.fId[fo[c]] = F[c][0]; p.fId[fo[c] + cs[c]] = F[c][1]; p.fId[fo[c] + 2 * cs[c]] = F[c][2]; }
 				}
 			}
 			if (k < p.kHc1) {
@@ -333,6 +226,7 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_EH(const __gri
 #pragma unroll
 		for (int c = 0; c < 4; ++c) ek_idx[c] = e[c];
 		hcV1 = nV1; hcV2 = nV2; hcI0 = nI0;
+		shk = sh;
 	}
 	// H of the chunk's last plane when it is not updated in this kernel (top of the domain:
 	// copy through; top plane of a slab with an upper neighbour: left to the slab kernel)
@@ -348,23 +242,20 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_EH(const __gri
 // ---------------------------------------------------------------------------------------
 // H of listed cells recomputed out of place from the source set and the FINAL E of the
 // destination set: the cells whose E neighbours were changed by hooks (Mur, excitation) after
-// k_fused_EH ran.  One thread per listed cell, all three components.
+// k_fused_EH ran.  One thread per listed cell, all three components.  UPML cells are skipped:
+// k_shell_H runs after the hooks and sees the final E anyway.
 // ---------------------------------------------------------------------------------------
 struct FixParams {
 	const float* Is; float* Id;
 	const float* Vd;                 // final E of this timestep
-	const float* fIs; float* fId;
 	const void* idx;
-	const float4 *hA, *hB, *hP0, *hP1, *hP2;
+	const float4 *hA, *hB;
 	const int* cell;                 // [count][3] x, y, local z
 	long long count;
-	int nx, ny;
 	int pitch; long long plane, comp;
-	int nboxes;
-	PmlBox box[OEMS_MAX_PML_BOXES];
 };
 
-template <typename IdxT, bool HAS_PML>
+template <typename IdxT>
 __global__ void k_fix_H(const __grid_constant__ FixParams p)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -374,13 +265,279 @@ __global__ void k_fix_H(const __grid_constant__ FixParams p)
 	const float* V0 = p.Vd; const float* V1 = p.Vd + p.comp; const float* V2 = p.Vd + 2 * p.comp;
 	const unsigned e = reinterpret_cast<const IdxT*>(p.idx)[o];
 	const float4 A = __ldg(p.hA + e), B = __ldg(p.hB + e);
+	if (A.w != 0.0f) return;
 	const float v0 = V0[o], v1 = V1[o], v2 = V2[o];
 	const float curl0 = fadd(fsub(fsub(v2, V2[o + p.pitch]), v1), V1[o + p.plane]);
 	const float curl1 = fadd(fsub(fsub(v0, V0[o + p.plane]), v2), V2[o + 1]);
 	const float curl2 = fadd(fsub(fsub(v1, V1[o + 1]), v0), V0[o + p.pitch]);
-	float a = p.Is[o], b = p.Is[p.comp + o], d = p.Is[2 * p.comp + o];
-	cell_update<HAS_PML>(p, p.hP0, p.hP1, p.hP2, p.fIs, p.fId, e, A, B, x, j, k, curl0, curl1, curl2, a, b, d);
-	p.Id[o] = a; p.Id[p.comp + o] = b; p.Id[2 * p.comp + o] = d;
+	p.Id[o] = leap(p.Is[o], A.x, B.x, curl0);
+	p.Id[p.comp + o] = leap(p.Is[p.comp + o], A.y, B.y, curl1);
+	p.Id[2 * p.comp + o] = leap(p.Is[2 * p.comp + o], A.z, B.z, curl2);
+}
+
+// ---------------------------------------------------------------------------------------
+// UPML shell of the one-pass schedule: the two half-steps of ONE UPML box, out of place
+// (field of the source set -> destination set), flux updated in place (every cell owns its
+// flux values).  Same arithmetic as the UPML branch of k_update_E / k_update_H.
+// Thread mapping: XL lanes side by side in x (4 cells each), 32/XL rows per warp, so that the
+// 8-cell-thin x slabs still fill their warps; z-marching with the k-1 / k+1 plane in registers.
+// The launch covers the whole float4 chunks the box touches in x: cells of those chunks that
+// lie in no UPML box get the plain leapfrog here (k_fused_EH skips whole chunks), cells of
+// another box are left to that box's launch.
+// ---------------------------------------------------------------------------------------
+struct ShellBoxParams {
+	float* flux;       // component 0 of this box
+	long long cs;      // flux component stride = cells of the box held here
+	int bs0, bs1, bs2; // box origin: x, y, local z (origin of the flux layout [k][j][i])
+	int bn0, bn1;      // box lines in x, y
+	int k0, k1;        // local planes to process
+	int c0, nchunk;    // float4 chunks that cover the box in x
+	int zchunk;
+	int xl;            // lanes side by side in x (power of two)
+	int gx, gy;        // blocks in x and y; blocks of this box = gx*gy*gz
+	unsigned blk0;     // first block of this box in the launch
+};
+struct ShellParams {
+	const float* Xs;   // field being updated, source set (E step: E_old, H step: H_old)
+	float* Xd;         // destination set
+	const float* Y;    // the other field (E step: H_old, H step: final E_new)
+	const void* idx;
+	const float4 *tA, *tB, *tP0, *tP1, *tP2;
+	int nx, ny, pitch;
+	long long plane, comp;
+	int nboxes;
+	unsigned nblocks;
+	ShellBoxParams box[OEMS_MAX_PML_BOXES];
+};
+
+// block -> (box, block coordinates inside the box)
+struct ShellBlock { int b, bx, by, bz; };
+__device__ __forceinline__ ShellBlock shell_block(const ShellParams& p)
+{
+	ShellBlock r;
+	r.b = 0;
+	while (r.b + 1 < p.nboxes && blockIdx.x >= p.box[r.b + 1].blk0) ++r.b;
+	unsigned l = blockIdx.x - p.box[r.b].blk0;
+	r.bx = (int)(l % (unsigned)p.box[r.b].gx); l /= (unsigned)p.box[r.b].gx;
+	r.by = (int)(l % (unsigned)p.box[r.b].gy);
+	r.bz = (int)(l / (unsigned)p.box[r.b].gy);
+	return r;
+}
+
+// true if a box before b covers (chunk, j, k) with its chunk-aligned footprint
+__device__ __forceinline__ bool shell_earlier_box(const ShellParams& p, int b, int chunk, int j, int k)
+{
+	for (int a = 0; a < b; ++a) {
+		const ShellBoxParams& q = p.box[a];
+		if ((unsigned)(chunk - q.c0) < (unsigned)q.nchunk && (unsigned)(j - q.bs1) < (unsigned)q.bn1 && k >= q.k0 && k < q.k1) return true;
+	}
+	return false;
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256, 3) k_shell_E(const __grid_constant__ ShellParams p)
+{
+	const ShellBlock sb = shell_block(p);
+	const ShellBoxParams& q = p.box[sb.b];
+	const int XL = q.xl;
+	const int lane = threadIdx.x, sub = lane & (XL - 1);
+	const int ch = sb.bx * XL + sub;
+	const int lj = (sb.by * blockDim.y + threadIdx.y) * (32 / XL) + lane / XL;
+	const int kb = q.k0 + sb.bz * q.zchunk;
+	const int ke = min(kb + q.zchunk, q.k1);
+	if (kb >= ke) return;
+	const bool active = ch < q.nchunk && lj < q.bn1;
+	if (__all_sync(0xffffffffu, !active)) return;
+	const int ic = (q.c0 + (ch < q.nchunk ? ch : 0)) * 4;
+	const int j = q.bs1 + (lj < q.bn1 ? lj : 0);
+	const int jm = j - (j > 0);
+	const long long row = (long long)j * p.pitch + ic;
+	const long long rowm = (long long)jm * p.pitch + ic;
+	const float* __restrict__ I0 = p.Y;
+	const float* __restrict__ I1 = p.Y + p.comp;
+	const float* __restrict__ I2 = p.Y + 2 * p.comp;
+	const float* __restrict__ V0 = p.Xs;
+	const float* __restrict__ V1 = p.Xs + p.comp;
+	const float* __restrict__ V2 = p.Xs + 2 * p.comp;
+
+	float4 i0km, i1km;
+	{
+		const int km = kb - (kb > 0);
+		const long long o = (long long)km * p.plane + row;
+		i0km = ld4(I0 + o);
+		i1km = ld4(I1 + o);
+	}
+	for (int k = kb; k < ke; ++k) {
+		const long long o = (long long)k * p.plane + row;
+		const long long om = (long long)k * p.plane + rowm;
+		unsigned e[4];
+		Idx4<IdxT>::load(p.idx, o, e);
+		if (k + 1 < ke && active && (sub & 7) == 0) {
+			const long long of = o + p.plane;
+			prefetch_l2(I0 + of); prefetch_l2(I1 + of); prefetch_l2(I2 + of);
+			prefetch_l2(V0 + of); prefetch_l2(V1 + of); prefetch_l2(V2 + of);
+			prefetch_l2(reinterpret_cast<const IdxT*>(p.idx) + of);
+			const float* fn = q.flux + ((long long)(k + 1 - q.bs2) * q.bn1 + lj) * q.bn0 + max(ic - q.bs0, 0);
+			prefetch_l2(fn); prefetch_l2(fn + q.cs); prefetch_l2(fn + 2 * q.cs);
+		}
+		const float4 i0c = ld4(I0 + o), i1c = ld4(I1 + o), i2c = ld4(I2 + o);
+		const float4 i0jm = ld4(I0 + om), i2jm = ld4(I2 + om);
+		float4 v0 = ld4(V0 + o), v1 = ld4(V1 + o), v2 = ld4(V2 + o);
+		float l1 = __shfl_up_sync(0xffffffffu, i1c.w, 1, XL);
+		float l2 = __shfl_up_sync(0xffffffffu, i2c.w, 1, XL);
+		if (sub == 0) {
+			if (ic > 0) { l1 = I1[o - 1]; l2 = I2[o - 1]; }
+			else { l1 = i1c.x; l2 = i2c.x; }
+		}
+		const float4 i1xm = make_float4(l1, i1c.x, i1c.y, i1c.z);
+		const float4 i2xm = make_float4(l2, i2c.x, i2c.y, i2c.z);
+		if (active) {
+			const long long frow = ((long long)(k - q.bs2) * q.bn1 + lj) * q.bn0;
+			unsigned done = 0;
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				const int li = ic + c - q.bs0;
+				const float4 A = __ldg(p.tA + e[c]), B = __ldg(p.tB + e[c]);
+				const float curl0 = fadd(fsub(fsub(comp(i2c, c), comp(i2jm, c)), comp(i1c, c)), comp(i1km, c));
+				const float curl1 = fadd(fsub(fsub(comp(i0c, c), comp(i0km, c)), comp(i2c, c)), comp(i2xm, c));
+				const float curl2 = fadd(fsub(fsub(comp(i1c, c), comp(i1xm, c)), comp(i0c, c)), comp(i0jm, c));
+				if (A.w == 0.0f) {
+					// cell outside every UPML box that shares a float4 chunk with the box; in place:
+					// exactly one launch may update it -> the first box whose footprint holds it
+					if (shell_earlier_box(p, sb.b, ic >> 2, j, k)) continue;
+					setcomp(v0, c, leap(comp(v0, c), A.x, B.x, curl0));
+					setcomp(v1, c, leap(comp(v1, c), A.y, B.y, curl1));
+					setcomp(v2, c, leap(comp(v2, c), A.z, B.z, curl2));
+				} else {
+					if ((unsigned)li >= (unsigned)q.bn0) continue; // belongs to another box
+					const float4 P0 = __ldg(p.tP0 + e[c]), P1 = __ldg(p.tP1 + e[c]), P2 = __ldg(p.tP2 + e[c]);
+					float* f = q.flux + frow + li;
+					setcomp(v0, c, leap_pml(comp(v0, c), A.x, B.x, curl0, P0.x, P1.x, P2.x, f, f));
+					setcomp(v1, c, leap_pml(comp(v1, c), A.y, B.y, curl1, P0.y, P1.y, P2.y, f + q.cs, f + q.cs));
+					setcomp(v2, c, leap_pml(comp(v2, c), A.z, B.z, curl2, P0.z, P1.z, P2.z, f + 2 * q.cs, f + 2 * q.cs));
+				}
+				done |= 1u << c;
+			}
+			if (done == 15u) {
+				st4(p.Xd + o, v0);
+				st4(p.Xd + p.comp + o, v1);
+				st4(p.Xd + 2 * p.comp + o, v2);
+			} else {
+#pragma unroll
+				for (int c = 0; c < 4; ++c)
+					if (done >> c & 1u) {
+						p.Xd[o + c] = comp(v0, c);
+						p.Xd[p.comp + o + c] = comp(v1, c);
+						p.Xd[2 * p.comp + o + c] = comp(v2, c);
+					}
+			}
+		}
+		i0km = i0c;
+		i1km = i1c;
+	}
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256, 3) k_shell_H(const __grid_constant__ ShellParams p)
+{
+	const ShellBlock sb = shell_block(p);
+	const ShellBoxParams& q = p.box[sb.b];
+	const int XL = q.xl;
+	const int lane = threadIdx.x, sub = lane & (XL - 1);
+	const int ch = sb.bx * XL + sub;
+	const int lj = (sb.by * blockDim.y + threadIdx.y) * (32 / XL) + lane / XL;
+	const int kb = q.k0 + sb.bz * q.zchunk;
+	const int ke = min(kb + q.zchunk, q.k1);
+	if (kb >= ke) return;
+	const bool active = ch < q.nchunk && lj < q.bn1;
+	if (__all_sync(0xffffffffu, !active)) return;
+	const int ic = (q.c0 + (ch < q.nchunk ? ch : 0)) * 4;
+	const int j = q.bs1 + (lj < q.bn1 ? lj : 0);
+	const bool upd = active && j < p.ny - 1; // UpdateCurrents stops one line short (engine.cpp:179-183)
+	const long long row = (long long)j * p.pitch + ic;
+	const long long rowp = (long long)(j < p.ny - 1 ? j + 1 : j) * p.pitch + ic;
+	const float* __restrict__ V0 = p.Y;
+	const float* __restrict__ V1 = p.Y + p.comp;
+	const float* __restrict__ V2 = p.Y + 2 * p.comp;
+	const float* __restrict__ I0 = p.Xs;
+	const float* __restrict__ I1 = p.Xs + p.comp;
+	const float* __restrict__ I2 = p.Xs + 2 * p.comp;
+	const bool has_right = ic + 4 < p.pitch;
+
+	float4 v0c, v1c;
+	{
+		const long long o = (long long)kb * p.plane + row;
+		v0c = ld4(V0 + o);
+		v1c = ld4(V1 + o);
+	}
+	for (int k = kb; k < ke; ++k) {
+		const long long o = (long long)k * p.plane + row;
+		const long long op = (long long)k * p.plane + rowp;
+		const long long on = o + p.plane; // plane k+1 is always held: k1 <= held planes - 1
+		unsigned e[4];
+		Idx4<IdxT>::load(p.idx, o, e);
+		if (k + 1 < ke && active && (sub & 7) == 0) {
+			const long long of = on + p.plane;
+			prefetch_l2(V0 + of); prefetch_l2(V1 + of); prefetch_l2(V2 + on);
+			prefetch_l2(I0 + on); prefetch_l2(I1 + on); prefetch_l2(I2 + on);
+			prefetch_l2(reinterpret_cast<const IdxT*>(p.idx) + on);
+			const float* fn = q.flux + ((long long)(k + 1 - q.bs2) * q.bn1 + lj) * q.bn0 + max(ic - q.bs0, 0);
+			prefetch_l2(fn); prefetch_l2(fn + q.cs); prefetch_l2(fn + 2 * q.cs);
+		}
+		const float4 v2c = ld4(V2 + o);
+		const float4 v0n = ld4(V0 + on), v1n = ld4(V1 + on);
+		const float4 v0jp = ld4(V0 + op), v2jp = ld4(V2 + op);
+		float4 c0 = ld4(I0 + o), c1 = ld4(I1 + o), c2 = ld4(I2 + o);
+		float r1 = __shfl_down_sync(0xffffffffu, v1c.x, 1, XL);
+		float r2 = __shfl_down_sync(0xffffffffu, v2c.x, 1, XL);
+		if (sub == XL - 1 || ch >= q.nchunk - 1) { // last lane of the group or last chunk of the box
+			if (has_right) { r1 = V1[o + 4]; r2 = V2[o + 4]; }
+			else { r1 = 0.0f; r2 = 0.0f; } // only reached by cells that are never written
+		}
+		const float4 v1xp = make_float4(v1c.y, v1c.z, v1c.w, r1);
+		const float4 v2xp = make_float4(v2c.y, v2c.z, v2c.w, r2);
+		if (upd) {
+			const long long frow = ((long long)(k - q.bs2) * q.bn1 + lj) * q.bn0;
+			unsigned done = 0;
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				const int li = ic + c - q.bs0;
+				if (ic + c >= p.nx - 1) continue;
+				const float4 A = __ldg(p.tA + e[c]), B = __ldg(p.tB + e[c]);
+				const float curl0 = fadd(fsub(fsub(comp(v2c, c), comp(v2jp, c)), comp(v1c, c)), comp(v1n, c));
+				const float curl1 = fadd(fsub(fsub(comp(v0c, c), comp(v0n, c)), comp(v2c, c)), comp(v2xp, c));
+				const float curl2 = fadd(fsub(fsub(comp(v1c, c), comp(v1xp, c)), comp(v0c, c)), comp(v0jp, c));
+				if (A.w == 0.0f) {
+					setcomp(c0, c, leap(comp(c0, c), A.x, B.x, curl0));
+					setcomp(c1, c, leap(comp(c1, c), A.y, B.y, curl1));
+					setcomp(c2, c, leap(comp(c2, c), A.z, B.z, curl2));
+				} else {
+					if ((unsigned)li >= (unsigned)q.bn0) continue; // belongs to another box
+					const float4 P0 = __ldg(p.tP0 + e[c]), P1 = __ldg(p.tP1 + e[c]), P2 = __ldg(p.tP2 + e[c]);
+					float* f = q.flux + frow + li;
+					setcomp(c0, c, leap_pml(comp(c0, c), A.x, B.x, curl0, P0.x, P1.x, P2.x, f, f));
+					setcomp(c1, c, leap_pml(comp(c1, c), A.y, B.y, curl1, P0.y, P1.y, P2.y, f + q.cs, f + q.cs));
+					setcomp(c2, c, leap_pml(comp(c2, c), A.z, B.z, curl2, P0.z, P1.z, P2.z, f + 2 * q.cs, f + 2 * q.cs));
+				}
+				done |= 1u << c;
+			}
+			if (done == 15u) {
+				st4(p.Xd + o, c0);
+				st4(p.Xd + p.comp + o, c1);
+				st4(p.Xd + 2 * p.comp + o, c2);
+			} else {
+#pragma unroll
+				for (int c = 0; c < 4; ++c)
+					if (done >> c & 1u) {
+						p.Xd[o + c] = comp(c0, c);
+						p.Xd[p.comp + o + c] = comp(c1, c);
+						p.Xd[2 * p.comp + o + c] = comp(c2, c);
+					}
+			}
+		}
+		v0c = v0n;
+		v1c = v1n;
+	}
 }
 
 // plain device-to-device plane copy helper for the parts of the destination set the fused
