@@ -202,6 +202,10 @@ int oems_cuda_set_tuning(oems_cuda_engine* h, int block_rows, int z_chunk, int u
    the second field set; automatic picks it whenever that holds.  UPML cells stay on a two-pass
    "shell" (k_shell_E / k_shell_H) around the one-pass interior. */
 int oems_cuda_set_option(oems_cuda_engine* h, const char* key, long long value);
+/* "tma" = 1 / 0: the one-pass kernel stages its inputs in shared memory through TMA bulk tensor
+   copies (default) or loads them into registers itself (k_fused_EH); identical results.
+   oems_cuda_get_option reports what is ACTIVE ("fused", "tma": 0 / 1). */
+int oems_cuda_get_option(oems_cuda_engine* h, const char* key, long long* value);
 
 /* measurement aid: runs n_ts timesteps without the graph and returns the average duration in
    ms of every kernel of the per-timestep schedule, timed with CUDA events on the engine's own

@@ -956,6 +956,52 @@ int Engine::build_fix_list()
 	return 0;
 }
 
+// TMA descriptors of the source set of one parity: H (box 136 x 9 x 1 x 3), E (136 x 8 x 1 x 3) and
+// the operator index (136 x 8 x 1); out-of-range elements are zero-filled (kernels_fused_tma.cuh)
+int Engine::make_tma_maps(int par)
+{
+	typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+	                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+	                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	static EncodeFn encode = nullptr;
+	if (!encode) {
+		void* fn = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+			cudaGetLastError();
+			return 1;
+		}
+		encode = (EncodeFn)fn;
+		static bool attr_done = false;
+		if (!attr_done) {
+			attr_done = true;
+			cudaFuncSetAttribute(k_fused_tma<uint16_t, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint16_t, 3>());
+			cudaFuncSetAttribute(k_fused_tma<uint16_t, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint16_t, 3>());
+			cudaFuncSetAttribute(k_fused_tma<uint32_t, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint32_t, 2>());
+			cudaFuncSetAttribute(k_fused_tma<uint32_t, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint32_t, 2>());
+			if (cudaGetLastError() != cudaSuccess) { encode = nullptr; return 1; }
+		}
+	}
+	const int S = par;
+	const cuuint64_t dim4[4] = {(cuuint64_t)pitch, (cuuint64_t)gn[1], (cuuint64_t)nzl, 3};
+	const cuuint64_t str4[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)plane * 4, (cuuint64_t)comp * 4};
+	const cuuint32_t ones[4] = {1, 1, 1, 1};
+	const cuuint32_t boxI[4] = {FT_W, FT_ROWS_I, 1, 3}, boxV[4] = {FT_W, FT_ROWS_V, 1, 3}, boxX[3] = {FT_W, FT_ROWS_V, 1};
+	const cuuint64_t dim3[3] = {(cuuint64_t)pitch, (cuuint64_t)gn[1], (cuuint64_t)nzl};
+	const cuuint64_t str3[2] = {(cuuint64_t)pitch * index_bytes, (cuuint64_t)plane * index_bytes};
+	FusedTmaParams& T = pFT[par];
+	CUresult r = encode(&T.mI, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sI[S], dim4, str4, boxI, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r == CUDA_SUCCESS)
+		r = encode(&T.mV, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sV[S], dim4, str4, boxV, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r == CUDA_SUCCESS)
+		r = encode(&T.mX, index_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d_idx, dim3, str3, boxX,
+		           ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return r == CUDA_SUCCESS ? 0 : 1;
+}
+
 void Engine::build_schedule_fused()
 {
 	const bool i16 = index_bytes == 2;
@@ -1033,6 +1079,9 @@ void Engine::build_schedule_fused()
 			}
 			w->nblocks = nb;
 		}
+		pFT[par].f = F;
+		if (par == 0) tma_active = tma_req != 0;
+		if (tma_active && make_tma_maps(par)) tma_active = false; // descriptors unavailable: register-staged kernel
 		FixParams& X = pFix[par];
 		memset(&X, 0, sizeof(X));
 		X.Is = sI[S]; X.Id = sI[D]; X.Vd = sV[D];
@@ -1073,6 +1122,17 @@ void Engine::build_schedule_fused()
 			const dim3 block(32, FUSED_TY + 1);
 			const dim3 g((unsigned)((pitch / 4 + 31) / 32), (unsigned)((q.ny + FUSED_TY - 1) / FUSED_TY),
 			             (unsigned)std::max(1, (q.kE1 - q.kE0 + q.zchunk - 1) / q.zchunk));
+			if (tma_active) {
+				const FusedTmaParams& t = pFT[par];
+				if (i16) {
+					const int sm = ft_smem_bytes<uint16_t, 3>();
+					if (has_pml) k_fused_tma<uint16_t, true, 3><<<g, block, sm, s>>>(t); else k_fused_tma<uint16_t, false, 3><<<g, block, sm, s>>>(t);
+				} else {
+					const int sm = ft_smem_bytes<uint32_t, 2>();
+					if (has_pml) k_fused_tma<uint32_t, true, 2><<<g, block, sm, s>>>(t); else k_fused_tma<uint32_t, false, 2><<<g, block, sm, s>>>(t);
+				}
+				return;
+			}
 			if (i16) { if (has_pml) k_fused_EH<uint16_t, true><<<g, block, 0, s>>>(q); else k_fused_EH<uint16_t, false><<<g, block, 0, s>>>(q); }
 			else { if (has_pml) k_fused_EH<uint32_t, true><<<g, block, 0, s>>>(q); else k_fused_EH<uint32_t, false><<<g, block, 0, s>>>(q); }
 		});
@@ -1222,10 +1282,25 @@ int Engine::set_option(const char* key, long long value)
 		if (value > 0 && edge_dirty) return 0;
 		return set_fused_active(value < 0 ? -1 : (value != 0));
 	}
-	// no options at present.  (An "L2-blocked" launch order -- E kernel on a few planes, then the
+	if (k == "tma") {
+		// 1: the one-pass kernel stages its inputs through TMA (default), 0: register-staged loads
+		tma_req = value != 0;
+		if (finalized) { CK(cudaStreamSynchronize(stream)); build_schedule(); }
+		return 0;
+	}
+	// (An "L2-blocked" launch order -- E kernel on a few planes, then the
 	// H kernel one plane behind so that it reads from L2 -- was measured in round 1 and was 1.7x
 	// SLOWER at 1024^3: see profiles/experiments_r01.md.)
 	return fail("set_option: unknown key " + k);
+}
+
+int Engine::get_option(const char* key, long long* value)
+{
+	const std::string k = key ? key : "";
+	if (!value) return fail("get_option: null pointer");
+	if (k == "fused") { *value = fused_active ? 1 : 0; return 0; }
+	if (k == "tma") { *value = (fused_active && tma_active) ? 1 : 0; return 0; }
+	return fail("get_option: unknown key " + k);
 }
 
 // iterate(n) bracketed by CUDA events on the engine's stream; returns the device time in ms

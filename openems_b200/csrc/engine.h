@@ -11,6 +11,7 @@
 #include "../../include/openems_b200.h"
 #include "kernels.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_fused_tma.cuh"
 
 struct UpmlBoxHost {
 	unsigned start[3], n[3];          // global
@@ -198,6 +199,10 @@ private:
 	cudaGraph_t graphf[2] = {nullptr, nullptr};
 	cudaGraphExec_t graphf_exec[2] = {nullptr, nullptr};
 	FusedParams pF[2];
+	FusedTmaParams pFT[2]; // the same with the TMA descriptors of the source set (kernels_fused_tma.cuh)
+	int tma_req = 1;       // option "tma": stage the inputs of the one-pass kernel through TMA
+	bool tma_active = false;
+	int make_tma_maps(int par);
 	FixParams pFix[2];
 	StencilParams pHtop[2];
 	MurParams pMurS[2], pMurD[2];
@@ -233,6 +238,7 @@ private:
 	void mark_edge_dirty();
 public:
 	int set_option(const char* key, long long value);
+	int get_option(const char* key, long long* value);
 private:
 	bool edge_dirty = false;
 	bool owned(unsigned z) const { return z >= zb && z < ze; }

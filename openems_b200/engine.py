@@ -384,6 +384,11 @@ class Engine_CUDA:
     def SetOption(self, key, value):
         self._ck(self._L.oems_cuda_set_option(self._h, key.encode(), int(value)))
 
+    def GetOption(self, key):
+        v = C.c_longlong()
+        self._ck(self._L.oems_cuda_get_option(self._h, key.encode(), C.byref(v)))
+        return v.value
+
     def TimeSchedule(self, n_ts):
         """average ms of every kernel of the per-timestep schedule (CUDA events on the engine stream)"""
         ms = np.zeros(64, np.float64)

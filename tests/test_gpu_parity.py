@@ -86,6 +86,7 @@ def test_one_pass_and_two_pass_schedules_agree_and_are_used():
     # automatic choice: one-pass, with the UPML boxes on the two-pass shell around it
     names = [n for n, _ in eng.TimeSchedule(0)]
     assert "fused_EH" in names and "shell_E" in names and "shell_H" in names
+    assert eng.GetOption("fused") == 1 and eng.GetOption("tma") == 1  # TMA-staged kernel, not the fallback
     s2 = cases.uniform_box(n=(27, 11, 33), bc=(BC_MUR, BC_MUR, BC_PMC, BC_PEC, BC_PEC, BC_MUR))
     e2 = operator_from_oracle(s2).CreateEngine()
     assert "fused_EH" in [n for n, _ in e2.TimeSchedule(0)]
@@ -93,11 +94,34 @@ def test_one_pass_and_two_pass_schedules_agree_and_are_used():
     e2.IterateTS(90)
     assert_fields_equal(e2, s2, "automatic one-pass, Mur/PMC/PEC")
     total = 0
-    for n, fused in ((3, 1), (4, 0), (5, 1), (31, 1), (2, 0), (40, 1)):
+    for n, fused, tma in ((3, 1, 1), (4, 0, 1), (5, 1, 0), (31, 1, 1), (2, 0, 0), (40, 1, 0), (7, 1, 1)):
         eng.SetOption("fused", fused)
+        eng.SetOption("tma", tma)
         names = [x for x, _ in eng.TimeSchedule(0)]
         assert ("fused_EH" in names) == bool(fused)
+        assert eng.GetOption("tma") == (1 if fused and tma else 0)
         s.iterate(n)
         eng.IterateTS(n)
         total += n
         assert_fields_equal(eng, s, "fused=%d after %d" % (fused, total))
+
+
+def test_graded_mesh_wide_operator_index():
+    """a graded mesh has (almost) one coefficient tuple per cell: more than 65535 tuples switch the
+    per-cell operator index to 32 bit (all kernels have that instance, the TMA kernel runs a
+    2-stage ring there); PML + Mur + PEC faces, both schedules, with and without TMA"""
+    rng = np.random.default_rng(11)
+    lines = [np.cumsum(1e-3 * (1.0 + 0.4 * rng.random(m))) for m in (50, 45, 41)]
+    from oracle.pyoracle import OracleSim, EXC_E_SOFT
+    s = OracleSim(lines[0], lines[1], lines[2], 1.0)
+    s.set_bc([BC_PML, BC_MUR, BC_PML, BC_PEC, BC_PMC, BC_PML], (5,) * 6)
+    s.set_excite_gauss(0.0, 299792458.0 / (20 * 1.4e-3))
+    c = (float(lines[0][25]), float(lines[1][22]), float(0.5 * (lines[2][20] + lines[2][21])))
+    s.add_excitation(c, c, EXC_E_SOFT, (0, 0, 1))
+    s.build()
+    eng = run_both(s, steps=(1, 40, 120), what="graded mesh")
+    assert eng.GetStats()["index_bytes"] == 4 and eng.GetOption("tma") == 1
+    eng.SetOption("tma", 0)
+    s.iterate(30)
+    eng.IterateTS(30)
+    assert_fields_equal(eng, s, "graded mesh, register-staged one-pass kernel")

@@ -15,15 +15,16 @@ so.set_excite_gauss(7.5e9, 7.5e9)
 so.add_excitation((n[0] // 2, n[1] // 2, n[2] // 2 + 0.5), (n[0] // 2, n[1] // 2, n[2] // 2 + 0.5), EXC_E_SOFT, (0, 0, 1))
 so.build()
 eng = so.CreateEngine()
-for fused in (1, 0):
+for fused, tma in ((1, 1), (1, 0), (0, 0)):
     eng.SetOption("fused", fused)
+    eng.SetOption("tma", tma)
     eng.IterateTS(6)
     t = {}
     for k, ms in eng.TimeSchedule(8):
         t[k] = t.get(k, 0) + ms
     st = eng.GetStats()
     ms_graph = eng.IterateTimed(20) / 20
-    print("%s bc=%s fused=%d pml_cells %d  %s  step(graph) %.3f ms  %.0f MC/s"
-          % (n, sys.argv[4], fused, st["pml_cells"], " ".join("%s %.3f" % (k, v) for k, v in t.items() if v > 0.02),
+    print("%s bc=%s fused=%d tma=%d pml_cells %d  %s  step(graph) %.3f ms  %.0f MC/s"
+          % (n, sys.argv[4], fused, eng.GetOption("tma"), st["pml_cells"], " ".join("%s %.3f" % (k, v) for k, v in t.items() if v > 0.02),
              ms_graph, n[0] * n[1] * n[2] / ms_graph / 1e3), flush=True)
 eng.close()
