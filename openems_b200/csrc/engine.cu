@@ -975,10 +975,10 @@ int Engine::make_tma_maps(int par)
 		static bool attr_done = false;
 		if (!attr_done) {
 			attr_done = true;
-			cudaFuncSetAttribute(k_fused_tma<uint16_t, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint16_t, 3>());
-			cudaFuncSetAttribute(k_fused_tma<uint16_t, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint16_t, 3>());
-			cudaFuncSetAttribute(k_fused_tma<uint32_t, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint32_t, 2>());
-			cudaFuncSetAttribute(k_fused_tma<uint32_t, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint32_t, 2>());
+			cudaFuncSetAttribute(k_fused_tma<uint16_t, true, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint16_t, FT_STAGES>());
+			cudaFuncSetAttribute(k_fused_tma<uint16_t, false, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint16_t, FT_STAGES>());
+			cudaFuncSetAttribute(k_fused_tma<uint32_t, true, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint32_t, FT_STAGES>());
+			cudaFuncSetAttribute(k_fused_tma<uint32_t, false, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint32_t, FT_STAGES>());
 			if (cudaGetLastError() != cudaSuccess) { encode = nullptr; return 1; }
 		}
 	}
@@ -1026,6 +1026,9 @@ void Engine::build_schedule_fused()
 		F.kH1 = (multi && peer_hi) ? pE.k1 - 1 : pH.k1;   // the slab's top plane waits for the ghost E plane
 		F.kHc1 = (multi && peer_hi) ? F.kH1 : pE.k1;       // planes above kH1 are copied through (top of the domain)
 		F.zchunk = has_pml ? std::min(pE.zchunk, 63) : pE.zchunk; // the kernel keeps one shell bit per plane of a chunk
+		// TMA-staged kernel: short marches keep the concurrently running blocks on the same few planes
+		// (measured optimum 16..24 planes at 1024^3, profiles/experiments_r01.md)
+		if (tma_req && tune_zchunk <= 0) F.zchunk = std::min(F.zchunk, 16);
 		// UPML shell: all boxes of a half-step in one launch (kernels_fused.cuh)
 		ShellParams& SE = pShE[par];
 		ShellParams& SH = pShH[par];
@@ -1062,7 +1065,7 @@ void Engine::build_schedule_fused()
 			// z chunk: long marches save the re-read of the carried plane, short ones give more blocks
 			for (ShellBoxParams* w : {&e, &h}) {
 				const int nk = std::max(0, w->k1 - w->k0);
-				int zc = 16;
+				int zc = shell_zchunk;
 				while (zc > 4 && (long long)w->gx * w->gy * ((nk + zc - 1) / zc) < 4 * 148) zc /= 2;
 				w->zchunk = std::max(1, std::min(zc, nk));
 			}
@@ -1125,11 +1128,11 @@ void Engine::build_schedule_fused()
 			if (tma_active) {
 				const FusedTmaParams& t = pFT[par];
 				if (i16) {
-					const int sm = ft_smem_bytes<uint16_t, 3>();
-					if (has_pml) k_fused_tma<uint16_t, true, 3><<<g, block, sm, s>>>(t); else k_fused_tma<uint16_t, false, 3><<<g, block, sm, s>>>(t);
+					const int sm = ft_smem_bytes<uint16_t, FT_STAGES>();
+					if (has_pml) k_fused_tma<uint16_t, true, FT_STAGES><<<g, block, sm, s>>>(t); else k_fused_tma<uint16_t, false, FT_STAGES><<<g, block, sm, s>>>(t);
 				} else {
-					const int sm = ft_smem_bytes<uint32_t, 2>();
-					if (has_pml) k_fused_tma<uint32_t, true, 2><<<g, block, sm, s>>>(t); else k_fused_tma<uint32_t, false, 2><<<g, block, sm, s>>>(t);
+					const int sm = ft_smem_bytes<uint32_t, FT_STAGES>();
+					if (has_pml) k_fused_tma<uint32_t, true, FT_STAGES><<<g, block, sm, s>>>(t); else k_fused_tma<uint32_t, false, FT_STAGES><<<g, block, sm, s>>>(t);
 				}
 				return;
 			}
@@ -1281,6 +1284,11 @@ int Engine::set_option(const char* key, long long value)
 		if (!finalized) { fused_req = value < 0 ? -1 : (value != 0); return 0; }
 		if (value > 0 && edge_dirty) return 0;
 		return set_fused_active(value < 0 ? -1 : (value != 0));
+	}
+	if (k == "shell_zchunk") { // planes a UPML shell block marches (tuning aid)
+		shell_zchunk = (int)std::max<long long>(1, std::min<long long>(64, value));
+		if (finalized) { CK(cudaStreamSynchronize(stream)); build_schedule(); }
+		return 0;
 	}
 	if (k == "tma") {
 		// 1: the one-pass kernel stages its inputs through TMA (default), 0: register-staged loads

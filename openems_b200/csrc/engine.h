@@ -202,6 +202,7 @@ private:
 	FusedTmaParams pFT[2]; // the same with the TMA descriptors of the source set (kernels_fused_tma.cuh)
 	int tma_req = 1;       // option "tma": stage the inputs of the one-pass kernel through TMA
 	bool tma_active = false;
+	int shell_zchunk = 16;
 	int make_tma_maps(int par);
 	FixParams pFix[2];
 	StencilParams pHtop[2];

@@ -285,6 +285,9 @@ __global__ void k_fix_H(const __grid_constant__ FixParams p)
 // lie in no UPML box get the plain leapfrog here (k_fused_EH skips whole chunks), cells of
 // another box are left to that box's launch.
 // ---------------------------------------------------------------------------------------
+#ifndef SHELL_MIN_BLOCKS
+#define SHELL_MIN_BLOCKS 3
+#endif
 struct ShellBoxParams {
 	float* flux;       // component 0 of this box
 	long long cs;      // flux component stride = cells of the box held here
@@ -335,7 +338,7 @@ __device__ __forceinline__ bool shell_earlier_box(const ShellParams& p, int b, i
 }
 
 template <typename IdxT>
-__global__ void __launch_bounds__(256, 3) k_shell_E(const __grid_constant__ ShellParams p)
+__global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_E(const __grid_constant__ ShellParams p)
 {
 	const ShellBlock sb = shell_block(p);
 	const ShellBoxParams& q = p.box[sb.b];
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(256, 3) k_shell_E(const __grid_constant__ Shel
 }
 
 template <typename IdxT>
-__global__ void __launch_bounds__(256, 3) k_shell_H(const __grid_constant__ ShellParams p)
+__global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_H(const __grid_constant__ ShellParams p)
 {
 	const ShellBlock sb = shell_block(p);
 	const ShellBoxParams& q = p.box[sb.b];

@@ -7,9 +7,9 @@
 // tensor copies per plane (TMA, cp.async.bulk.tensor) that land the tile of H_old (3 x 9 rows),
 // E_old (3 x 8 rows) and the operator index (8 rows), 136 values wide (x0-4 .. x0+131: the x-1
 // neighbour and the halo column x0+128 included), in a ring of shared-memory stages, signalled
-// by an mbarrier per stage.  The copies of the planes kk+1 .. kk+STAGES-1 are in flight while
-// plane kk is computed, so HBM latency is covered by the ring (about 60 KB per block in
-// flight) and not by occupancy; no thread holds load results in registers across a wait.
+// by an mbarrier per stage.  The copy of plane kk+1 (.. kk+STAGES-1) is in flight while plane kk
+// is computed, so HBM latency is covered by the ring (30 KB per block and stage) and not by
+// occupancy; no thread holds load results in registers across a wait.
 // Out-of-range rows / columns (x0-4 < 0, j0-1 < 0, beyond the pitch or ny) are zero-filled by
 // the TMA unit; the clamped neighbours of index 0 (engine.cpp:117,122,127) are taken from the
 // own cell as before.
@@ -17,6 +17,12 @@
 #include <cuda.h>
 #include "kernels_fused.cuh"
 
+#ifndef FT_STAGES
+#define FT_STAGES 2                   // ring depth; 2 measured faster than 3 (more of the SM's 256 KB left as L1)
+#endif
+#ifndef FT_MIN_BLOCKS
+#define FT_MIN_BLOCKS 2
+#endif
 #define FT_W 136                      // staged row: x0-4 .. x0+131
 #define FT_ROWS_I (FUSED_TY + 2)      // H rows j0-1 .. j0+TY
 #define FT_ROWS_V (FUSED_TY + 1)      // E / index rows j0 .. j0+TY
@@ -91,7 +97,7 @@ template <> struct SIdx4<uint32_t> {
 };
 
 template <typename IdxT, bool HAS_PML, int STAGES>
-__global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_tma(const __grid_constant__ FusedTmaParams P)
+__global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tma(const __grid_constant__ FusedTmaParams P)
 {
 	extern __shared__ __align__(128) unsigned char ft_smem[];
 	typedef FtStage<IdxT> ST;

@@ -1,0 +1,53 @@
+"""Tuning sweep of the UPML shell kernels (development aid).
+usage: python tools/sweep_shell.py build | run"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VARIANTS = {"mb3": [], "mb2": ["SHELL_MIN_BLOCKS=2"], "mb4": ["SHELL_MIN_BLOCKS=4"]}
+LIBDIR = os.path.join(ROOT, "openems_b200", "lib", "variants")
+
+
+def build():
+    from openems_b200 import build as b
+    os.makedirs(LIBDIR, exist_ok=True)
+    for name, defs in VARIANTS.items():
+        out = os.path.join(LIBDIR, "lib_sh_%s.so" % name)
+        b.build(force=True, defines=defs, out=out)
+        print("built", out)
+
+
+def worker():
+    import bench
+    n = 1024
+    so, _ = bench.build_c5((n, n, n))
+    eng = so.operator().CreateEngine()
+    res = []
+    for zc in (4, 8, 16, 32):
+        eng.SetOption("shell_zchunk", zc)
+        eng.SetTuning(0, 0, 0)
+        eng.IterateTS(3)
+        eng.Synchronize()
+        t = dict()
+        for name, ms in eng.TimeSchedule(5):
+            t[name] = t.get(name, 0) + ms
+        res.append((zc, round(t["shell_E"], 4), round(t["shell_H"], 4), round(t["fused_EH"], 4), round(sum(t.values()), 4)))
+    print("RESULT " + json.dumps(res))
+
+
+def run():
+    for name in VARIANTS:
+        lib = os.path.join(LIBDIR, "lib_sh_%s.so" % name)
+        if not os.path.exists(lib):
+            continue
+        env = dict(os.environ, OPENEMS_B200_LIB=lib)
+        out = subprocess.run([sys.executable, __file__, "worker"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+        line = [l for l in out.splitlines() if l.startswith("RESULT ")]
+        print(name, line[0][7:] if line else out[-800:], flush=True)
+
+
+if __name__ == "__main__":
+    {"build": build, "worker": worker, "run": run}[sys.argv[1]]()
