@@ -952,6 +952,7 @@ int Engine::build_fix_list()
 		cells[3 * q + 2] = (int)(k / (nx * ny)) - z0;
 	}
 	d_fix_cells = fix_count ? upload(cells) : nullptr;
+	h_fix_cells = cells;
 	if (fix_count && !d_fix_cells) return fail("out of device memory (fix-up list)");
 	return 0;
 }
@@ -975,10 +976,13 @@ int Engine::make_tma_maps(int par)
 		static bool attr_done = false;
 		if (!attr_done) {
 			attr_done = true;
-			cudaFuncSetAttribute(k_fused_tma<uint16_t, true, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint16_t, FT_STAGES>());
-			cudaFuncSetAttribute(k_fused_tma<uint16_t, false, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint16_t, FT_STAGES>());
-			cudaFuncSetAttribute(k_fused_tma<uint32_t, true, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint32_t, FT_STAGES>());
-			cudaFuncSetAttribute(k_fused_tma<uint32_t, false, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes<uint32_t, FT_STAGES>());
+			const int s16 = ft_smem_bytes<uint16_t, FT_STAGES>(), s32 = ft_smem_bytes<uint32_t, FT_STAGES>();
+			cudaFuncSetAttribute(k_fused_tma<uint16_t, true, FT_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
+			cudaFuncSetAttribute(k_fused_tma<uint16_t, true, FT_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
+			cudaFuncSetAttribute(k_fused_tma<uint16_t, false, FT_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
+			cudaFuncSetAttribute(k_fused_tma<uint32_t, true, FT_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
+			cudaFuncSetAttribute(k_fused_tma<uint32_t, true, FT_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
+			cudaFuncSetAttribute(k_fused_tma<uint32_t, false, FT_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
 			if (cudaGetLastError() != cudaSuccess) { encode = nullptr; return 1; }
 		}
 	}
@@ -1007,6 +1011,35 @@ void Engine::build_schedule_fused()
 	const bool i16 = index_bytes == 2;
 	const bool multi = peers_linked;
 	labelsf.clear();
+	// TMA descriptors of both source sets; without them the register-staged kernel is used
+	tma_active = tma_req != 0 && make_tma_maps(0) == 0 && make_tma_maps(1) == 0;
+	// UPML boxes the one-pass kernel updates itself ("x slabs"): thin in x, at the low end of the mesh
+	// or inside the last x tile (not starting on its first line: the tile before computes that line as its
+	// halo column with the plain formula), at most one per end, and with no H cell of the fix-up list
+	// inside (those are recomputed from the hooks' final E, which an in-place flux cannot redo)
+	xs_box[0] = xs_box[1] = -1;
+	if (tma_active && xslab_req) {
+		const int x0_last = 128 * ((pitch / 4 + 31) / 32 - 1);
+		for (int b = 0; b < pE.nboxes; ++b) {
+			const PmlBox& B = pE.box[b];
+			if (B.n[0] > 16) continue;
+			int g = -1;
+			if (B.s[0] == 0) g = 0;
+			else if (B.s[0] + B.n[0] == (int)gn[0] && B.s[0] > x0_last) g = 1;
+			if (g < 0 || xs_box[g] >= 0) continue;
+			bool hit = false;
+			for (long long q = 0; q < fix_count && !hit; ++q) {
+				const int* c = &h_fix_cells[3 * (size_t)q];
+				hit = (unsigned)(c[0] - B.s[0]) < (unsigned)B.n[0] && (unsigned)(c[1] - B.s[1]) < (unsigned)B.n[1] && (unsigned)(c[2] - B.s[2]) < (unsigned)B.n[2];
+			}
+			if (!hit) xs_box[g] = b;
+		}
+		if ((xs_box[0] >= 0 || xs_box[1] >= 0) && !d_flux_v2) {
+			d_flux_v2 = dalloc<float>((size_t)flux_floats);
+			if (!d_flux_v2) { cudaGetLastError(); xs_box[0] = xs_box[1] = -1; }
+			else cudaMemsetAsync(d_flux_v2, 0, (size_t)flux_floats * sizeof(float), stream);
+		}
+	}
 	for (int par = 0; par < 2; ++par) {
 		const int S = par, D = par ^ 1;
 		auto& L = stepf[par];
@@ -1035,23 +1068,36 @@ void Engine::build_schedule_fused()
 		memset(&SE, 0, sizeof(SE));
 		SE.idx = d_idx;
 		SE.nx = (int)gn[0]; SE.ny = (int)gn[1]; SE.pitch = pitch; SE.plane = plane; SE.comp = comp;
-		SE.nboxes = pE.nboxes;
 		SH = SE;
 		SE.Xs = sV[S]; SE.Xd = sV[S]; SE.Y = sI[S]; // in place: see kernels_fused.cuh
 		SE.tA = d_tab[0]; SE.tB = d_tab[1]; SE.tP0 = d_tab[2]; SE.tP1 = d_tab[3]; SE.tP2 = d_tab[4];
 		SH.Xs = sI[S]; SH.Xd = sI[D]; SH.Y = sV[D];
 		SH.tA = d_tab[5]; SH.tB = d_tab[6]; SH.tP0 = d_tab[7]; SH.tP1 = d_tab[8]; SH.tP2 = d_tab[9];
-		F.nsh = pE.nboxes;
+		int ns = 0;
+		float* const fluxV[2] = {d_flux_v, d_flux_v2};
+		FusedTmaParams& FT = pFT[par];
+		memset(FT.xs, 0, sizeof(FT.xs));
+		FT.bx_off = 0; FT.bx_stride = 1;
+		FT.eP0 = d_tab[2]; FT.eP1 = d_tab[3]; FT.eP2 = d_tab[4];
+		FT.hP0 = d_tab[7]; FT.hP1 = d_tab[8]; FT.hP2 = d_tab[9];
 		for (int b = 0; b < pE.nboxes; ++b) {
 			const PmlBox& B = pE.box[b];
-			F.sh[b].c0 = B.s[0] / 4; F.sh[b].cn = (B.s[0] + B.n[0] - 1) / 4 - F.sh[b].c0 + 1;
-			F.sh[b].j0 = B.s[1]; F.sh[b].jn = B.n[1];
-			F.sh[b].k0 = B.s[2]; F.sh[b].kn = B.n[2];
+			if (b == xs_box[0] || b == xs_box[1]) {
+				XSlab& X = FT.xs[b == xs_box[0] ? 0 : 1];
+				X.n0 = B.n[0]; X.x_first = B.s[0];
+				X.s1 = B.s[1]; X.n1 = B.n[1]; X.s2 = B.s[2]; X.n2 = B.n[2];
+				X.cs = (long long)B.n[0] * B.n[1] * B.n[2];
+				X.fVs = fluxV[S] + B.off; X.fVd = fluxV[D] + B.off; X.fI = d_flux_i + B.off;
+				continue;
+			}
+			F.sh[ns].c0 = B.s[0] / 4; F.sh[ns].cn = (B.s[0] + B.n[0] - 1) / 4 - F.sh[ns].c0 + 1;
+			F.sh[ns].j0 = B.s[1]; F.sh[ns].jn = B.n[1];
+			F.sh[ns].k0 = B.s[2]; F.sh[ns].kn = B.n[2];
 			ShellBoxParams q;
 			memset(&q, 0, sizeof(q));
 			q.cs = (long long)B.n[0] * B.n[1] * B.n[2];
 			q.bs0 = B.s[0]; q.bs1 = B.s[1]; q.bs2 = B.s[2]; q.bn0 = B.n[0]; q.bn1 = B.n[1];
-			q.c0 = F.sh[b].c0; q.nchunk = F.sh[b].cn;
+			q.c0 = F.sh[ns].c0; q.nchunk = F.sh[ns].cn;
 			// lanes side by side in x: the smallest power of two that covers the box
 			q.xl = q.nchunk <= 4 ? 4 : q.nchunk <= 8 ? 8 : q.nchunk <= 16 ? 16 : 32;
 			const int rows = 8 * (32 / q.xl);
@@ -1069,9 +1115,11 @@ void Engine::build_schedule_fused()
 				while (zc > 4 && (long long)w->gx * w->gy * ((nk + zc - 1) / zc) < 4 * 148) zc /= 2;
 				w->zchunk = std::max(1, std::min(zc, nk));
 			}
-			SE.box[b] = e;
-			SH.box[b] = h;
+			SE.box[ns] = e;
+			SH.box[ns] = h;
+			++ns;
 		}
+		F.nsh = SE.nboxes = SH.nboxes = ns;
 		for (ShellParams* w : {&SE, &SH}) {
 			unsigned nb = 0;
 			for (int b = 0; b < w->nboxes; ++b) {
@@ -1082,9 +1130,7 @@ void Engine::build_schedule_fused()
 			}
 			w->nblocks = nb;
 		}
-		pFT[par].f = F;
-		if (par == 0) tma_active = tma_req != 0;
-		if (tma_active && make_tma_maps(par)) tma_active = false; // descriptors unavailable: register-staged kernel
+		FT.f = F;
 		FixParams& X = pFix[par];
 		memset(&X, 0, sizeof(X));
 		X.Is = sI[S]; X.Id = sI[D]; X.Vd = sV[D];
@@ -1126,14 +1172,21 @@ void Engine::build_schedule_fused()
 			const dim3 g((unsigned)((pitch / 4 + 31) / 32), (unsigned)((q.ny + FUSED_TY - 1) / FUSED_TY),
 			             (unsigned)std::max(1, (q.kE1 - q.kE0 + q.zchunk - 1) / q.zchunk));
 			if (tma_active) {
-				const FusedTmaParams& t = pFT[par];
-				if (i16) {
-					const int sm = ft_smem_bytes<uint16_t, FT_STAGES>();
-					if (has_pml) k_fused_tma<uint16_t, true, FT_STAGES><<<g, block, sm, s>>>(t); else k_fused_tma<uint16_t, false, FT_STAGES><<<g, block, sm, s>>>(t);
-				} else {
-					const int sm = ft_smem_bytes<uint32_t, FT_STAGES>();
-					if (has_pml) k_fused_tma<uint32_t, true, FT_STAGES><<<g, block, sm, s>>>(t); else k_fused_tma<uint32_t, false, FT_STAGES><<<g, block, sm, s>>>(t);
-				}
+				FusedTmaParams t = pFT[par];
+				const int sm = i16 ? ft_smem_bytes<uint16_t, FT_STAGES>() : ft_smem_bytes<uint32_t, FT_STAGES>();
+				auto launch = [&](dim3 gg, bool xs) {
+					if (gg.x == 0) return;
+					if (i16) {
+						if (xs) k_fused_tma<uint16_t, true, FT_STAGES, true><<<gg, block, sm, s>>>(t);
+						else if (has_pml) k_fused_tma<uint16_t, true, FT_STAGES, false><<<gg, block, sm, s>>>(t);
+						else k_fused_tma<uint16_t, false, FT_STAGES, false><<<gg, block, sm, s>>>(t);
+					} else {
+						if (xs) k_fused_tma<uint32_t, true, FT_STAGES, true><<<gg, block, sm, s>>>(t);
+						else if (has_pml) k_fused_tma<uint32_t, true, FT_STAGES, false><<<gg, block, sm, s>>>(t);
+						else k_fused_tma<uint32_t, false, FT_STAGES, false><<<gg, block, sm, s>>>(t);
+					}
+				};
+				launch(g, xs_box[0] >= 0 || xs_box[1] >= 0);
 				return;
 			}
 			if (i16) { if (has_pml) k_fused_EH<uint16_t, true><<<g, block, 0, s>>>(q); else k_fused_EH<uint16_t, false><<<g, block, 0, s>>>(q); }
@@ -1213,12 +1266,37 @@ void Engine::build_schedule_fused()
 	kernels_per_step = (unsigned)stepf[0].size();
 }
 
+// the voltage flux of the x-slab boxes sits in set 1 after an odd number of one-pass timesteps
+void Engine::flux_sets_sync(bool to_set0)
+{
+	if (!d_flux_v2 || !(numTS_host & 1u)) return;
+	for (int g = 0; g < 2; ++g) {
+		if (xs_box[g] < 0) continue;
+		const PmlBox& B = pE.box[xs_box[g]];
+		const size_t n = (size_t)3 * B.n[0] * B.n[1] * B.n[2] * sizeof(float);
+		if (to_set0) cudaMemcpyAsync(d_flux_v + B.off, d_flux_v2 + B.off, n, cudaMemcpyDeviceToDevice, stream);
+		else cudaMemcpyAsync(d_flux_v2 + B.off, d_flux_v + B.off, n, cudaMemcpyDeviceToDevice, stream);
+	}
+	cudaStreamSynchronize(stream);
+}
+
+// schedule rebuild that keeps the state: the set of x-slab boxes may change with the options
+int Engine::rebuild_schedule()
+{
+	CK(cudaStreamSynchronize(stream));
+	if (fused_active) flux_sets_sync(true);
+	build_schedule();
+	if (fused_active) flux_sets_sync(false);
+	return 0;
+}
+
 // switching between the one-pass and the two-pass schedule keeps the current fields: the two-pass
 // kernels work in place on set 0
 int Engine::set_fused_active(int req)
 {
 	const bool on = fused_possible && !edge_dirty && req != 0;
 	CK(cudaStreamSynchronize(stream));
+	if (fused_active) flux_sets_sync(true);
 	if (fused_active && !on && (numTS_host & 1u)) {
 		const size_t nfield = (size_t)3 * comp;
 		CK(cudaMemcpyAsync(sV[0], sV[1], nfield * sizeof(float), cudaMemcpyDeviceToDevice, stream));
@@ -1234,6 +1312,7 @@ int Engine::set_fused_active(int req)
 	}
 	fused_req = req;
 	build_schedule();
+	if (fused_active) flux_sets_sync(false);
 	return 0;
 }
 
@@ -1287,13 +1366,20 @@ int Engine::set_option(const char* key, long long value)
 	}
 	if (k == "shell_zchunk") { // planes a UPML shell block marches (tuning aid)
 		shell_zchunk = (int)std::max<long long>(1, std::min<long long>(64, value));
-		if (finalized) { CK(cudaStreamSynchronize(stream)); build_schedule(); }
+		if (finalized) return rebuild_schedule();
 		return 0;
 	}
 	if (k == "tma") {
 		// 1: the one-pass kernel stages its inputs through TMA (default), 0: register-staged loads
 		tma_req = value != 0;
-		if (finalized) { CK(cudaStreamSynchronize(stream)); build_schedule(); }
+		if (finalized) return rebuild_schedule();
+		return 0;
+	}
+	if (k == "xslab") {
+		// 1: thin UPML boxes at the x ends are updated inside the one-pass kernel, 0: shell launches (default:
+		// measured faster, profiles/experiments_r01.md #12)
+		xslab_req = value != 0;
+		if (finalized) return rebuild_schedule();
 		return 0;
 	}
 	// (An "L2-blocked" launch order -- E kernel on a few planes, then the
@@ -1308,6 +1394,7 @@ int Engine::get_option(const char* key, long long* value)
 	if (!value) return fail("get_option: null pointer");
 	if (k == "fused") { *value = fused_active ? 1 : 0; return 0; }
 	if (k == "tma") { *value = (fused_active && tma_active) ? 1 : 0; return 0; }
+	if (k == "xslab") { *value = fused_active ? (xs_box[0] >= 0) + (xs_box[1] >= 0) : 0; return 0; }
 	return fail("get_option: unknown key " + k);
 }
 
@@ -1359,6 +1446,7 @@ int Engine::reset()
 	if (has_pml) {
 		CK(cudaMemsetAsync(d_flux_v, 0, (size_t)flux_floats * sizeof(float), stream));
 		CK(cudaMemsetAsync(d_flux_i, 0, (size_t)flux_floats * sizeof(float), stream));
+		if (d_flux_v2) CK(cudaMemsetAsync(d_flux_v2, 0, (size_t)flux_floats * sizeof(float), stream));
 	}
 	if (pMur.nplanes) {
 		CK(cudaMemsetAsync(pMur.vP, 0, (size_t)pMur.total * sizeof(float), stream));
@@ -1692,7 +1780,11 @@ int Engine::get_upml_flux(int box, int is_curr, float* out)
 	if (B.ln[2] == 0) return 0;
 	const long long cs = (long long)B.ln[0] * B.ln[1] * B.ln[2];
 	std::vector<float> h((size_t)3 * cs);
-	CK(cudaMemcpyAsync(h.data(), (is_curr ? d_flux_i : d_flux_v) + B.flux_off, h.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+	const float* src = is_curr ? d_flux_i : d_flux_v;
+	if (!is_curr && fused_active && d_flux_v2 && (numTS_host & 1u))
+		for (int g = 0; g < 2; ++g)
+			if (xs_box[g] >= 0 && pE.box[xs_box[g]].off == B.flux_off) src = d_flux_v2; // x-slab box: the current flux sits in set 1
+	CK(cudaMemcpyAsync(h.data(), src + B.flux_off, h.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
 	CK(cudaStreamSynchronize(stream));
 	for (int n = 0; n < 3; ++n)
 		for (int li = 0; li < B.ln[0]; ++li)

@@ -202,6 +202,13 @@ private:
 	FusedTmaParams pFT[2]; // the same with the TMA descriptors of the source set (kernels_fused_tma.cuh)
 	int tma_req = 1;       // option "tma": stage the inputs of the one-pass kernel through TMA
 	bool tma_active = false;
+	// UPML boxes updated inside the one-pass kernel ("x slabs", kernels_fused_tma.cuh): index into pE.box, -1 none
+	int xs_box[2] = {-1, -1};
+	int xslab_req = 0;           // option "xslab" (off: slower than the shell so far, profiles/experiments_r01.md #12)
+	float* d_flux_v2 = nullptr;  // second voltage-flux set (only the x-slab boxes use it)
+	std::vector<int> h_fix_cells;
+	void flux_sets_sync(bool to_set0);
+	int rebuild_schedule();
 	int shell_zchunk = 16;
 	int make_tma_maps(int par);
 	FixParams pFix[2];

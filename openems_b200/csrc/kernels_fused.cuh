@@ -55,6 +55,16 @@ struct FusedParams {
 	struct ShellBox { int c0, cn, j0, jn, k0, kn; } sh[OEMS_MAX_PML_BOXES];
 };
 
+// out-of-place UPML update of one component: takes the flux of timestep n, returns the new field
+// value and the new flux (engine_ext_upml.cpp:52-137 / :144-229 around the leapfrog)
+__device__ __forceinline__ float leap_pml_oop(float X, float m_vv, float m_vi, float curl, float a_vv, float a_fn,
+                                              float a_fo, float F, float& Fn)
+{
+	const float f = fsub(fmul(a_vv, X), fmul(a_fo, F));
+	Fn = fadd(fmul(F, m_vv), fmul(m_vi, curl));
+	return fadd(f, fmul(a_fn, Fn));
+}
+
 template <typename IdxT, bool HAS_PML>
 __global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_EH(const __grid_constant__ FusedParams p)
 {

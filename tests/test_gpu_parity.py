@@ -125,3 +125,25 @@ def test_graded_mesh_wide_operator_index():
     s.iterate(30)
     eng.IterateTS(30)
     assert_fields_equal(eng, s, "graded mesh, register-staged one-pass kernel")
+
+
+@pytest.mark.parametrize("n,pml", [((23, 26, 21), 4), ((150, 20, 18), 8), ((300, 12, 40), 8), ((9, 7, 60), 1)])
+def test_x_slab_boxes_inside_the_one_pass_kernel(n, pml):
+    """option "xslab": the UPML boxes at the x ends are updated by lanes of the TMA one-pass kernel
+    (one cell per lane, flux of the voltages ping-ponged) instead of the shell launches; one, two
+    and three x tiles; toggled mid-run at odd and even timestep counts; flux compared as well"""
+    s = cases.uniform_box(n=n, bc=(BC_PML,) * 6, pml=pml)
+    eng = operator_from_oracle(s).CreateEngine()
+    eng.SetOption("xslab", 1)
+    assert eng.GetOption("xslab") == 2 and eng.GetOption("tma") == 1
+    total = 0
+    for steps, xs in ((1, 1), (6, 1), (3, 0), (4, 1), (45, 1), (2, 0), (9, 1)):
+        eng.SetOption("xslab", xs)
+        assert eng.GetOption("xslab") == 2 * xs
+        s.iterate(steps)
+        eng.IterateTS(steps)
+        total += steps
+        assert_fields_equal(eng, s, "x slabs inline=%d after %d steps" % (xs, total))
+        for b, box in enumerate(s.upml_boxes()):
+            for w in (0, 1):
+                assert np.array_equal(eng.GetUPMLFlux(b, w, box["n"]).view(np.uint32), s.upml_flux(b, w).view(np.uint32))
