@@ -184,6 +184,9 @@ def run_reference(args):
 
 def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:  # keep stdout to the one JSON line (NCCL prints its version there at VERSION/INFO level)
+        os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:  # the host-side operator build is OpenMP-parallel: share the cores between ranks
         os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
     import torch
