@@ -170,6 +170,18 @@ int oems_cuda_add_dump(oems_cuda_engine* h, int is_H, int interp, unsigned nx, u
    (asynchronously into pinned staging, then to the caller's buffer) */
 int oems_cuda_read_dump(oems_cuda_engine* h, int dump_id, float* out);
 
+/* ProcessFieldsFD (Common/processfields_fd.cpp:40-107): running DFT of a field dump, kept on the
+   device.  oems_cuda_add_fd_dump attaches n_freq complex<float> accumulators (zero) to a dump
+   made by oems_cuda_add_dump.  oems_cuda_fd_accumulate is ProcessFieldsFD::Process for one
+   sample: it evaluates the dump at the current timestep on the device (no D2H) and does
+   field_fd[f] += field_td * w[f] with w[f] = {re, im} of the reference's exp_jwt_2_dt
+   (processfields_fd.cpp:84-86), which the caller computes exactly as the reference does.
+   oems_cuda_read_fd (PostProcess / DumpFDData) copies out[n_freq][3][nz][ny][nx][2] -- the block
+   HDF5_File_Writer::WriteVectorField(name, complex<float>****, ...) splits into _real / _imag. */
+int oems_cuda_add_fd_dump(oems_cuda_engine* h, int dump_id, unsigned n_freq, int* fd_id);
+int oems_cuda_fd_accumulate(oems_cuda_engine* h, int fd_id, const float* weights_re_im);
+int oems_cuda_read_fd(oems_cuda_engine* h, int fd_id, float* out_re_im, unsigned* n_samples);
+
 /* slow path for unknown callers: Engine::GetVolt/SetVolt/GetCurr/SetCurr (FDTD/engine.h:55-101) */
 int oems_cuda_get_field(oems_cuda_engine* h, int is_curr, unsigned n, unsigned x, unsigned y,
                         unsigned z, float* value);

@@ -1702,6 +1702,57 @@ int Engine::read_dump(int id, float* out)
 	return 0;
 }
 
+// ------------------------------------------------------------------------------ FD dumps
+// ProcessFieldsFD (Common/processfields_fd.cpp:40-107): one complex<float> accumulator per
+// frequency and dump point, kept on the device; D2H once at the end (PostProcess)
+int Engine::add_fd_dump(int dump_id, unsigned nfreq, int* id)
+{
+	if (dump_id < 0 || dump_id >= (int)dumps.size()) return fail("add_fd_dump: bad dump id");
+	if (nfreq == 0) return fail("add_fd_dump: no frequencies"); // the reference disables such a dump (processfields_fd.cpp:44-49)
+	CK(cudaSetDevice(device));
+	FdHost F;
+	F.dump = dump_id; F.nfreq = nfreq; F.samples = 0;
+	const size_t n = 3 * dumps[dump_id].count;
+	F.d_acc = dalloc<float2>(n * nfreq);
+	F.d_w = dalloc<float2>(nfreq);
+	if (!F.d_acc || !F.d_w) return fail("out of device memory (FD dump)");
+	CK(cudaMemsetAsync(F.d_acc, 0, n * nfreq * sizeof(float2), stream));
+	if (id) *id = (int)fds.size();
+	fds.push_back(F);
+	return 0;
+}
+
+int Engine::fd_accumulate(int fd_id, const float* w)
+{
+	if (fd_id < 0 || fd_id >= (int)fds.size()) return fail("fd_accumulate: bad id");
+	if (!w) return fail("fd_accumulate: null pointer");
+	CK(cudaSetDevice(device));
+	FdHost& F = fds[fd_id];
+	DumpHost& D = dumps[F.dump];
+	D.p.V = sV[cur()]; D.p.I = sI[cur()];
+	launch1d(k_dump, D.p, (long long)D.count, stream);
+	CK(cudaMemcpyAsync(F.d_w, w, F.nfreq * sizeof(float2), cudaMemcpyHostToDevice, stream));
+	FdParams q;
+	q.td = D.d_out; q.acc = F.d_acc; q.w = F.d_w; q.n = (long long)(3 * D.count); q.nfreq = F.nfreq;
+	launch1d(k_fd_accumulate, q, q.n, stream);
+	kernels_launched += 2;
+	++F.samples;
+	CK(cudaStreamSynchronize(stream)); // w is the caller's buffer
+	return 0;
+}
+
+int Engine::read_fd(int fd_id, float* out, unsigned* samples)
+{
+	if (fd_id < 0 || fd_id >= (int)fds.size()) return fail("read_fd: bad id");
+	CK(cudaSetDevice(device));
+	FdHost& F = fds[fd_id];
+	const size_t n = 3 * dumps[F.dump].count * F.nfreq;
+	if (out) CK(cudaMemcpyAsync(out, F.d_acc, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	if (samples) *samples = F.samples;
+	return 0;
+}
+
 // ------------------------------------------------------------------------------ field access
 int Engine::get_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned z, float* v)
 {

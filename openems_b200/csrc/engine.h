@@ -53,6 +53,14 @@ struct DumpHost {
 	std::vector<void*> dev_allocs;
 };
 
+struct FdHost {
+	int dump;          // time-domain dump this spectrum is taken from
+	unsigned nfreq;
+	float2* d_acc;     // [nfreq][3*count]
+	float2* d_w;       // [nfreq]
+	unsigned samples;
+};
+
 struct LorDev {
 	LorParams v, i;
 	bool v_on, i_on;
@@ -96,6 +104,10 @@ public:
 	int add_dump(int is_H, int interp, unsigned nx, unsigned ny, unsigned nz, const unsigned* px, const unsigned* py,
 	             const unsigned* pz, const double* const el[3], const double* const del[3], int* id);
 	int read_dump(int id, float* out);
+	int add_fd_dump(int dump_id, unsigned nfreq, int* id);
+	int fd_accumulate(int fd_id, const float* w);
+	int read_fd(int fd_id, float* out, unsigned* samples);
+	std::vector<FdHost> fds;
 	int get_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned z, float* v);
 	int set_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned z, float v);
 	int get_fields(int is_curr, float* out);

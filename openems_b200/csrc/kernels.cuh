@@ -742,6 +742,33 @@ struct DumpParams {
 	int nx, ny, gnz, z0;
 	int pitch; long long plane, comp;
 };
+// ---------------------------------------------------------------------------------------
+// ProcessFieldsFD::Process (Common/processfields_fd.cpp:72-107): running DFT of a field dump,
+//   field_fd[f] += field_td * exp_jwt_2_dt[f]      (complex<float> += float * complex<float>)
+// with the weights computed by the caller exactly as the reference does.  The time-domain
+// sample is the output of k_dump, which stays on the device.
+// ---------------------------------------------------------------------------------------
+struct FdParams {
+	const float* td;   // [3*count] time-domain dump
+	float2* acc;       // [nfreq][3*count]
+	const float2* w;   // [nfreq] weights of this sample
+	long long n;       // 3*count
+	unsigned nfreq;
+};
+__global__ void k_fd_accumulate(const __grid_constant__ FdParams p)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= p.n) return;
+	const float v = p.td[t];
+	for (unsigned f = 0; f < p.nfreq; ++f) {
+		const float2 w = p.w[f];
+		float2 a = p.acc[(long long)f * p.n + t];
+		a.x = fadd(a.x, fmul(v, w.x));
+		a.y = fadd(a.y, fmul(v, w.y));
+		p.acc[(long long)f * p.n + t] = a;
+	}
+}
+
 __device__ __forceinline__ double dump_raw(const DumpParams& p, int is_H, int n, const int pos[3])
 {
 	const long long o = n * p.comp + (long long)(pos[2] - p.z0) * p.plane + (long long)pos[1] * p.pitch + pos[0];

@@ -371,6 +371,30 @@ class Engine_CUDA:
         self._ck(self._L.oems_cuda_read_dump(self._h, dump_id, _ptr(out, _fp)))
         return out
 
+    def AddFDDump(self, dump_id, n_freq):
+        """ProcessFieldsFD::InitProcess: complex accumulators for n_freq frequencies on the device"""
+        i = C.c_int()
+        self._ck(self._L.oems_cuda_add_fd_dump(self._h, dump_id, int(n_freq), C.byref(i)))
+        if not hasattr(self, "_fd_shapes"):
+            self._fd_shapes = {}
+        self._fd_shapes[i.value] = (int(n_freq),) + self._dump_shapes[dump_id]
+        return i.value
+
+    def AccumulateFD(self, fd_id, weights):
+        """ProcessFieldsFD::Process for one sample; weights = complex64 exp_jwt_2_dt per frequency
+        (processfields_fd.cpp:84-86)"""
+        w = np.ascontiguousarray(weights, np.complex64)
+        if w.shape != (self._fd_shapes[fd_id][0],):
+            raise ValueError("one weight per frequency")
+        self._ck(self._L.oems_cuda_fd_accumulate(self._h, fd_id, _ptr(w.view(np.float32), _fp)))
+
+    def ReadFD(self, fd_id):
+        """the accumulated spectra, complex64 [n_freq][3][nz][ny][nx], and the sample count"""
+        out = np.zeros(self._fd_shapes[fd_id], np.complex64)
+        n = C.c_uint()
+        self._ck(self._L.oems_cuda_read_fd(self._h, fd_id, _ptr(out.view(np.float32), _fp), C.byref(n)))
+        return out, n.value
+
     def GetStats(self):
         s = Stats()
         self._ck(self._L.oems_cuda_get_stats(self._h, C.byref(s)))

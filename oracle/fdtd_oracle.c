@@ -1801,3 +1801,30 @@ void orc_dump_field(const orc_sim* s, int is_H, int interp, const unsigned start
 				out[off] = (float)o[0]; out[cnt + off] = (float)o[1]; out[2 * cnt + off] = (float)o[2];
 			}
 }
+
+
+/* ProcessFieldsFD::Process Common/processfields_fd.cpp:72-107 -- the running DFT of a field dump.
+   weight: exp_jwt_2_dt of lines 84-86: std::exp((complex<float>)(-2.0*_I*M_PI*f*T)), then *= 2
+   (single-sided spectrum), then *= Op->GetTimestep()*m_FD_Interval (converted to float by
+   complex<float>::operator*=).  std::exp(complex<float>) is cexpf. */
+#include <complex.h>
+void orc_fd_weight(double freq, double T, double dT, unsigned interval, float out[2])
+{
+	const double complex arg = -2.0 * I * M_PI * freq * T;
+	float complex e = cexpf((float complex)arg);
+	float re = crealf(e), im = cimagf(e);
+	re *= 2.0f; im *= 2.0f;
+	const float sc = (float)(dT * (double)interval);
+	re *= sc; im *= sc;
+	out[0] = re; out[1] = im;
+}
+/* lines 88-100: field_fd += field_td * exp_jwt_2_dt, complex<float> += float * complex<float>
+   (operator*(const float&, const complex<float>&) scales both parts); acc is interleaved re/im */
+void orc_fd_accumulate(float* acc, const float* td, size_t n, const float w[2])
+{
+	for (size_t t = 0; t < n; ++t) {
+		const float pr = td[t] * w[0], pi = td[t] * w[1];
+		acc[2 * t] = acc[2 * t] + pr;
+		acc[2 * t + 1] = acc[2 * t + 1] + pi;
+	}
+}

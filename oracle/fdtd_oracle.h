@@ -23,6 +23,7 @@
  */
 #ifndef FDTD_ORACLE_H
 #define FDTD_ORACLE_H
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -130,6 +131,10 @@ double orc_energy(const orc_sim* s);
    (tools/hdf5_file_writer.cpp:286-302). interp: 0 none 1 node 2 cell. */
 void orc_dump_field(const orc_sim* s, int is_H, int interp, const unsigned start[3],
                     const unsigned stop[3], float* out);
+/* ProcessFieldsFD::Process Common/processfields_fd.cpp:72-107: weight of one sample (lines 84-86)
+   and the accumulation field_fd += field_td * weight (lines 88-100), acc interleaved re/im */
+void orc_fd_weight(double freq, double T, double dT, unsigned interval, float out[2]);
+void orc_fd_accumulate(float* acc, const float* td, size_t n, const float w[2]);
 /* mesh helpers, operator.cpp:143-206 */
 double orc_edge_length(const orc_sim* s, int n, const unsigned pos[3], int dual);
 double orc_disc_line(const orc_sim* s, int n, unsigned pos, int dual);

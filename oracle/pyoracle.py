@@ -93,6 +93,8 @@ def lib():
         "orc_raw_field": (None, [vp, C.c_int, _u3, _d3]),
         "orc_energy": (C.c_double, [vp]),
         "orc_dump_field": (None, [vp, C.c_int, C.c_int, _u3, _u3, _fp]),
+        "orc_fd_weight": (None, [C.c_double, C.c_double, C.c_double, C.c_uint, _fp]),
+        "orc_fd_accumulate": (None, [_fp, _fp, C.c_size_t, _fp]),
         "orc_edge_length": (C.c_double, [vp, C.c_int, _u3, C.c_int]),
         "orc_disc_line": (C.c_double, [vp, C.c_int, C.c_uint, C.c_int]),
         # sse-compressed multithreaded restatement (fdtd_oracle_sse.c)
@@ -342,6 +344,21 @@ class OracleSim:
         out = np.zeros((3, n[2], n[1], n[0]), dtype=np.float32)
         lib().orc_dump_field(self._h, int(is_H), interp, _u3(*start), _u3(*stop), out.ctypes.data_as(_fp))
         return out
+
+    @staticmethod
+    def fd_weight(freq, T, dT, interval):
+        """exp_jwt_2_dt of processfields_fd.cpp:84-86 as complex64"""
+        w = np.zeros(2, np.float32)
+        lib().orc_fd_weight(float(freq), float(T), float(dT), int(interval), w.ctypes.data_as(_fp))
+        return np.complex64(complex(w[0], w[1]))
+
+    @staticmethod
+    def fd_accumulate(acc, td, weight):
+        """acc (complex64, any shape) += td (float32, same shape) * weight, processfields_fd.cpp:88-100"""
+        assert acc.dtype == np.complex64 and td.dtype == np.float32 and acc.shape == td.shape and acc.flags.c_contiguous
+        w = np.array([np.float32(weight.real), np.float32(weight.imag)], np.float32)
+        tdc = np.ascontiguousarray(td)
+        lib().orc_fd_accumulate(acc.view(np.float32).ctypes.data_as(_fp), tdc.ctypes.data_as(_fp), tdc.size, w.ctypes.data_as(_fp))
 
     def edge_length(self, n, pos, dual=False):
         return lib().orc_edge_length(self._h, n, _u3(*pos), int(dual))

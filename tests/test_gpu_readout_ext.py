@@ -254,3 +254,38 @@ def test_steady_state_detection_sinus(fused):
         assert got == pytest.approx(ref, rel=1e-9, abs=1e-300), (it, got, ref)
     assert checks >= 7 and 0 < ref < 1
     assert_fields_equal(eng, s, "steady state run")
+
+
+@pytest.mark.parametrize("is_H,interp", [(0, 2), (1, 2), (0, 0)])
+def test_fd_dump_running_dft_on_device(is_H, interp):
+    """ProcessFieldsFD (processfields_fd.cpp:72-107) -- the running DFT of an
+    NF2FF-style dump box accumulated on the device, bit-equal to the reference's
+    complex<float> accumulation of the same samples; D2H only at the end"""
+    s = cases.uniform_box(n=(30, 26, 28), bc=(BC_PML, BC_PML, BC_MUR, BC_MUR, BC_PEC, BC_PML), pml=5)
+    eng = operator_from_oracle(s).CreateEngine()
+    start, stop = (7, 6, 3), (22, 19, 21)
+    el = [[s.edge_length(n, [p if a == n else 0 for a in range(3)], False) for p in range(s.N[n])] for n in range(3)]
+    dl = [[s.edge_length(n, [p if a == n else 0 for a in range(3)], True) for p in range(s.N[n])] for n in range(3)]
+    d = eng.AddDump(is_H, interp, np.arange(start[0], stop[0] + 1), np.arange(start[1], stop[1] + 1),
+                    np.arange(start[2], stop[2] + 1), el, dl)
+    freqs = [2e9, 5.5e9, 7.5e9]
+    fd = eng.AddFDDump(d, len(freqs))
+    interval = 3
+    ref = np.zeros((len(freqs),) + (3, stop[2] - start[2] + 1, stop[1] - start[1] + 1, stop[0] - start[0] + 1), np.complex64)
+    for it in range(40):
+        s.iterate(interval)
+        eng.IterateTS(interval)
+        # Engine_Interface_FDTD::GetTime(dualTime): H dumps are half a timestep later
+        T = (s.num_ts + (0.5 if is_H else 0.0)) * s.dT
+        w = np.array([OracleSim.fd_weight(f, T, s.dT, interval) for f in freqs], np.complex64)
+        eng.AccumulateFD(fd, w)
+        td = s.dump_field(is_H, interp, start, stop)
+        for n in range(len(freqs)):
+            OracleSim.fd_accumulate(ref[n], td, w[n])
+    got, nsamp = eng.ReadFD(fd)
+    assert nsamp == 40 and np.abs(ref).max() > 0
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    with pytest.raises(EngineError):
+        eng.AddFDDump(d, 0)
+    with pytest.raises(EngineError):
+        eng.AddFDDump(99, 1)

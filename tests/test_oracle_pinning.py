@@ -148,3 +148,22 @@ def test_pml_absorbs_radiated_energy():
         s.iterate(600)
         e[name] = float((s.curr.astype(np.float64) ** 2).sum() * MUE0)
     assert e["pec"] > 0 and e["pml"] < 1e-3 * e["pec"]
+
+
+def test_fd_dump_restatement_matches_numpy_complex64():
+    """ProcessFieldsFD::Process (processfields_fd.cpp:84-100): the restated weight and the
+    complex<float> accumulation against an independent complex64 evaluation"""
+    from oracle.pyoracle import OracleSim
+    rng = np.random.default_rng(3)
+    td = rng.standard_normal((3, 4, 5, 6)).astype(np.float32)
+    acc = np.zeros(td.shape, np.complex64)
+    ref = np.zeros(td.shape, np.complex64)
+    dT, interval = 1.7e-12, 4
+    for it in range(1, 30):
+        T = it * interval * dT
+        w = OracleSim.fd_weight(3.3e9, T, dT, interval)
+        e = np.exp(np.complex64(-2j * np.pi * 3.3e9 * T))
+        assert abs(w - e * np.float32(2) * np.float32(dT * interval)) <= 2e-7 * abs(w)
+        OracleSim.fd_accumulate(acc, td, w)
+        ref = (ref + (td * np.float32(w.real) + 1j * (td * np.float32(w.imag))).astype(np.complex64)).astype(np.complex64)
+    assert np.array_equal(acc.view(np.uint32), ref.view(np.uint32))
