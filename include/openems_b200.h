@@ -182,6 +182,18 @@ int oems_cuda_add_fd_dump(oems_cuda_engine* h, int dump_id, unsigned n_freq, int
 int oems_cuda_fd_accumulate(oems_cuda_engine* h, int fd_id, const float* weights_re_im);
 int oems_cuda_read_fd(oems_cuda_engine* h, int fd_id, float* out_re_im, unsigned* n_samples);
 
+/* ProcessModeMatch (Common/processmodematch.cpp:71-266): waveguide-port mode matching.  start3 /
+   stop3 = the surface AFTER InitProcess has sorted it and excluded the boundaries (lines 86-104),
+   ny its normal; dist0 / dist1 = the normalised m_ModeDist[0/1][posP][posPP] (fparser evaluation and
+   normalisation stay on the host, lines 119-190), area = Op->GetNodeArea(ny,pos,dualMesh) of the same
+   points; is_H = m_ModeFieldType.  oems_cuda_read_mode_match is CalcMultipleIntegrals (lines
+   222-266) at the current timestep: out2 = {value, value^2/purity}, node-interpolated fields, summed
+   in the reference's loop order. */
+int oems_cuda_add_mode_match(oems_cuda_engine* h, int is_H, int ny, const unsigned* start3, const unsigned* stop3,
+                             const double* dist0, const double* dist1, const double* area,
+                             const double* const edge_len[3], const double* const dual_edge_len[3], int* id);
+int oems_cuda_read_mode_match(oems_cuda_engine* h, int id, double* out2);
+
 /* slow path for unknown callers: Engine::GetVolt/SetVolt/GetCurr/SetCurr (FDTD/engine.h:55-101) */
 int oems_cuda_get_field(oems_cuda_engine* h, int is_curr, unsigned n, unsigned x, unsigned y,
                         unsigned z, float* value);

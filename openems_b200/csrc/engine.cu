@@ -1753,6 +1753,58 @@ int Engine::read_fd(int fd_id, float* out, unsigned* samples)
 	return 0;
 }
 
+// ------------------------------------------------------------------------------ mode matching
+// ProcessModeMatch (Common/processmodematch.cpp): start/stop are the box AFTER InitProcess has
+// sorted it and pulled it off the boundaries (lines 86-104); dist0/dist1 are the normalised
+// m_ModeDist arrays [nl0][nl1], area the GetNodeArea values of the same points
+int Engine::add_mode_match(int is_H, int ny, const unsigned start[3], const unsigned stop[3], const double* dist0,
+                           const double* dist1, const double* area, const double* const el[3], const double* const del[3], int* id)
+{
+	if (!finalized) return fail("add_mode_match: engine not finalized");
+	if (slab_set) return fail("add_mode_match: not supported on a z-slab engine yet");
+	if (ny < 0 || ny > 2 || !dist0 || !dist1 || !area) return fail("add_mode_match: bad arguments");
+	for (int a = 0; a < 3; ++a)
+		if (start[a] > stop[a] || stop[a] >= gn[a]) return fail("add_mode_match: box outside the mesh");
+	if (start[ny] != stop[ny]) return fail("add_mode_match: the box is not a surface normal to ny");
+	CK(cudaSetDevice(device));
+	const int nP = (ny + 1) % 3, nPP = (ny + 2) % 3;
+	ModeParams M;
+	memset(&M, 0, sizeof(M));
+	M.d.V = d_V; M.d.I = d_I;
+	for (int a = 0; a < 3; ++a) {
+		M.d.el[a] = upload(std::vector<double>(el[a], el[a] + gn[a]));
+		M.d.del[a] = upload(std::vector<double>(del[a], del[a] + gn[a]));
+	}
+	M.d.is_H = is_H; M.d.interp = 1; // NODE_INTERPOLATE, processmodematch.cpp:82
+	M.d.nx = (int)gn[0]; M.d.ny = (int)gn[1]; M.d.gnz = (int)gn[2]; M.d.z0 = z0;
+	M.d.pitch = pitch; M.d.plane = plane; M.d.comp = comp;
+	M.ny = ny; M.line = (int)start[ny];
+	M.startP = (int)start[nP]; M.startPP = (int)start[nPP];
+	M.nl0 = stop[nP] - start[nP] + 1; M.nl1 = stop[nPP] - start[nPP] + 1;
+	const size_t n = (size_t)M.nl0 * M.nl1;
+	M.dist0 = upload(std::vector<double>(dist0, dist0 + n));
+	M.dist1 = upload(std::vector<double>(dist1, dist1 + n));
+	M.area = upload(std::vector<double>(area, area + n));
+	M.out = dalloc<double>(2);
+	if (!M.dist0 || !M.dist1 || !M.area || !M.out) return fail("out of device memory (mode match)");
+	if (id) *id = (int)modes.size();
+	modes.push_back(M);
+	return 0;
+}
+
+int Engine::read_mode_match(int id, double out[2])
+{
+	if (id < 0 || id >= (int)modes.size()) return fail("read_mode_match: bad id");
+	CK(cudaSetDevice(device));
+	ModeParams& M = modes[id];
+	M.d.V = sV[cur()]; M.d.I = sI[cur()];
+	k_mode_match<<<1, 32, 0, stream>>>(M);
+	++kernels_launched;
+	CK(cudaMemcpyAsync(out, M.out, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	return 0;
+}
+
 // ------------------------------------------------------------------------------ field access
 int Engine::get_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned z, float* v)
 {

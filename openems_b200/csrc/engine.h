@@ -108,6 +108,10 @@ public:
 	int fd_accumulate(int fd_id, const float* w);
 	int read_fd(int fd_id, float* out, unsigned* samples);
 	std::vector<FdHost> fds;
+	int add_mode_match(int is_H, int ny, const unsigned start[3], const unsigned stop[3], const double* dist0, const double* dist1,
+	                   const double* area, const double* const el[3], const double* const del[3], int* id);
+	int read_mode_match(int id, double out[2]);
+	std::vector<ModeParams> modes;
 	int get_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned z, float* v);
 	int set_field(int is_curr, unsigned n, unsigned x, unsigned y, unsigned z, float v);
 	int get_fields(int is_curr, float* out);

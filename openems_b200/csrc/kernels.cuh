@@ -777,15 +777,11 @@ __device__ __forceinline__ double dump_raw(const DumpParams& p, int is_H, int n,
 	if (delta != 0.0) return __ddiv_rn(value, delta);
 	return 0.0;
 }
-__global__ void k_dump(const __grid_constant__ DumpParams p)
+// Engine_Interface_FDTD::GetEField / GetHField (engine_interface_fdtd.cpp:63-124,150-204): the
+// field at mesh position pos with interpolation type p.interp (0 none, 1 node, 2 cell), fp64
+__device__ __forceinline__ void field_interp(const DumpParams& p, const int pos[3], double out[3])
 {
-	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const long long cnt = (long long)p.onx * p.ony * p.onz;
-	if (t >= cnt) return;
-	const unsigned ox = (unsigned)(t % p.onx), oy = (unsigned)((t / p.onx) % p.ony), oz = (unsigned)(t / ((long long)p.onx * p.ony));
-	const int pos[3] = {(int)p.px[ox], (int)p.py[oy], (int)p.pz[oz]};
 	const int N[3] = {p.nx, p.ny, p.gnz};
-	double out[3];
 	int ip[3] = {pos[0], pos[1], pos[2]};
 	if (!p.is_H) {
 		if (p.interp == 1) {
@@ -842,9 +838,72 @@ __global__ void k_dump(const __grid_constant__ DumpParams p)
 			for (int n = 0; n < 3; ++n) out[n] = dump_raw(p, 1, n, pos);
 		}
 	}
+}
+
+__global__ void k_dump(const __grid_constant__ DumpParams p)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long cnt = (long long)p.onx * p.ony * p.onz;
+	if (t >= cnt) return;
+	const unsigned ox = (unsigned)(t % p.onx), oy = (unsigned)((t / p.onx) % p.ony), oz = (unsigned)(t / ((long long)p.onx * p.ony));
+	const int pos[3] = {(int)p.px[ox], (int)p.py[oy], (int)p.pz[oz]};
+	double out[3];
+	field_interp(p, pos, out);
 	p.out[t] = (float)out[0];
 	p.out[cnt + t] = (float)out[1];
 	p.out[2 * cnt + t] = (float)out[2];
+}
+
+// ---------------------------------------------------------------------------------------
+// ProcessModeMatch::CalcMultipleIntegrals (Common/processmodematch.cpp:222-266): projection of the
+// node-interpolated tangential field on a plane onto a mode template,
+//   value  += field_n * dist_n * area      purity += field_n * field_n * area     (n = 0, 1)
+// summed in the reference's loop order (posP outer, posPP inner, n innermost): one warp gathers 32
+// points at a time, then accumulates their terms in order through shuffles.
+// ---------------------------------------------------------------------------------------
+struct ModeParams {
+	DumpParams d;          // fields, edge lengths, interpolation (node), mesh
+	int ny;                // plane normal
+	int line;              // start[ny]
+	int startP, startPP;   // first line in nP = (ny+1)%3, nPP = (ny+2)%3
+	unsigned nl0, nl1;     // m_numLines
+	const double* dist0;   // [nl0*nl1] normalised mode template of component nP
+	const double* dist1;   // component nPP
+	const double* area;    // Op->GetNodeArea(ny, pos, dualMesh)
+	double* out;           // [2]: value, value^2 / purity
+};
+__global__ void k_mode_match(const __grid_constant__ ModeParams p)
+{
+	const unsigned lane = threadIdx.x;
+	const unsigned npts = p.nl0 * p.nl1;
+	const int nP = (p.ny + 1) % 3, nPP = (p.ny + 2) % 3;
+	double value = 0.0, purity = 0.0;
+	for (unsigned base = 0; base < npts; base += 32) {
+		double tv0 = 0.0, tv1 = 0.0, tp0 = 0.0, tp1 = 0.0;
+		const unsigned q = base + lane;
+		if (q < npts) {
+			int pos[3];
+			pos[p.ny] = p.line;
+			pos[nP] = p.startP + (int)(q / p.nl1);
+			pos[nPP] = p.startPP + (int)(q % p.nl1);
+			double f[3];
+			field_interp(p.d, pos, f);
+			const double a = p.area[q], f0 = f[nP], f1 = f[nPP];
+			tv0 = __dmul_rn(__dmul_rn(f0, p.dist0[q]), a); tp0 = __dmul_rn(__dmul_rn(f0, f0), a);
+			tv1 = __dmul_rn(__dmul_rn(f1, p.dist1[q]), a); tp1 = __dmul_rn(__dmul_rn(f1, f1), a);
+		}
+		const unsigned cnt = min(32u, npts - base);
+		for (unsigned s = 0; s < cnt; ++s) {
+			value = __dadd_rn(value, __shfl_sync(0xffffffffu, tv0, s));
+			purity = __dadd_rn(purity, __shfl_sync(0xffffffffu, tp0, s));
+			value = __dadd_rn(value, __shfl_sync(0xffffffffu, tv1, s));
+			purity = __dadd_rn(purity, __shfl_sync(0xffffffffu, tp1, s));
+		}
+	}
+	if (lane == 0) {
+		p.out[0] = value;
+		p.out[1] = purity != 0.0 ? __ddiv_rn(__dmul_rn(value, value), purity) : 0.0;
+	}
 }
 
 // ---------------------------------------------------------------------------------------

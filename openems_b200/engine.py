@@ -395,6 +395,25 @@ class Engine_CUDA:
         self._ck(self._L.oems_cuda_read_fd(self._h, fd_id, _ptr(out.view(np.float32), _fp), C.byref(n)))
         return out, n.value
 
+    def AddModeMatch(self, is_H, ny, start, stop, dist0, dist1, area, edge_len, dual_edge_len):
+        """ProcessModeMatch::InitProcess with the host-evaluated, normalised mode template"""
+        st, sp = _u32(start), _u32(stop)
+        d0, d1, ar = (np.ascontiguousarray(a, np.float64) for a in (dist0, dist1, area))
+        el = [np.ascontiguousarray(a, np.float64) for a in edge_len]
+        dl = [np.ascontiguousarray(a, np.float64) for a in dual_edge_len]
+        elp = (_dp * 3)(*[a.ctypes.data_as(_dp) for a in el])
+        dlp = (_dp * 3)(*[a.ctypes.data_as(_dp) for a in dl])
+        i = C.c_int()
+        self._ck(self._L.oems_cuda_add_mode_match(self._h, int(is_H), int(ny), _ptr(st, _up), _ptr(sp, _up), _ptr(d0, _dp),
+                                                  _ptr(d1, _dp), _ptr(ar, _dp), elp, dlp, C.byref(i)))
+        return i.value
+
+    def ReadModeMatch(self, mode_id):
+        """ProcessModeMatch::CalcMultipleIntegrals: (value, value^2/purity)"""
+        out = np.zeros(2, np.float64)
+        self._ck(self._L.oems_cuda_read_mode_match(self._h, mode_id, _ptr(out, _dp)))
+        return float(out[0]), float(out[1])
+
     def GetStats(self):
         s = Stats()
         self._ck(self._L.oems_cuda_get_stats(self._h, C.byref(s)))

@@ -1828,3 +1828,36 @@ void orc_fd_accumulate(float* acc, const float* td, size_t n, const float w[2])
 		acc[2 * t + 1] = acc[2 * t + 1] + pi;
 	}
 }
+
+
+/* ProcessModeMatch::CalcMultipleIntegrals Common/processmodematch.cpp:222-266 on the surface
+   start..stop (already sorted / pulled off the boundaries as InitProcess does, lines 86-104) with
+   the normalised mode template dist0/dist1 [posP][posPP]; node interpolation (line 82);
+   area = Operator::GetNodeArea operator.cpp:235-240 = GetNodeWidth(nP)*GetNodeWidth(nPP),
+   GetNodeWidth = GetEdgeLength(ny,pos,!dualMesh) operator.h:174 */
+void orc_mode_match(const orc_sim* s, int is_H, int ny, const unsigned start[3], const unsigned stop[3],
+                    const double* dist0, const double* dist1, double out2[2])
+{
+	const int nP = (ny + 1) % 3, nPP = (ny + 2) % 3;
+	const unsigned nl0 = stop[nP] - start[nP] + 1, nl1 = stop[nPP] - start[nPP] + 1;
+	double value = 0, purity = 0;
+	unsigned pos[3] = {0, 0, 0};
+	pos[ny] = start[ny];
+	for (unsigned posP = 0; posP < nl0; ++posP) {
+		pos[nP] = start[nP] + posP;
+		for (unsigned posPP = 0; posPP < nl1; ++posPP) {
+			pos[nPP] = start[nPP] + posPP;
+			const double area = orc_edge_length(s, nP, pos, !is_H) * orc_edge_length(s, nPP, pos, !is_H);
+			double o[3];
+			if (is_H) interp_H(s, 1, pos, o); else interp_E(s, 1, pos, o);
+			const double* dist[2] = {dist0, dist1};
+			for (int n = 0; n < 2; ++n) {
+				const double field = o[(ny + n + 1) % 3];
+				value += field * dist[n][(size_t)posP * nl1 + posPP] * area;
+				purity += field * field * area;
+			}
+		}
+	}
+	out2[1] = purity != 0 ? value * value / purity : 0;
+	out2[0] = value;
+}

@@ -135,6 +135,9 @@ void orc_dump_field(const orc_sim* s, int is_H, int interp, const unsigned start
    and the accumulation field_fd += field_td * weight (lines 88-100), acc interleaved re/im */
 void orc_fd_weight(double freq, double T, double dT, unsigned interval, float out[2]);
 void orc_fd_accumulate(float* acc, const float* td, size_t n, const float w[2]);
+/* ProcessModeMatch::CalcMultipleIntegrals Common/processmodematch.cpp:222-266; out2 = {value, purity ratio} */
+void orc_mode_match(const orc_sim* s, int is_H, int ny, const unsigned start[3], const unsigned stop[3],
+                    const double* dist0, const double* dist1, double out2[2]);
 /* mesh helpers, operator.cpp:143-206 */
 double orc_edge_length(const orc_sim* s, int n, const unsigned pos[3], int dual);
 double orc_disc_line(const orc_sim* s, int n, unsigned pos, int dual);

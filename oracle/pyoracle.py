@@ -93,6 +93,7 @@ def lib():
         "orc_raw_field": (None, [vp, C.c_int, _u3, _d3]),
         "orc_energy": (C.c_double, [vp]),
         "orc_dump_field": (None, [vp, C.c_int, C.c_int, _u3, _u3, _fp]),
+        "orc_mode_match": (None, [vp, C.c_int, C.c_int, _u3, _u3, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "orc_fd_weight": (None, [C.c_double, C.c_double, C.c_double, C.c_uint, _fp]),
         "orc_fd_accumulate": (None, [_fp, _fp, C.c_size_t, _fp]),
         "orc_edge_length": (C.c_double, [vp, C.c_int, _u3, C.c_int]),
@@ -344,6 +345,16 @@ class OracleSim:
         out = np.zeros((3, n[2], n[1], n[0]), dtype=np.float32)
         lib().orc_dump_field(self._h, int(is_H), interp, _u3(*start), _u3(*stop), out.ctypes.data_as(_fp))
         return out
+
+    def mode_match(self, is_H, ny, start, stop, dist0, dist1):
+        """ProcessModeMatch::CalcMultipleIntegrals: (value, value^2/purity)"""
+        d0 = np.ascontiguousarray(dist0, np.float64)
+        d1 = np.ascontiguousarray(dist1, np.float64)
+        out = np.zeros(2, np.float64)
+        dp = C.POINTER(C.c_double)
+        lib().orc_mode_match(self._h, int(is_H), int(ny), _u3(*start), _u3(*stop), d0.ctypes.data_as(dp), d1.ctypes.data_as(dp),
+                             out.ctypes.data_as(dp))
+        return float(out[0]), float(out[1])
 
     @staticmethod
     def fd_weight(freq, T, dT, interval):

@@ -289,3 +289,47 @@ def test_fd_dump_running_dft_on_device(is_H, interp):
         eng.AddFDDump(d, 0)
     with pytest.raises(EngineError):
         eng.AddFDDump(99, 1)
+
+
+@pytest.mark.parametrize("is_H", [0, 1])
+def test_mode_matching_plane_integral(is_H):
+    """SURVEY 8f rank 3: ProcessModeMatch::CalcMultipleIntegrals (processmodematch.cpp:222-266) on
+    the device -- TE10-like template on a cross-section of a PEC waveguide (graded mesh), value and
+    purity equal to the reference's sequential fp64 sums at every sample"""
+    rng = np.random.default_rng(5)
+    x = np.cumsum(np.r_[0, 1 + 0.3 * rng.random(23)]) * 1e-3
+    y = np.cumsum(np.r_[0, 1 + 0.2 * rng.random(15)]) * 1e-3
+    z = np.arange(60) * 1e-3
+    s = OracleSim(x, y, z, 1.0)
+    s.set_bc([BC_PEC, BC_PEC, BC_PEC, BC_PEC, BC_PML, BC_PML], (6,) * 6)
+    s.set_excite_gauss(9e9, 3e9)
+    s.add_excitation((x[0], y[0], z[12]), (x[-1], y[-1], z[12]), EXC_E_SOFT, (0, 1, 0))
+    s.build()
+    eng = operator_from_oracle(s).CreateEngine()
+    ny = 2
+    # ProcessModeMatch::InitProcess pulls the surface off the boundaries (lines 97-100)
+    start, stop = (1, 1, 40), (len(x) - 2, len(y) - 2, 40)
+    el = [[s.edge_length(n, [p if a == n else 0 for a in range(3)], False) for p in range(s.N[n])] for n in range(3)]
+    dl = [[s.edge_length(n, [p if a == n else 0 for a in range(3)], True) for p in range(s.N[n])] for n in range(3)]
+    nl0, nl1 = stop[0] - start[0] + 1, stop[1] - start[1] + 1
+    dist = np.zeros((2, nl0, nl1))
+    area = np.zeros((nl0, nl1))
+    for a in range(nl0):
+        for b in range(nl1):
+            pos = [start[0] + a, start[1] + b, start[2]]
+            xx = s.disc_line(0, pos[0], bool(is_H))
+            # E mode: Ey ~ sin(pi x / a); H mode: Hx ~ -sin(pi x / a)
+            dist[0, a, b] = -np.sin(np.pi * xx / x[-1]) if is_H else 0.0
+            dist[1, a, b] = 0.0 if is_H else np.sin(np.pi * xx / x[-1])
+            area[a, b] = s.edge_length(0, pos, not is_H) * s.edge_length(1, pos, not is_H)
+    dist /= np.sqrt(((dist ** 2) * area).sum())
+    m = eng.AddModeMatch(is_H, ny, start, stop, dist[0], dist[1], area, el, dl)
+    peak = 0.0
+    for it in range(60):
+        s.iterate(5)
+        eng.IterateTS(5)
+        got = eng.ReadModeMatch(m)
+        ref = s.mode_match(is_H, ny, start, stop, dist[0], dist[1])
+        assert got == ref, (it, got, ref)
+        peak = max(peak, abs(ref[0]))
+    assert peak > 0 and 0.5 < ref[1] <= 1.0 + 1e-12  # the excited field is mostly the template mode
