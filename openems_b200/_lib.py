@@ -121,6 +121,7 @@ SIGNATURES = {
     "oems_synth_lorentz_order": (C.c_int, [_vp]),
     "oems_synth_lorentz_count": (C.c_uint, [_vp, C.c_int]),
     "oems_synth_upload": (C.c_int, [_vp, _vp]),
+    "oems_synth_pin": (C.c_int, [_vp]),
 }
 
 _lib = None

@@ -134,7 +134,15 @@ int Engine::set_operator_compressed(unsigned nu, const oems_coeff_entry* table, 
 		}
 	}
 	const char* src = (const char*)index + (size_t)z0 * gn[1] * gn[0] * ib;
-	{
+	cudaPointerAttributes attr;
+	const bool src_pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (src_pinned) {
+		// page-locked source (oems_synth_pin, cudaHostRegister / cudaMallocHost by the caller): one DMA
+		const size_t row_bytes = (size_t)gn[0] * ib;
+		CK(cudaMemcpy2DAsync(p, (size_t)pitch * ib, src, row_bytes, row_bytes, (size_t)gn[1] * nzl, cudaMemcpyHostToDevice, stream));
+		CK(cudaStreamSynchronize(stream));
+	} else {
 		// double-buffered pinned staging: the caller's buffer is pageable, a direct copy would run
 		// at a fraction of the PCIe rate
 		const size_t row_bytes = (size_t)gn[0] * ib, total_rows = (size_t)gn[1] * nzl;
@@ -328,6 +336,14 @@ int Engine::steadystate_check(double* last_diff, unsigned* n_checks)
 	return 0;
 }
 
+// development aid: OEMS_TIMING=1 prints how long the stages of the operator upload take
+struct StageTimer {
+	bool on; cudaStream_t st; double t0; const char* what;
+	static double now() { return omp_get_wtime(); }
+	StageTimer(const char* w, cudaStream_t s) : on(getenv("OEMS_TIMING") != nullptr), st(s), t0(0), what(w) { if (on) t0 = now(); }
+	void lap(const char* name) { if (!on) return; cudaStreamSynchronize(st); const double t = now(); fprintf(stderr, "[oems timing] %s: %s %.1f ms\n", what, name, (t - t0) * 1e3); t0 = t; }
+};
+
 // ------------------------------------------------------------------------------ compression
 // Re-keys the operator per cell: the 12 stencil coefficients plus, inside UPML
 // boxes, the 18 auxiliary coefficients form one 128-byte tuple; equal tuples (memcmp, like
@@ -450,7 +466,7 @@ int Engine::build_pml()
 	flux_floats = 0;
 	pml_cells = 0;
 	int nb = 0;
-	std::vector<long long> e_cell, e_fo, e_cs;
+	edge_possible = false;
 	for (auto& B : h_upml) {
 		// part of the box on the planes this GPU updates (owned planes)
 		const unsigned bz0 = std::max(B.start[2], zb), bz1 = std::min(B.start[2] + B.n[2], ze);
@@ -469,7 +485,38 @@ int Engine::build_pml()
 		pE.box[nb] = pb;
 		pH.box[nb] = pb;
 		++nb;
-		// cells of the box the H stencil never visits (last line of a direction)
+		// cells of the box the H stencil never visits (last line of a direction): listed only when
+		// somebody writes a current there (build_edge_list)
+		if (B.ls[0] + B.ln[0] == (int)gn[0] || B.ls[1] + B.ln[1] == (int)gn[1] || (int)bz0 + B.ln[2] == (int)gn[2]) edge_possible = true;
+	}
+	pE.nboxes = pH.nboxes = nb;
+	has_pml = nb > 0;
+	pml_disjoint = true;
+	for (int a = 0; a < nb; ++a)
+		for (int b = a + 1; b < nb; ++b) {
+			bool overlap = true;
+			for (int d = 0; d < 3; ++d)
+				overlap &= pE.box[a].s[d] < pE.box[b].s[d] + pE.box[b].n[d] && pE.box[b].s[d] < pE.box[a].s[d] + pE.box[a].n[d];
+			if (overlap) pml_disjoint = false;
+		}
+	if (has_pml) {
+		d_flux_v = dalloc<float>((size_t)flux_floats);
+		d_flux_i = dalloc<float>((size_t)flux_floats);
+		if (!d_flux_v || !d_flux_i) return fail("out of device memory (UPML flux)");
+	}
+	pEdge.count = 0;
+	return 0;
+}
+
+// UPML cells the H stencil never visits (k_upml_untouched_H): built the first time a current is
+// written there -- at 1024^3 the list has 6.3 M entries and costs 0.1 s that no ordinary run needs
+int Engine::build_edge_list()
+{
+	std::vector<long long> e_cell, e_fo, e_cs;
+	for (auto& B : h_upml) {
+		if (B.ln[2] <= 0) continue;
+		const unsigned bz0 = B.gz0;
+		const long long cs = (long long)B.ln[0] * B.ln[1] * B.ln[2];
 		auto add_edge = [&](int li, int lj, int lk) {
 			e_cell.push_back(cell_off(B.ls[0] + li, B.ls[1] + lj, bz0 + lk));
 			e_fo.push_back(B.flux_off + ((long long)lk * B.ln[1] + lj) * B.ln[0] + li);
@@ -489,21 +536,6 @@ int Engine::build_pml()
 				for (int li = 0; li < B.ln[0]; ++li)
 					if (!(hx && li == lx) && !(hy && lj == ly)) add_edge(li, lj, lz);
 	}
-	pE.nboxes = pH.nboxes = nb;
-	has_pml = nb > 0;
-	pml_disjoint = true;
-	for (int a = 0; a < nb; ++a)
-		for (int b = a + 1; b < nb; ++b) {
-			bool overlap = true;
-			for (int d = 0; d < 3; ++d)
-				overlap &= pE.box[a].s[d] < pE.box[b].s[d] + pE.box[b].n[d] && pE.box[b].s[d] < pE.box[a].s[d] + pE.box[a].n[d];
-			if (overlap) pml_disjoint = false;
-		}
-	if (has_pml) {
-		d_flux_v = dalloc<float>((size_t)flux_floats);
-		d_flux_i = dalloc<float>((size_t)flux_floats);
-		if (!d_flux_v || !d_flux_i) return fail("out of device memory (UPML flux)");
-	}
 	pEdge.count = (long long)e_cell.size();
 	if (pEdge.count) {
 		pEdge.cell = upload(e_cell);
@@ -514,6 +546,7 @@ int Engine::build_pml()
 		pEdge.tP0 = d_tab[7]; pEdge.tP1 = d_tab[8]; pEdge.tP2 = d_tab[9];
 		pEdge.flux = d_flux_i;
 		pEdge.comp = comp;
+		if (!pEdge.cell || !pEdge.fluxoff || !pEdge.fluxcs) return fail("out of device memory (UPML edge list)");
 	}
 	return 0;
 }
@@ -699,12 +732,14 @@ int Engine::finalize()
 	CK(cudaSetDevice(device));
 	if (!stream) CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 
+	StageTimer tm("finalize", stream);
 	std::vector<uint32_t> index32;
 	if (have_dense) {
 		if (compress_dense(index32)) return 1;
 	}
 	if (build_tables_and_index(index32)) return 1;
 	std::vector<uint32_t>().swap(index32);
+	tm.lap("tables");
 
 	const size_t nfield = (size_t)3 * comp;
 	d_V = dalloc<float>(nfield);
@@ -735,7 +770,9 @@ int Engine::finalize()
 	pE.k0 = (int)zb - z0; pE.k1 = (int)ze - z0;
 	pH.k0 = (int)zb - z0; pH.k1 = (int)std::min(ze, gn[2] - 1) - z0;
 
+	tm.lap("field set 0");
 	if (build_pml()) return 1;
+	tm.lap("upml boxes");
 	pE.flux = d_flux_v; pH.flux = d_flux_i;
 	sV[0] = d_V; sI[0] = d_I;
 	// the one-pass schedule needs a second field set, no volume hooks between the half-steps and
@@ -749,6 +786,7 @@ int Engine::finalize()
 			fused_possible = false; // not enough memory for the ping-pong set: stay with two passes
 		}
 	}
+	tm.lap("field set 1");
 	if (build_mur()) return 1;
 	if (build_exc()) return 1;
 	if (build_lorentz()) return 1;
@@ -777,8 +815,10 @@ int Engine::finalize()
 	if (fused_possible && build_fix_list()) return 1;
 	CK(cudaStreamSynchronize(stream));
 	CK(cudaGetLastError());
+	tm.lap("hooks, fix list");
 
 	build_schedule();
+	tm.lap("schedule");
 	finalized = true;
 	// free host staging
 	std::vector<oems_coeff_entry>().swap(h_table);
@@ -1867,7 +1907,9 @@ int Engine::set_fields(int is_curr, const float* in)
 // only scheduled once the caller has poked a current there (SetCurr / set_fields).
 void Engine::mark_edge_dirty()
 {
-	if (edge_dirty || !pEdge.count) return;
+	if (edge_dirty || !edge_possible) return;
+	if (!pEdge.count && build_edge_list()) return;
+	if (!pEdge.count) return;
 	edge_dirty = true;
 	set_fused_active(0); // the one-pass schedule does not carry this rare path; also rebuilds the schedule
 }

@@ -175,6 +175,8 @@ private:
 
 	StencilParams pE{}, pH{};
 	PmlEdgeParams pEdge{};
+	bool edge_possible = false; // some UPML box touches the last line of a direction
+	int build_edge_list();
 	bool has_pml = false;
 	MurParams pMur{};
 	ExcParams pExc[2]{};

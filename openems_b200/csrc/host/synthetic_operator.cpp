@@ -1,6 +1,7 @@
 // synthetic_operator.cpp -- see synthetic_operator.h.
 // Host-only C++ (no CUDA): the operator build stays on the host like the reference's
 // Operator::CalcECOperator; only the result is uploaded.
+#include <cuda_runtime.h>
 #include "synthetic_operator.h"
 
 #include <omp.h>
@@ -76,6 +77,7 @@ struct oems_synth {
 
 	// results
 	bool built = false;
+	bool pinned = false; // index registered as page-locked memory (oems_synth_pin)
 	double dT = 0;
 	unsigned nyquist = 0, sig_len = 0;
 	std::vector<float> sig[2];
@@ -471,7 +473,11 @@ oems_synth* oems_synth_create(unsigned nx, unsigned ny, unsigned nz, const doubl
 	s->gd = grid_delta;
 	return s;
 }
-void oems_synth_destroy(oems_synth* s) { delete s; }
+void oems_synth_destroy(oems_synth* s)
+{
+	if (s && s->pinned) cudaHostUnregister(const_cast<void*>(oems_synth_index(s)));
+	delete s;
+}
 void oems_synth_set_bc(oems_synth* s, const int bc[6], const unsigned pml_size[6])
 {
 	for (int n = 0; n < 6; ++n) { s->bc[n] = bc[n]; if (pml_size) s->pml[n] = pml_size[n]; }
@@ -898,6 +904,21 @@ void oems_synth_upml_box(const oems_synth* s, int b, unsigned start[3], unsigned
 }
 int oems_synth_lorentz_order(const oems_synth* s) { return s->lor_order; }
 unsigned oems_synth_lorentz_count(const oems_synth* s, int o) { return (unsigned)s->lor[o].pos[0].size(); }
+
+// page-locks the per-cell index so that oems_cuda_set_operator_compressed can DMA it straight
+// from the builder's buffer (PCIe rate) instead of staging it through a pinned bounce buffer
+int oems_synth_pin(oems_synth* s)
+{
+	if (!s || !s->built) return 1;
+	if (s->pinned) return 0;
+	const size_t bytes = (size_t)s->index_bytes * (s->index_bytes == 2 ? s->idx16.size() : s->idx32.size());
+	if (cudaHostRegister(const_cast<void*>(oems_synth_index(s)), bytes, cudaHostRegisterPortable) != cudaSuccess) {
+		cudaGetLastError();
+		return 2;
+	}
+	s->pinned = true;
+	return 0;
+}
 
 int oems_synth_upload(const oems_synth* s, oems_cuda_engine* eng)
 {

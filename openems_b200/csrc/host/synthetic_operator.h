@@ -62,6 +62,8 @@ unsigned oems_synth_lorentz_count(const oems_synth* s, int o);
 
 /* uploads everything into a created (not yet finalized) engine and finalizes it */
 int oems_synth_upload(const oems_synth* s, oems_cuda_engine* eng);
+/* page-lock the index buffer (needs a CUDA device); engine uploads then run at the PCIe rate */
+int oems_synth_pin(oems_synth* s);
 
 #ifdef __cplusplus
 }

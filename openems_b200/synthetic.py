@@ -157,6 +157,13 @@ class SyntheticOperator:
     def lorentz_counts(self):
         return [self._L.oems_synth_lorentz_count(self._h, o) for o in range(self._L.oems_synth_lorentz_order(self._h))]
 
+    def pin(self):
+        """page-lock the operator index (once, after build): engine creation then copies it host ->
+        device at the PCIe rate; returns False when there is no CUDA device to register with"""
+        if not self._built:
+            self.build()
+        return self._L.oems_synth_pin(self._h) == 0
+
     # ---- hand-over to the engine: Operator::CreateEngine
     def operator(self):
         if not self._built:
