@@ -116,6 +116,14 @@ int oems_cuda_add_rlc(oems_cuda_engine* h, unsigned count, const int* dir, const
 int oems_cuda_add_steadystate(oems_cuda_engine* h, unsigned period_ts, unsigned count,
                               const unsigned* pos3, const unsigned* dir);
 int oems_cuda_steadystate_check(oems_cuda_engine* h, double* last_diff, unsigned* n_checks);
+/* Operator_Ext_Absorbing_BC (local absorbing sheet, one per CSXCAD primitive, openems.cpp:411-441;
+   FDTD/extensions/operator_ext_absorbing_bc.h:94-113): m_ny, m_sheetX0 / m_sheetX1 (mesh indices),
+   m_normalSignPositive, m_ABCtype (1 MUR_1ST, 2 MUR_1ST_SA) and the ArrayIJ coefficient tables
+   m_K1_nyP / m_K1_nyPP [numLines0][numLines1] (+ m_K2_* for type 2).  The six hooks of
+   Engine_Ext_Absorbing_BC (engine_ext_absorbing_bc.cpp:108-366) run on the device in the reference's
+   order (sheets are the last extensions inserted: first in the post/apply lists). */
+int oems_cuda_add_absorbing_sheet(oems_cuda_engine* h, int ny, const unsigned* x0, const unsigned* x1, int normal_positive, int type,
+                                  const float* K1_nyP, const float* K1_nyPP, const float* K2_nyP, const float* K2_nyPP);
 /* ends the upload: compresses, moves everything to HBM, fixes the extension schedule in the
    order of Engine::SortExtensionByPriority (FDTD/engine.cpp:87-98) and captures the
    per-timestep CUDA graph.  Replaces Engine::Init (engine.cpp:51-59). */

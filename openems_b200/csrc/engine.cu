@@ -551,6 +551,81 @@ int Engine::build_edge_list()
 	return 0;
 }
 
+// ------------------------------------------------------------------------------ absorbing sheets
+int Engine::add_absorbing_sheet(int ny, const unsigned x0[3], const unsigned x1[3], int positive, int type, const float* K1P,
+                                const float* K1PP, const float* K2P, const float* K2PP)
+{
+	if (finalized) return fail("engine already finalized");
+	if (h_sheet.size() >= 8) return fail("add_absorbing_sheet: too many sheets");
+	if (ny < 0 || ny > 2 || (type != 1 && type != 2) || !K1P || !K1PP) return fail("add_absorbing_sheet: bad arguments");
+	if (type == 2 && (!K2P || !K2PP)) return fail("add_absorbing_sheet: super-absorption needs the K2 arrays");
+	SheetHost S;
+	S.ny = ny; S.type = type; S.positive = positive != 0;
+	for (int a = 0; a < 3; ++a) {
+		if (x0[a] > x1[a] || x1[a] >= gn[a]) return fail("add_absorbing_sheet: sheet outside the mesh");
+		S.x0[a] = x0[a]; S.x1[a] = x1[a];
+	}
+	if (x0[ny] != x1[ny]) return fail("add_absorbing_sheet: not a sheet normal to ny");
+	// shifted lines of the engine extension ctor (engine_ext_absorbing_bc.cpp:64-71) must exist
+	const long long line = x0[ny], lo = S.positive ? line : line - (type == 2 ? 2 : 1), hi = S.positive ? line + 1 : line;
+	if (lo < 0 || hi >= (long long)gn[ny]) return fail("add_absorbing_sheet: the shifted line is outside the mesh");
+	const int nP = (ny + 1) % 3, nPP = (ny + 2) % 3;
+	const size_t n = (size_t)(x1[nP] - x0[nP] + 1) * (x1[nPP] - x0[nPP] + 1);
+	S.K1P.assign(K1P, K1P + n); S.K1PP.assign(K1PP, K1PP + n);
+	if (type == 2) { S.K2P.assign(K2P, K2P + n); S.K2PP.assign(K2PP, K2PP + n); }
+	h_sheet.push_back(std::move(S));
+	return 0;
+}
+
+int Engine::build_sheets()
+{
+	sheet_dev.clear();
+	if (h_sheet.empty()) return 0;
+	if (slab_set) return fail("absorbing sheets on a z-slab engine are not supported yet");
+	for (const SheetHost& S : h_sheet) {
+		const int ny = S.ny, nP = (ny + 1) % 3, nPP = (ny + 2) % 3;
+		const unsigned nl0 = S.x1[nP] - S.x0[nP] + 1, nl1 = S.x1[nPP] - S.x0[nPP] + 1;
+		const unsigned line = S.x0[ny];
+		const unsigned shift_V = line + (S.positive ? 1 : -1);
+		const unsigned pos_I = line + (S.positive ? 0 : -1), shift_I = line + (S.positive ? 1 : -2);
+		SheetDev D;
+		memset(&D, 0, sizeof(D));
+		auto off = [&](int comp_n, unsigned l, unsigned a, unsigned b) {
+			unsigned pos[3];
+			pos[ny] = l; pos[nP] = S.x0[nP] + a; pos[nPP] = S.x0[nPP] + b;
+			return (long long)comp_n * comp + cell_off(pos[0], pos[1], pos[2]);
+		};
+		// voltage list: all sheet points, component nyP then nyPP of a point (order is irrelevant: distinct cells)
+		std::vector<long long> o, os;
+		std::vector<float> k1, k2;
+		for (unsigned a = 0; a < nl0; ++a)
+			for (unsigned b = 0; b < nl1; ++b) {
+				const size_t q = (size_t)a * nl1 + b;
+				o.push_back(off(nP, line, a, b)); os.push_back(off(nP, shift_V, a, b)); k1.push_back(S.K1P[q]);
+				o.push_back(off(nPP, line, a, b)); os.push_back(off(nPP, shift_V, a, b)); k1.push_back(S.K1PP[q]);
+			}
+		D.v.count = (long long)o.size();
+		D.v.o = upload(o); D.v.os = upload(os); D.v.K1 = upload(k1);
+		D.v.store = dalloc<float>(o.size());
+		D.v.X = d_V;
+		if (S.type == 2 && nl0 > 1 && nl1 > 1) {
+			o.clear(); os.clear(); k1.clear();
+			for (unsigned a = 0; a + 1 < nl0; ++a)
+				for (unsigned b = 0; b + 1 < nl1; ++b) {
+					const size_t q = (size_t)a * nl1 + b;
+					o.push_back(off(nP, pos_I, a, b)); os.push_back(off(nP, shift_I, a, b)); k1.push_back(S.K1P[q]); k2.push_back(S.K2P[q]);
+					o.push_back(off(nPP, pos_I, a, b)); os.push_back(off(nPP, shift_I, a, b)); k1.push_back(S.K1PP[q]); k2.push_back(S.K2PP[q]);
+				}
+			D.i.count = (long long)o.size();
+			D.i.o = upload(o); D.i.os = upload(os); D.i.K1 = upload(k1); D.i.K2 = upload(k2);
+			D.i.store = dalloc<float>(o.size());
+			D.i.X = d_I;
+		}
+		sheet_dev.push_back(D);
+	}
+	return 0;
+}
+
 int Engine::build_mur()
 {
 	memset(&pMur, 0, sizeof(pMur));
@@ -791,6 +866,7 @@ int Engine::finalize()
 	if (build_exc()) return 1;
 	if (build_lorentz()) return 1;
 	if (build_rlc()) return 1;
+	if (build_sheets()) return 1;
 	ss_on = false;
 	if (ss_period) {
 		const unsigned cnt = (unsigned)ss_dir.size();
@@ -858,6 +934,9 @@ void Engine::build_schedule()
 		if (lor_dev[o].v_on) (labels.push_back("lorentz_pre_V"), step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_pre, lor_dev[o].v, lor_dev[o].v.count, s); }));
 	for (size_t r = 0; r < rlc_dev.size(); ++r)
 		(labels.push_back("rlc_pre"), step.push_back([this, r](cudaStream_t s) { launch1d(k_rlc_pre, rlc_dev[r], rlc_dev[r].count, s); }));
+	// absorbing sheets were inserted last (openems.cpp:1242-1243): first in the apply list, last here
+	for (size_t a = 0; a < sheet_dev.size(); ++a)
+		(labels.push_back("sheet_pre_V"), step.push_back([this, a](cudaStream_t s) { launch1d(k_sheet_pre, sheet_dev[a].v, sheet_dev[a].v.count, s); }));
 	// ---- multi-GPU: the ghost H plane of this step must have arrived
 	if (multi && peer_lo)
 		(labels.push_back("halo_wait_H"), step.push_back([this](cudaStream_t s) {
@@ -871,7 +950,9 @@ void Engine::build_schedule()
 			if (i16) { if (has_pml) k_update_E<uint16_t, true><<<g, block, 0, s>>>(pE); else k_update_E<uint16_t, false><<<g, block, 0, s>>>(pE); }
 			else { if (has_pml) k_update_E<uint32_t, true><<<g, block, 0, s>>>(pE); else k_update_E<uint32_t, false><<<g, block, 0, s>>>(pE); }
 		}));
-	// ---- post-voltage hooks (UPML fused), then Mur post
+	// ---- post-voltage hooks (UPML fused), then the absorbing sheets, then Mur post
+	for (size_t a = sheet_dev.size(); a-- > 0;)
+		(labels.push_back("sheet_post_V"), step.push_back([this, a](cudaStream_t s) { launch1d(k_sheet_post, sheet_dev[a].v, sheet_dev[a].v.count, s); }));
 	if (pMur.nplanes) (labels.push_back("mur_post"), step.push_back([this](cudaStream_t s) { launch1d(k_mur_post, pMur, pMur.total, s); }));
 	// ---- apply-voltage hooks in list order: SteadyState, RLC, Lorentz, Mur, Excitation
 	auto ss_launch = [this](const SsParams& q, cudaStream_t s) {
@@ -880,6 +961,8 @@ void Engine::build_schedule()
 		k_ss_snapshot<<<8, 256, 0, s>>>(q);
 	};
 	if (ss_on) (labels.push_back("steadystate"), step.push_back([this, ss_launch](cudaStream_t s) { ss_launch(pSs, s); }));
+	for (size_t a = sheet_dev.size(); a-- > 0;)
+		(labels.push_back("sheet_apply_V"), step.push_back([this, a](cudaStream_t s) { launch1d(k_sheet_apply_V, sheet_dev[a].v, sheet_dev[a].v.count, s); }));
 	for (size_t r = rlc_dev.size(); r-- > 0;) // same priority: reversed insertion order
 		(labels.push_back("rlc_apply"), step.push_back([this, r](cudaStream_t s) { launch1d(k_rlc_apply, rlc_dev[r], rlc_dev[r].count, s); }));
 	for (size_t o = 0; o < lor_dev.size(); ++o)
@@ -896,6 +979,8 @@ void Engine::build_schedule()
 	// ---- pre-current hooks: Lorentz (UPML fused)
 	for (size_t o = 0; o < lor_dev.size(); ++o)
 		if (lor_dev[o].i_on) (labels.push_back("lorentz_pre_I"), step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_pre, lor_dev[o].i, lor_dev[o].i.count, s); }));
+	for (size_t a = 0; a < sheet_dev.size(); ++a)
+		if (sheet_dev[a].i.count) (labels.push_back("sheet_pre_I"), step.push_back([this, a](cudaStream_t s) { launch1d(k_sheet_pre, sheet_dev[a].i, sheet_dev[a].i.count, s); }));
 	if (multi && peer_hi)
 		(labels.push_back("halo_wait_E"), step.push_back([this](cudaStream_t s) {
 			WaitParams w{d_flagE, d_numTS, 1u, d_halo_err, 4000000000ll};
@@ -913,7 +998,11 @@ void Engine::build_schedule()
 			if (i16) launch1d(k_upml_untouched_H<uint16_t>, pEdge, pEdge.count, s);
 			else launch1d(k_upml_untouched_H<uint32_t>, pEdge, pEdge.count, s);
 		}));
-	// ---- apply-current hooks: Lorentz, Excitation
+	// ---- post-current and apply-current hooks: absorbing sheets (super-absorption), Lorentz, Excitation
+	for (size_t a = sheet_dev.size(); a-- > 0;)
+		if (sheet_dev[a].i.count) (labels.push_back("sheet_post_I"), step.push_back([this, a](cudaStream_t s) { launch1d(k_sheet_post, sheet_dev[a].i, sheet_dev[a].i.count, s); }));
+	for (size_t a = sheet_dev.size(); a-- > 0;)
+		if (sheet_dev[a].i.count) (labels.push_back("sheet_apply_I"), step.push_back([this, a](cudaStream_t s) { launch1d(k_sheet_apply_I, sheet_dev[a].i, sheet_dev[a].i.count, s); }));
 	for (size_t o = 0; o < lor_dev.size(); ++o)
 		if (lor_dev[o].i_on) (labels.push_back("lorentz_apply_I"), step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_apply, lor_dev[o].i, lor_dev[o].i.count, s); }));
 	if (pExc[1].groups) (labels.push_back("excite_I"), step.push_back([this](cudaStream_t s) { launch1d(k_excite, pExc[1], pExc[1].groups, s); }));
@@ -977,6 +1066,17 @@ int Engine::build_fix_list()
 				pos[M.ny] = M.line; pos[nyP] = a; pos[nyPP] = b;
 				add(nyP, pos[0], pos[1], pos[2]);
 				add(nyPP, pos[0], pos[1], pos[2]);
+			}
+	}
+	for (const SheetHost& S : h_sheet) { // Apply2Voltages overwrites the two tangential components on the sheet
+		const int nP = (S.ny + 1) % 3, nPP = (S.ny + 2) % 3;
+		long long pos[3];
+		pos[S.ny] = S.x0[S.ny];
+		for (unsigned a = S.x0[nP]; a <= S.x1[nP]; ++a)
+			for (unsigned b = S.x0[nPP]; b <= S.x1[nPP]; ++b) {
+				pos[nP] = a; pos[nPP] = b;
+				add(nP, pos[0], pos[1], pos[2]);
+				add(nPP, pos[0], pos[1], pos[2]);
 			}
 	}
 	const ExcHost& E = h_exc[0];
@@ -1178,6 +1278,10 @@ void Engine::build_schedule_fused()
 		X.hA = d_tab[5]; X.hB = d_tab[6];
 		X.cell = d_fix_cells; X.count = fix_count;
 		X.pitch = pitch; X.plane = plane; X.comp = comp;
+		for (size_t a = 0; a < sheet_dev.size(); ++a) {
+			// index 0: hooks that read the source set (pre), 1: hooks on the destination set (post, apply)
+			pShV[par][a] = sheet_dev[a].v; pShI[par][a] = sheet_dev[a].i;
+		}
 		pMurS[par] = pMur; pMurS[par].V = sV[S];
 		pMurD[par] = pMur; pMurD[par].V = sV[D];
 		pExcD[par][0] = pExc[0]; pExcD[par][0].X = sV[D];
@@ -1189,6 +1293,15 @@ void Engine::build_schedule_fused()
 
 		// ---- pre-voltage hooks on the source set
 		if (pMur.nplanes) { lab("mur_pre"); L.push_back([this, par](cudaStream_t s) { launch1d(k_mur_pre, pMurS[par], pMurS[par].total, s); }); }
+		// absorbing sheets: both pre hooks read timestep-n values -> the source set, before k_shell_E touches it
+		for (size_t a = 0; a < sheet_dev.size(); ++a) {
+			lab("sheet_pre_V");
+			L.push_back([this, par, a](cudaStream_t s) { SheetParams q = pShV[par][a]; q.X = sV[par]; launch1d(k_sheet_pre, q, q.count, s); });
+			if (sheet_dev[a].i.count) {
+				lab("sheet_pre_I");
+				L.push_back([this, par, a](cudaStream_t s) { SheetParams q = pShI[par][a]; q.X = sI[par]; launch1d(k_sheet_pre, q, q.count, s); });
+			}
+		}
 		if (multi && peer_lo) {
 			lab("halo_wait_H");
 			L.push_back([this](cudaStream_t s) {
@@ -1233,6 +1346,10 @@ void Engine::build_schedule_fused()
 			else { if (has_pml) k_fused_EH<uint32_t, true><<<g, block, 0, s>>>(q); else k_fused_EH<uint32_t, false><<<g, block, 0, s>>>(q); }
 		});
 		// ---- post / apply voltage hooks on the destination set
+		for (size_t a = sheet_dev.size(); a-- > 0;) {
+			lab("sheet_post_V");
+			L.push_back([this, par, a](cudaStream_t s) { SheetParams q = pShV[par][a]; q.X = sV[par ^ 1]; launch1d(k_sheet_post, q, q.count, s); });
+		}
 		if (pMur.nplanes) {
 			lab("mur_post"); L.push_back([this, par](cudaStream_t s) { launch1d(k_mur_post, pMurD[par], pMurD[par].total, s); });
 		}
@@ -1245,6 +1362,10 @@ void Engine::build_schedule_fused()
 				k_ss_energy<<<148 * 2, dim3(32, 8), 0, s>>>(q);
 				k_ss_snapshot<<<8, 256, 0, s>>>(q);
 			});
+		}
+		for (size_t a = sheet_dev.size(); a-- > 0;) {
+			lab("sheet_apply_V");
+			L.push_back([this, par, a](cudaStream_t s) { SheetParams q = pShV[par][a]; q.X = sV[par ^ 1]; launch1d(k_sheet_apply_V, q, q.count, s); });
 		}
 		if (pMur.nplanes) {
 			lab("mur_apply"); L.push_back([this, par](cudaStream_t s) { launch1d(k_mur_apply, pMurD[par], pMurD[par].total, s); });
@@ -1291,6 +1412,17 @@ void Engine::build_schedule_fused()
 				else { if (has_pml) k_update_H<uint32_t, true><<<g, block, 0, s>>>(q); else k_update_H<uint32_t, false><<<g, block, 0, s>>>(q); }
 			});
 		}
+		// ---- post / apply current hooks of the absorbing sheets: H of the destination set is final here
+		for (size_t a = sheet_dev.size(); a-- > 0;)
+			if (sheet_dev[a].i.count) {
+				lab("sheet_post_I");
+				L.push_back([this, par, a](cudaStream_t s) { SheetParams q = pShI[par][a]; q.X = sI[par ^ 1]; launch1d(k_sheet_post, q, q.count, s); });
+			}
+		for (size_t a = sheet_dev.size(); a-- > 0;)
+			if (sheet_dev[a].i.count) {
+				lab("sheet_apply_I");
+				L.push_back([this, par, a](cudaStream_t s) { SheetParams q = pShI[par][a]; q.X = sI[par ^ 1]; launch1d(k_sheet_apply_I, q, q.count, s); });
+			}
 		if (pExc[1].groups) { lab("excite_I"); L.push_back([this, par](cudaStream_t s) { launch1d(k_excite, pExcD[par][1], pExcD[par][1].groups, s); }); }
 		if (multi && peer_hi) {
 			lab("halo_push_H");
@@ -1487,6 +1619,10 @@ int Engine::reset()
 		CK(cudaMemsetAsync(d_flux_v, 0, (size_t)flux_floats * sizeof(float), stream));
 		CK(cudaMemsetAsync(d_flux_i, 0, (size_t)flux_floats * sizeof(float), stream));
 		if (d_flux_v2) CK(cudaMemsetAsync(d_flux_v2, 0, (size_t)flux_floats * sizeof(float), stream));
+	}
+	for (SheetDev& D : sheet_dev) {
+		CK(cudaMemsetAsync(D.v.store, 0, (size_t)D.v.count * sizeof(float), stream));
+		if (D.i.count) CK(cudaMemsetAsync(D.i.store, 0, (size_t)D.i.count * sizeof(float), stream));
 	}
 	if (pMur.nplanes) {
 		CK(cudaMemsetAsync(pMur.vP, 0, (size_t)pMur.total * sizeof(float), stream));

@@ -53,6 +53,13 @@ struct DumpHost {
 	std::vector<void*> dev_allocs;
 };
 
+struct SheetHost {    // one local absorbing sheet (Operator_Ext_Absorbing_BC)
+	int ny, type, positive;
+	unsigned x0[3], x1[3];
+	std::vector<float> K1P, K1PP, K2P, K2PP;
+};
+struct SheetDev { SheetParams v, i; };
+
 struct FdHost {
 	int dump;          // time-domain dump this spectrum is taken from
 	unsigned nfreq;
@@ -108,6 +115,12 @@ public:
 	int fd_accumulate(int fd_id, const float* w);
 	int read_fd(int fd_id, float* out, unsigned* samples);
 	std::vector<FdHost> fds;
+	int add_absorbing_sheet(int ny, const unsigned x0[3], const unsigned x1[3], int positive, int type, const float* K1P,
+	                        const float* K1PP, const float* K2P, const float* K2PP);
+	int build_sheets();
+	std::vector<SheetHost> h_sheet;
+	std::vector<SheetDev> sheet_dev;
+	SheetParams pShV[2][8], pShI[2][8]; // per parity of the one-pass schedule: [0] works on the source set, [1] on the destination set
 	int add_mode_match(int is_H, int ny, const unsigned start[3], const unsigned stop[3], const double* dist0, const double* dist1,
 	                   const double* area, const double* const el[3], const double* const del[3], int* id);
 	int read_mode_match(int id, double out[2]);

@@ -561,6 +561,47 @@ __global__ void k_rlc_apply(const __grid_constant__ RlcParams p)
 	p.V[p.tgt[i]] = vd0;
 }
 
+// ---------------------------------------------------------------------------------------
+// Local absorbing sheets: Engine_Ext_Absorbing_BC engine_ext_absorbing_bc.cpp:108-366 (1st order
+// Mur on a sheet inside the mesh, optionally with super-absorption on H).  One list entry per
+// sheet point and tangential component; pre/post/apply exactly as the reference's six hooks.
+// ---------------------------------------------------------------------------------------
+struct SheetParams {
+	float* X;              // V or I of the set the hook works on
+	const long long* o;    // [count] offset of the sheet value (incl. component)
+	const long long* os;   // [count] offset of the shifted value
+	const float* K1;       // [count]
+	const float* K2;       // [count] (current lists of super-absorbing sheets)
+	float* store;          // [count] m_V_nyP/nyPP or m_I_nyP/nyPP
+	long long count;
+};
+__global__ void k_sheet_pre(const __grid_constant__ SheetParams p)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= p.count) return;
+	p.store[t] = fsub(p.X[p.os[t]], fmul(p.K1[t], p.X[p.o[t]]));          // :128-129, :246-247
+}
+__global__ void k_sheet_post(const __grid_constant__ SheetParams p)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= p.count) return;
+	p.store[t] = fadd(p.store[t], fmul(p.K1[t], p.X[p.os[t]]));           // :164-165, :303-304
+}
+__global__ void k_sheet_apply_V(const __grid_constant__ SheetParams p)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= p.count) return;
+	p.X[p.o[t]] = p.store[t];                                               // :199-200
+}
+__global__ void k_sheet_apply_I(const __grid_constant__ SheetParams p)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= p.count) return;
+	// (Hsa*K2 + Hc)/(K2 + 1.0): float numerator, double denominator                       :355-356
+	const float num = fadd(fmul(p.store[t], p.K2[t]), p.X[p.o[t]]);
+	p.X[p.o[t]] = (float)__ddiv_rn((double)num, __dadd_rn((double)p.K2[t], 1.0));
+}
+
 __global__ void k_tick(unsigned* numTS) { *numTS += 1; }
 
 // upload helper: operator index of the padding cells (i >= nx) points at the all-zero entry

@@ -60,6 +60,7 @@ class Operator_CUDA:
         self.mur = []
         self.lorentz = []
         self.rlc = []
+        self.sheets = []
         self.steadystate = None
         self.mesh = None  # (x, y, z, gridDelta) for field probes / dumps
 
@@ -130,6 +131,11 @@ class Operator_CUDA:
             pos3 = np.array([[p[a] for p in pts for _ in range(3)] for a in range(3)], np.uint32)
             direction = np.array([d for _ in pts for d in range(3)], np.uint32)
         self.steadystate = (int(period_ts), _u32(pos3), _u32(direction))
+
+    def AddAbsorbingSheet(self, ny, x0, x1, normal_positive, abc_type, K1P, K1PP, K2P=None, K2PP=None):
+        """Operator_Ext_Absorbing_BC: sheet on mesh indices x0..x1 normal to ny, coefficient tables [nl0][nl1]"""
+        self.sheets.append((int(ny), _u32(x0), _u32(x1), int(bool(normal_positive)), int(abc_type), _f32(K1P), _f32(K1PP),
+                            None if K2P is None else _f32(K2P), None if K2PP is None else _f32(K2PP)))
 
     def AddLumpedRLC(self, direction, pos3, coeffs):
         names = ("ilv", "i2v", "vvd", "vv2", "vj1", "vj2", "ib0", "b1", "b2")
@@ -217,6 +223,9 @@ class Engine_CUDA:
                 self._ck(L.oems_cuda_add_lorentz(h, pos3.shape[1], _ptr(pos3, _up), *[_ptr(a, _fp) for a in co]))
             for d, pos3, co in op.rlc:
                 self._ck(L.oems_cuda_add_rlc(h, len(d), _ptr(d, _ip), _ptr(pos3, _up), *[_ptr(a, _fp) for a in co]))
+            for ny, x0, x1, pos, ty, k1p, k1pp, k2p, k2pp in op.sheets:
+                self._ck(L.oems_cuda_add_absorbing_sheet(h, ny, _ptr(x0, _up), _ptr(x1, _up), pos, ty, _ptr(k1p, _fp), _ptr(k1pp, _fp),
+                                                         None if k2p is None else _ptr(k2p, _fp), None if k2pp is None else _ptr(k2pp, _fp)))
             if op.steadystate is not None:
                 per, pos3, d = op.steadystate
                 self._ck(L.oems_cuda_add_steadystate(h, per, len(d), _ptr(pos3, _up), _ptr(d, _up)))

@@ -1372,6 +1372,160 @@ static void add_ext(orc_sim* s, int prio, void* data, hook_fn preV, hook_fn post
 	e->preI = preI; e->postI = postI; e->applyI = applyI;
 }
 
+/* ---- local absorbing sheets --------------------------------------------------------------
+   openEMS::SetupAbsorbingSheets openems.cpp:411-441 (one extension per primitive, added after
+   the lumped RLC extension, :1242-1243), Operator_Ext_Absorbing_BC::SetInitParams / BuildExtension
+   operator_ext_absorbing_bc.cpp:60-245, Engine_Ext_Absorbing_BC engine_ext_absorbing_bc.cpp:38-366.
+   x0/x1 are the snapped mesh indices of the sheet (m_sheetX0/X1). */
+int orc_add_absorbing_sheet(orc_sim* s, const unsigned x0[3], const unsigned x1[3], int normal_positive, int type,
+                            double phase_velocity)
+{
+	if (s->built || s->nabc >= 8) return -1;
+	abc_t* a = &s->abc[s->nabc];
+	memset(a, 0, sizeof(*a));
+	int sheet = 0;
+	a->ny = -1;
+	for (int d = 0; d < 3; ++d) {
+		a->x0[d] = x0[d]; a->x1[d] = x1[d];
+		unsigned nc = x1[d] - x0[d] + 1;
+		sheet += nc == 1;
+		if (nc == 1) a->ny = d;
+	}
+	if (sheet != 1) return -2; /* "Absorbing sheet is not a sheet! Skipping." :112-117 */
+	a->phase_velocity = phase_velocity == 0.0 ? C0 : phase_velocity; /* :120-127 */
+	a->type = type; a->positive = normal_positive != 0;
+	++s->nabc;
+	return 0;
+}
+static void build_abc(orc_sim* s, abc_t* a)
+{
+	/* BuildExtension :138-245 */
+	a->nyP = (a->ny + 1) % 3; a->nyPP = (a->ny + 2) % 3;
+	unsigned pos[3] = {0, 0, 0};
+	pos[a->ny] = a->x0[a->ny];
+	const double delta = fabs(orc_edge_length(s, a->ny, pos, 0));
+	const float vt = (float)(a->phase_velocity * s->dT); /* FDTD_FLOAT vt_nyP = m_phaseVelocity*dT */
+	a->nl[0] = a->x1[a->nyP] - a->x0[a->nyP] + 1;
+	a->nl[1] = a->x1[a->nyPP] - a->x0[a->nyPP] + 1;
+	const size_t n = (size_t)a->nl[0] * a->nl[1];
+	a->K1P = xcalloc(n, sizeof(float)); a->K1PP = xcalloc(n, sizeof(float));
+	a->K2P = xcalloc(n, sizeof(float)); a->K2PP = xcalloc(n, sizeof(float));
+	a->vP = xcalloc(n, sizeof(float)); a->vPP = xcalloc(n, sizeof(float));
+	a->iP = xcalloc(n, sizeof(float)); a->iPP = xcalloc(n, sizeof(float));
+	for (size_t q = 0; q < n; ++q) {
+		a->K1P[q] = (float)((vt - delta) / (vt + delta));
+		a->K1PP[q] = (float)((vt - delta) / (vt + delta));
+		if (a->type == 2) { a->K2P[q] = (float)(vt / delta); a->K2PP[q] = (float)(vt / delta); }
+	}
+	/* Engine_Ext_Absorbing_BC ctor :64-71 */
+	a->shift_V = a->x0[a->ny] + (a->positive ? 1 : -1);
+	a->pos_I = a->x0[a->ny] + (a->positive ? 0 : -1);
+	a->shift_I = a->x0[a->ny] + (a->positive ? 1 : -2);
+}
+static void abc_preV(orc_sim* s, ext_t* e, int tid, int nth)
+{
+	(void)nth;
+	if (tid != 0) return; /* SetNumberOfThreads(1) :79 */
+	abc_t* a = e->data;
+	unsigned pos[3] = {0, 0, 0}, ps[3] = {0, 0, 0};
+	pos[a->ny] = a->x0[a->ny]; ps[a->ny] = a->shift_V;
+	for (unsigned i = 0; i < a->nl[0]; ++i) {
+		ps[a->nyP] = pos[a->nyP] = a->x0[a->nyP] + i;
+		for (unsigned j = 0; j < a->nl[1]; ++j) {
+			ps[a->nyPP] = pos[a->nyPP] = a->x0[a->nyPP] + j;
+			size_t o = (size_t)i * a->nl[1] + j;
+			a->vP[o] = VOLT(s, a->nyP, ps) - a->K1P[o] * VOLT(s, a->nyP, pos);
+			a->vPP[o] = VOLT(s, a->nyPP, ps) - a->K1PP[o] * VOLT(s, a->nyPP, pos);
+		}
+	}
+}
+static void abc_postV(orc_sim* s, ext_t* e, int tid, int nth)
+{
+	(void)nth;
+	if (tid != 0) return;
+	abc_t* a = e->data;
+	unsigned ps[3] = {0, 0, 0};
+	ps[a->ny] = a->shift_V;
+	for (unsigned i = 0; i < a->nl[0]; ++i) {
+		ps[a->nyP] = a->x0[a->nyP] + i;
+		for (unsigned j = 0; j < a->nl[1]; ++j) {
+			ps[a->nyPP] = a->x0[a->nyPP] + j;
+			size_t o = (size_t)i * a->nl[1] + j;
+			a->vP[o] += a->K1P[o] * VOLT(s, a->nyP, ps);
+			a->vPP[o] += a->K1PP[o] * VOLT(s, a->nyPP, ps);
+		}
+	}
+}
+static void abc_applyV(orc_sim* s, ext_t* e, int tid, int nth)
+{
+	(void)nth;
+	if (tid != 0) return;
+	abc_t* a = e->data;
+	unsigned pos[3] = {0, 0, 0};
+	pos[a->ny] = a->x0[a->ny];
+	for (unsigned i = 0; i < a->nl[0]; ++i) {
+		pos[a->nyP] = a->x0[a->nyP] + i;
+		for (unsigned j = 0; j < a->nl[1]; ++j) {
+			pos[a->nyPP] = a->x0[a->nyPP] + j;
+			size_t o = (size_t)i * a->nl[1] + j;
+			VOLT(s, a->nyP, pos) = a->vP[o];
+			VOLT(s, a->nyPP, pos) = a->vPP[o];
+		}
+	}
+}
+static void abc_preI(orc_sim* s, ext_t* e, int tid, int nth)
+{
+	(void)nth;
+	abc_t* a = e->data;
+	if (tid != 0 || a->type != 2) return; /* super-absorption only :232-233 */
+	unsigned pos[3] = {0, 0, 0}, ps[3] = {0, 0, 0};
+	pos[a->ny] = a->pos_I; ps[a->ny] = a->shift_I;
+	for (unsigned i = 0; i + 1 < a->nl[0]; ++i) {
+		ps[a->nyP] = pos[a->nyP] = a->x0[a->nyP] + i;
+		for (unsigned j = 0; j + 1 < a->nl[1]; ++j) {
+			ps[a->nyPP] = pos[a->nyPP] = a->x0[a->nyPP] + j;
+			size_t o = (size_t)i * a->nl[1] + j;
+			a->iP[o] = CURR(s, a->nyP, ps) - a->K1P[o] * CURR(s, a->nyP, pos);
+			a->iPP[o] = CURR(s, a->nyPP, ps) - a->K1PP[o] * CURR(s, a->nyPP, pos);
+		}
+	}
+}
+static void abc_postI(orc_sim* s, ext_t* e, int tid, int nth)
+{
+	(void)nth;
+	abc_t* a = e->data;
+	if (tid != 0 || a->type != 2) return;
+	unsigned ps[3] = {0, 0, 0};
+	ps[a->ny] = a->shift_I;
+	for (unsigned i = 0; i + 1 < a->nl[0]; ++i) {
+		ps[a->nyP] = a->x0[a->nyP] + i;
+		for (unsigned j = 0; j + 1 < a->nl[1]; ++j) {
+			ps[a->nyPP] = a->x0[a->nyPP] + j;
+			size_t o = (size_t)i * a->nl[1] + j;
+			a->iP[o] += a->K1P[o] * CURR(s, a->nyP, ps);
+			a->iPP[o] += a->K1PP[o] * CURR(s, a->nyPP, ps);
+		}
+	}
+}
+static void abc_applyI(orc_sim* s, ext_t* e, int tid, int nth)
+{
+	(void)nth;
+	abc_t* a = e->data;
+	if (tid != 0 || a->type != 2) return;
+	unsigned pos[3] = {0, 0, 0};
+	pos[a->ny] = a->pos_I;
+	for (unsigned i = 0; i + 1 < a->nl[0]; ++i) {
+		pos[a->nyP] = a->x0[a->nyP] + i;
+		for (unsigned j = 0; j + 1 < a->nl[1]; ++j) {
+			pos[a->nyPP] = a->x0[a->nyPP] + j;
+			size_t o = (size_t)i * a->nl[1] + j;
+			/* (Hsa*K2 + Hc)/(K2 + 1.0): float numerator, double denominator :355-356 */
+			CURR(s, a->nyP, pos) = (float)((a->iP[o] * a->K2P[o] + CURR(s, a->nyP, pos)) / (a->K2P[o] + 1.0));
+			CURR(s, a->nyPP, pos) = (float)((a->iPP[o] * a->K2PP[o] + CURR(s, a->nyPP, pos)) / (a->K2PP[o] + 1.0));
+		}
+	}
+}
+
 /* Engine::SortExtensionByPriority engine.cpp:87-98: stable ascending sort, then reverse */
 static void sort_exts(orc_sim* s)
 {
@@ -1459,6 +1613,11 @@ int orc_build(orc_sim* s, unsigned max_ts)
 		add_ext(s, PRIO_DEFAULT, NULL, lor_preV, NULL, lor_applyV, lor_preI, NULL, lor_applyI);
 	for (int r = 0; r < s->nrlc; ++r)
 		add_ext(s, PRIO_DEFAULT, &s->rlc[r], rlc_preV, NULL, rlc_applyV, NULL, NULL, NULL);
+	/* absorbing sheets come last, openems.cpp:1242-1243 */
+	for (int a = 0; a < s->nabc; ++a) {
+		build_abc(s, &s->abc[a]);
+		add_ext(s, PRIO_DEFAULT, &s->abc[a], abc_preV, abc_postV, abc_applyV, abc_preI, abc_postI, abc_applyI);
+	}
 	sort_exts(s);
 
 	s->volt = xcalloc(3 * nc, sizeof(float));
@@ -1860,4 +2019,21 @@ void orc_mode_match(const orc_sim* s, int is_H, int ny, const unsigned start[3],
 	}
 	out2[1] = purity != 0 ? value * value / purity : 0;
 	out2[0] = value;
+}
+
+
+/* absorbing sheet tables for the engine upload */
+int orc_abc_count(const orc_sim* s) { return s->nabc; }
+void orc_abc_info(const orc_sim* s, int a, int* ny, int* type, int* positive, unsigned x0[3], unsigned x1[3])
+{
+	const abc_t* A = &s->abc[a];
+	*ny = A->ny; *type = A->type; *positive = A->positive;
+	for (int d = 0; d < 3; ++d) { x0[d] = A->x0[d]; x1[d] = A->x1[d]; }
+}
+void orc_abc_coeff(const orc_sim* s, int a, float* K1P, float* K1PP, float* K2P, float* K2PP)
+{
+	const abc_t* A = &s->abc[a];
+	const size_t n = (size_t)A->nl[0] * A->nl[1];
+	memcpy(K1P, A->K1P, n * sizeof(float)); memcpy(K1PP, A->K1PP, n * sizeof(float));
+	memcpy(K2P, A->K2P, n * sizeof(float)); memcpy(K2PP, A->K2PP, n * sizeof(float));
 }

@@ -138,6 +138,13 @@ void orc_fd_accumulate(float* acc, const float* td, size_t n, const float w[2]);
 /* ProcessModeMatch::CalcMultipleIntegrals Common/processmodematch.cpp:222-266; out2 = {value, purity ratio} */
 void orc_mode_match(const orc_sim* s, int is_H, int ny, const unsigned start[3], const unsigned stop[3],
                     const double* dist0, const double* dist1, double out2[2]);
+/* local absorbing sheets (Operator_Ext_Absorbing_BC / Engine_Ext_Absorbing_BC); x0/x1 mesh indices
+   of the sheet, type 1 = MUR_1ST, 2 = MUR_1ST_SA, phase_velocity 0 -> C0; call before orc_build */
+int orc_add_absorbing_sheet(orc_sim* s, const unsigned x0[3], const unsigned x1[3], int normal_positive, int type,
+                            double phase_velocity);
+int orc_abc_count(const orc_sim* s);
+void orc_abc_info(const orc_sim* s, int a, int* ny, int* type, int* positive, unsigned x0[3], unsigned x1[3]);
+void orc_abc_coeff(const orc_sim* s, int a, float* K1P, float* K1PP, float* K2P, float* K2PP);
 /* mesh helpers, operator.cpp:143-206 */
 double orc_edge_length(const orc_sim* s, int n, const unsigned pos[3], int dual);
 double orc_disc_line(const orc_sim* s, int n, unsigned pos, int dual);

@@ -45,6 +45,16 @@ typedef struct {
 	float *vP, *vPP;       /* engine state */
 } mur_t;
 
+/* Operator_Ext_Absorbing_BC / Engine_Ext_Absorbing_BC: local absorbing sheet */
+typedef struct {
+	int ny, nyP, nyPP, type, positive;     /* type 1: MUR_1ST, 2: MUR_1ST_SA */
+	unsigned x0[3], x1[3], nl[2];
+	double phase_velocity;
+	unsigned shift_V, pos_I, shift_I;
+	float *K1P, *K1PP, *K2P, *K2PP;        /* ArrayIJ [i][j] */
+	float *vP, *vPP, *iP, *iPP;            /* engine state */
+} abc_t;
+
 typedef struct {
 	unsigned count;
 	int volt_on, curr_on, volt_lor_on, curr_lor_on;
@@ -114,6 +124,7 @@ struct orc_sim {
 	int lor_order; lor_order_t lor[MAX_ORDER];
 	rlc_t* rlc; int nrlc;
 	ss_t* ss;
+	abc_t abc[8]; int nabc;
 
 	/* engine */
 	float *volt, *curr;

@@ -57,6 +57,10 @@ def lib():
         "orc_add_lumped_rc": (C.c_int, [vp, _d3, _d3, C.c_int, C.c_double, C.c_double, C.c_int]),
         "orc_add_rlc_raw": (C.c_int, [vp, C.c_uint, C.POINTER(C.c_int), _up] + [_fp] * 9),
         "orc_add_steadystate": (C.c_int, [vp, C.c_uint, C.c_uint, _up, C.POINTER(C.c_int)]),
+        "orc_add_absorbing_sheet": (C.c_int, [vp, _u3, _u3, C.c_int, C.c_int, C.c_double]),
+        "orc_abc_count": (C.c_int, [vp]),
+        "orc_abc_info": (None, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _u3, _u3]),
+        "orc_abc_coeff": (None, [vp, C.c_int, _fp, _fp, _fp, _fp]),
         "orc_steadystate_last_diff": (C.c_double, [vp]),
         "orc_set_excite_gauss": (None, [vp, C.c_double, C.c_double]),
         "orc_set_excite_sinus": (None, [vp, C.c_double]),
@@ -268,6 +272,27 @@ class OracleSim:
         shape = (3, nl[0], nl[1], nl[2])
         return np.ctypeslib.as_array(lib().orc_upml_flux(self._h, b, int(is_curr)),
                                      shape=(int(np.prod(shape)),)).reshape(shape)
+
+    def add_absorbing_sheet(self, x0, x1, normal_positive, abc_type, phase_velocity=0.0):
+        """local absorbing sheet on mesh indices x0..x1 (one direction single-line); type 1 Mur 1st order,
+        2 with super-absorption"""
+        rc = lib().orc_add_absorbing_sheet(self._h, _u3(*x0), _u3(*x1), int(normal_positive), int(abc_type), float(phase_velocity))
+        if rc:
+            raise RuntimeError("orc_add_absorbing_sheet rc=%d" % rc)
+
+    def absorbing_sheets(self):
+        out = []
+        for a in range(lib().orc_abc_count(self._h)):
+            ny, ty, pos = C.c_int(), C.c_int(), C.c_int()
+            x0, x1 = (C.c_uint * 3)(), (C.c_uint * 3)()
+            lib().orc_abc_info(self._h, a, C.byref(ny), C.byref(ty), C.byref(pos), x0, x1)
+            nP, nPP = (ny.value + 1) % 3, (ny.value + 2) % 3
+            n = (x1[nP] - x0[nP] + 1) * (x1[nPP] - x0[nPP] + 1)
+            k = [np.zeros(n, np.float32) for _ in range(4)]
+            lib().orc_abc_coeff(self._h, a, *[v.ctypes.data_as(_fp) for v in k])
+            out.append(dict(ny=ny.value, type=ty.value, positive=pos.value, x0=tuple(x0), x1=tuple(x1),
+                            K1P=k[0], K1PP=k[1], K2P=k[2], K2PP=k[3]))
+        return out
 
     def mur_planes(self):
         out = []

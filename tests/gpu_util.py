@@ -4,7 +4,7 @@ import numpy as np
 from openems_b200 import Operator_CUDA
 
 
-def operator_from_oracle(s, include=("exc", "mur", "upml", "lorentz")):
+def operator_from_oracle(s, include=("exc", "mur", "upml", "lorentz", "sheets")):
     """copies the host-side operator data of an OracleSim into an Operator_CUDA, exactly the
     data Operator_CUDA::CreateEngine would read from the reference's Operator/Operator_Ext_*"""
     op = Operator_CUDA(s.N)
@@ -23,6 +23,11 @@ def operator_from_oracle(s, include=("exc", "mur", "upml", "lorentz")):
     if "upml" in include:
         for b in s.upml_boxes():
             op.AddUPML(b["start"], b["n"], b["vv"], b["vvfn"], b["vvfo"], b["ii"], b["iifn"], b["iifo"])
+    if "sheets" in include:
+        for a in s.absorbing_sheets():
+            sa = a["type"] == 2
+            op.AddAbsorbingSheet(a["ny"], a["x0"], a["x1"], a["positive"], a["type"], a["K1P"], a["K1PP"],
+                                 a["K2P"] if sa else None, a["K2PP"] if sa else None)
     if "lorentz" in include:
         for L in s.lorentz():
             op.AddLorentzOrder(L["pos"], L["v_int"], L["v_ext"], L["v_lor"], L["i_int"], L["i_ext"], L["i_lor"])

@@ -147,3 +147,37 @@ def test_x_slab_boxes_inside_the_one_pass_kernel(n, pml):
         for b, box in enumerate(s.upml_boxes()):
             for w in (0, 1):
                 assert np.array_equal(eng.GetUPMLFlux(b, w, box["n"]).view(np.uint32), s.upml_flux(b, w).view(np.uint32))
+
+
+@pytest.mark.parametrize("case", ["line", "box"])
+def test_local_absorbing_sheets(case):
+    """Engine_Ext_Absorbing_BC (engine_ext_absorbing_bc.cpp:108-366) -- first order
+    Mur sheets inside the mesh, with and without super-absorption, both normal signs, next to UPML and
+    Mur faces; all six hooks in the reference's order, both schedules"""
+    from oracle.pyoracle import OracleSim, EXC_E_SOFT
+    if case == "line":
+        # parallel-plate line along z (Rect_Waveguide_W_Local_Absorbers.py in small): sheets two lines from the ends
+        x, y, z = np.arange(9) * 1e-3, np.arange(8) * 1e-3, np.arange(70) * 1e-3
+        s = OracleSim(x, y, z, 1.0)
+        s.set_bc([BC_PEC, BC_PEC, BC_PMC, BC_PMC, BC_PEC, BC_PEC])
+        s.set_excite_gauss(8e9, 3e9)
+        s.add_excitation((x[0], y[0], z[30]), (x[-1], y[-1], z[30]), EXC_E_SOFT, (1, 0, 0))
+        s.add_absorbing_sheet((0, 0, 2), (8, 7, 2), True, 2, 0.0)
+        s.add_absorbing_sheet((0, 0, 67), (8, 7, 67), False, 2, 3.2e8)
+        steps = (1, 60, 400)
+    else:
+        x, y, z = np.arange(34) * 1e-3, np.cumsum(np.r_[0, np.linspace(1, 1.6, 27)]) * 1e-3, np.arange(30) * 1e-3
+        s = OracleSim(x, y, z, 1.0)
+        s.set_bc([BC_PML, BC_MUR, BC_PEC, BC_PML, BC_PMC, BC_PEC], (5,) * 6)
+        s.set_excite_gauss(6e9, 4e9)
+        c = cases.edge_center((x, y, z), 2, (15, 12, 14))
+        s.add_excitation(c, c, EXC_E_SOFT, (0, 0, 1))
+        s.add_absorbing_sheet((8, 2, 20), (25, 2, 27), True, 1, 0.0)        # y-normal, plain Mur
+        s.add_absorbing_sheet((3, 3, 27), (30, 20, 27), False, 2, 0.0)      # z-normal, super-absorbing, reaches into the UPML
+        s.add_absorbing_sheet((29, 4, 3), (29, 18, 12), False, 2, 2.5e8)    # x-normal
+        steps = (1, 25, 120)
+    s.build()
+    assert len(s.absorbing_sheets()) in (2, 3)
+    eng = run_both(s, steps=steps, what="absorbing sheets " + case)
+    names = [n for n, _ in eng.TimeSchedule(0)]
+    assert "fused_EH" in names and "sheet_apply_V" in names and "sheet_apply_I" in names
