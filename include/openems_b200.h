@@ -116,6 +116,16 @@ int oems_cuda_add_rlc(oems_cuda_engine* h, unsigned count, const int* dir, const
 int oems_cuda_add_steadystate(oems_cuda_engine* h, unsigned period_ts, unsigned count,
                               const unsigned* pos3, const unsigned* dir);
 int oems_cuda_steadystate_check(oems_cuda_engine* h, double* last_diff, unsigned* n_checks);
+/* Operator_Ext_TFSF (plane-wave excitation, FDTD/extensions/operator_ext_tfsf.h): m_Start, m_Stop,
+   m_ActiveDir[n][l] as active6[2n+l], and the per-face tables m_VoltDelay / m_VoltDelayDelta /
+   m_VoltAmp / m_CurrDelay / m_CurrDelayDelta / m_CurrAmp [n][l][c] passed as 12 pointers each, index
+   (n*2+l)*2+c, NULL for inactive faces; each table has numLines[nP]*numLines[nPP] entries.  The
+   engine runs Engine_Ext_TFSF::DoPostVoltageUpdates / DoPostCurrentUpdates
+   (engine_ext_tfsf.cpp:36-215) on the device, in the reference's update order and C++ arithmetic
+   types; the delay lookup is evaluated per update (same expression as m_DelayLookup). */
+int oems_cuda_set_tfsf(oems_cuda_engine* h, const unsigned* start3, const unsigned* stop3, const int* active6,
+                       const unsigned* const* volt_delay, const float* const* volt_delay_delta, const float* const* volt_amp,
+                       const unsigned* const* curr_delay, const float* const* curr_delay_delta, const float* const* curr_amp);
 /* Operator_Ext_Absorbing_BC (local absorbing sheet, one per CSXCAD primitive, openems.cpp:411-441;
    FDTD/extensions/operator_ext_absorbing_bc.h:94-113): m_ny, m_sheetX0 / m_sheetX1 (mesh indices),
    m_normalSignPositive, m_ABCtype (1 MUR_1ST, 2 MUR_1ST_SA) and the ArrayIJ coefficient tables

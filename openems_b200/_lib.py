@@ -53,6 +53,7 @@ SIGNATURES = {
     "oems_cuda_add_rlc": (C.c_int, [_vp, C.c_uint, _ip, _up] + [_fp] * 9),
     "oems_cuda_add_steadystate": (C.c_int, [_vp, C.c_uint, C.c_uint, _up, _up]),
     "oems_cuda_steadystate_check": (C.c_int, [_vp, _dp, _up]),
+    "oems_cuda_set_tfsf": (C.c_int, [_vp, _up, _up, C.POINTER(C.c_int), C.POINTER(_up), C.POINTER(_fp), C.POINTER(_fp), C.POINTER(_up), C.POINTER(_fp), C.POINTER(_fp)]),
     "oems_cuda_add_absorbing_sheet": (C.c_int, [_vp, C.c_int, _up, _up, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
     "oems_cuda_finalize": (C.c_int, [_vp]),
     "oems_cuda_iterate": (C.c_int, [_vp, C.c_uint]),

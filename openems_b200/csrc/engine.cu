@@ -551,6 +551,86 @@ int Engine::build_edge_list()
 	return 0;
 }
 
+// ------------------------------------------------------------------------------ TFSF
+int Engine::set_tfsf(const unsigned start[3], const unsigned stop[3], const int active[6], const unsigned* const* vdelay,
+                     const float* const* vdd, const float* const* vamp, const unsigned* const* cdelay, const float* const* cdd,
+                     const float* const* camp)
+{
+	if (finalized) return fail("engine already finalized");
+	TfsfHost& T = h_tfsf;
+	for (int n = 0; n < 3; ++n) {
+		if (start[n] > stop[n] || stop[n] >= gn[n]) return fail("set_tfsf: box outside the mesh");
+		T.start[n] = start[n]; T.stop[n] = stop[n];
+		T.active[n][0] = active[2 * n] != 0; T.active[n][1] = active[2 * n + 1] != 0;
+		if (T.active[n][0] && start[n] == 0) return fail("set_tfsf: an active low face needs a line below it");
+	}
+	for (int n = 0; n < 3; ++n) {
+		const size_t numP = (size_t)(stop[(n + 1) % 3] - start[(n + 1) % 3] + 1) * (stop[(n + 2) % 3] - start[(n + 2) % 3] + 1);
+		for (int l = 0; l < 2; ++l)
+			for (int c = 0; c < 2; ++c) {
+				const int q = (n * 2 + l) * 2 + c;
+				if (!T.active[n][l]) continue;
+				if (!vdelay[q] || !vdd[q] || !vamp[q] || !cdelay[q] || !cdd[q] || !camp[q]) return fail("set_tfsf: missing table of an active face");
+				T.delay[0][q].assign(vdelay[q], vdelay[q] + numP); T.dd[0][q].assign(vdd[q], vdd[q] + numP); T.amp[0][q].assign(vamp[q], vamp[q] + numP);
+				T.delay[1][q].assign(cdelay[q], cdelay[q] + numP); T.dd[1][q].assign(cdd[q], cdd[q] + numP); T.amp[1][q].assign(camp[q], camp[q] + numP);
+			}
+	}
+	T.on = true;
+	return 0;
+}
+
+int Engine::build_tfsf()
+{
+	memset(pTfsf, 0, sizeof(pTfsf));
+	const TfsfHost& T = h_tfsf;
+	if (!T.on) return 0;
+	if (sig_len == 0) return fail("TFSF without a signal (set_signal)");
+	for (int w = 0; w < 2; ++w) {
+		// the reference's loop nest: n, lower then upper face, i over nP, j over nPP, component nP then nPP
+		std::map<long long, std::vector<std::pair<int, unsigned>>> groups; // target -> (table, point) in order
+		std::vector<long long> order;
+		for (int n = 0; n < 3; ++n) {
+			const int nP = (n + 1) % 3, nPP = (n + 2) % 3;
+			const unsigned nl0 = T.stop[nP] - T.start[nP] + 1, nl1 = T.stop[nPP] - T.start[nPP] + 1;
+			for (int l = 0; l < 2; ++l) {
+				if (!T.active[n][l]) continue;
+				unsigned u = 0;
+				for (unsigned i = 0; i < nl0; ++i)
+					for (unsigned j = 0; j < nl1; ++j, ++u) {
+						unsigned pos[3];
+						pos[nP] = T.start[nP] + i; pos[nPP] = T.start[nPP] + j;
+						pos[n] = l ? T.stop[n] : (w ? T.start[n] - 1 : T.start[n]);
+						if (!owned(pos[2])) continue;
+						for (int c = 0; c < 2; ++c) {
+							const long long t = (long long)(c ? nPP : nP) * comp + cell_off(pos[0], pos[1], pos[2]);
+							auto it = groups.find(t);
+							if (it == groups.end()) { groups[t] = {{(n * 2 + l) * 2 + c, u}}; order.push_back(t); }
+							else it->second.push_back({(n * 2 + l) * 2 + c, u});
+						}
+					}
+			}
+		}
+		if (order.empty()) continue;
+		std::vector<long long> tgt;
+		std::vector<unsigned> gstart, delay;
+		std::vector<float> dd, amp;
+		for (long long t : order) {
+			tgt.push_back(t);
+			gstart.push_back((unsigned)amp.size());
+			for (auto& e : groups[t]) { delay.push_back(T.delay[w][e.first][e.second]); dd.push_back(T.dd[w][e.first][e.second]); amp.push_back(T.amp[w][e.first][e.second]); }
+		}
+		gstart.push_back((unsigned)amp.size());
+		TfsfParams& P = pTfsf[w];
+		P.X = w ? d_I : d_V;
+		P.tgt = upload(tgt); P.gstart = upload(gstart); P.delay = upload(delay); P.dd = upload(dd); P.amp = upload(amp);
+		P.sig = d_sig[w ? 0 : 1]; // "get the current signal since an H-field is added" and vice versa
+		P.numTS = d_numTS;
+		P.groups = (unsigned)tgt.size(); P.length = sig_len; P.period = sig_period;
+		if (!P.tgt || !P.gstart || !P.delay || !P.dd || !P.amp) return fail("out of device memory (TFSF)");
+	}
+	return 0;
+}
+
 // ------------------------------------------------------------------------------ absorbing sheets
 int Engine::add_absorbing_sheet(int ny, const unsigned x0[3], const unsigned x1[3], int positive, int type, const float* K1P,
                                 const float* K1PP, const float* K2P, const float* K2PP)
@@ -867,6 +947,7 @@ int Engine::finalize()
 	if (build_lorentz()) return 1;
 	if (build_rlc()) return 1;
 	if (build_sheets()) return 1;
+	if (build_tfsf()) return 1;
 	ss_on = false;
 	if (ss_period) {
 		const unsigned cnt = (unsigned)ss_dir.size();
@@ -950,7 +1031,8 @@ void Engine::build_schedule()
 			if (i16) { if (has_pml) k_update_E<uint16_t, true><<<g, block, 0, s>>>(pE); else k_update_E<uint16_t, false><<<g, block, 0, s>>>(pE); }
 			else { if (has_pml) k_update_E<uint32_t, true><<<g, block, 0, s>>>(pE); else k_update_E<uint32_t, false><<<g, block, 0, s>>>(pE); }
 		}));
-	// ---- post-voltage hooks (UPML fused), then the absorbing sheets, then Mur post
+	// ---- post-voltage hooks: UPML (fused), TFSF, absorbing sheets, Mur
+	if (pTfsf[0].groups) (labels.push_back("tfsf_V"), step.push_back([this](cudaStream_t s) { launch1d(k_tfsf, pTfsf[0], pTfsf[0].groups, s); }));
 	for (size_t a = sheet_dev.size(); a-- > 0;)
 		(labels.push_back("sheet_post_V"), step.push_back([this, a](cudaStream_t s) { launch1d(k_sheet_post, sheet_dev[a].v, sheet_dev[a].v.count, s); }));
 	if (pMur.nplanes) (labels.push_back("mur_post"), step.push_back([this](cudaStream_t s) { launch1d(k_mur_post, pMur, pMur.total, s); }));
@@ -998,7 +1080,8 @@ void Engine::build_schedule()
 			if (i16) launch1d(k_upml_untouched_H<uint16_t>, pEdge, pEdge.count, s);
 			else launch1d(k_upml_untouched_H<uint32_t>, pEdge, pEdge.count, s);
 		}));
-	// ---- post-current and apply-current hooks: absorbing sheets (super-absorption), Lorentz, Excitation
+	// ---- post-current hooks: UPML (fused), TFSF; then absorbing sheets (super-absorption), Lorentz, Excitation
+	if (pTfsf[1].groups) (labels.push_back("tfsf_I"), step.push_back([this](cudaStream_t s) { launch1d(k_tfsf, pTfsf[1], pTfsf[1].groups, s); }));
 	for (size_t a = sheet_dev.size(); a-- > 0;)
 		if (sheet_dev[a].i.count) (labels.push_back("sheet_post_I"), step.push_back([this, a](cudaStream_t s) { launch1d(k_sheet_post, sheet_dev[a].i, sheet_dev[a].i.count, s); }));
 	for (size_t a = sheet_dev.size(); a-- > 0;)
@@ -1068,6 +1151,21 @@ int Engine::build_fix_list()
 				add(nyPP, pos[0], pos[1], pos[2]);
 			}
 	}
+	if (h_tfsf.on) // DoPostVoltageUpdates adds to the tangential E on the six faces
+		for (int n = 0; n < 3; ++n) {
+			const int nP = (n + 1) % 3, nPP = (n + 2) % 3;
+			for (int l = 0; l < 2; ++l) {
+				if (!h_tfsf.active[n][l]) continue;
+				long long pos[3];
+				pos[n] = l ? h_tfsf.stop[n] : h_tfsf.start[n];
+				for (unsigned a = h_tfsf.start[nP]; a <= h_tfsf.stop[nP]; ++a)
+					for (unsigned b = h_tfsf.start[nPP]; b <= h_tfsf.stop[nPP]; ++b) {
+						pos[nP] = a; pos[nPP] = b;
+						add(nP, pos[0], pos[1], pos[2]);
+						add(nPP, pos[0], pos[1], pos[2]);
+					}
+			}
+		}
 	for (const SheetHost& S : h_sheet) { // Apply2Voltages overwrites the two tangential components on the sheet
 		const int nP = (S.ny + 1) % 3, nPP = (S.ny + 2) % 3;
 		long long pos[3];
@@ -1346,6 +1444,9 @@ void Engine::build_schedule_fused()
 			else { if (has_pml) k_fused_EH<uint32_t, true><<<g, block, 0, s>>>(q); else k_fused_EH<uint32_t, false><<<g, block, 0, s>>>(q); }
 		});
 		// ---- post / apply voltage hooks on the destination set
+		pTfsfD[par][0] = pTfsf[0]; pTfsfD[par][0].X = sV[D];
+		pTfsfD[par][1] = pTfsf[1]; pTfsfD[par][1].X = sI[D];
+		if (pTfsf[0].groups) { lab("tfsf_V"); L.push_back([this, par](cudaStream_t s) { launch1d(k_tfsf, pTfsfD[par][0], pTfsfD[par][0].groups, s); }); }
 		for (size_t a = sheet_dev.size(); a-- > 0;) {
 			lab("sheet_post_V");
 			L.push_back([this, par, a](cudaStream_t s) { SheetParams q = pShV[par][a]; q.X = sV[par ^ 1]; launch1d(k_sheet_post, q, q.count, s); });
@@ -1412,7 +1513,9 @@ void Engine::build_schedule_fused()
 				else { if (has_pml) k_update_H<uint32_t, true><<<g, block, 0, s>>>(q); else k_update_H<uint32_t, false><<<g, block, 0, s>>>(q); }
 			});
 		}
-		// ---- post / apply current hooks of the absorbing sheets: H of the destination set is final here
+		// ---- post-current hook of the TFSF box, then post / apply current hooks of the absorbing sheets: H of the
+		//      destination set is final here
+		if (pTfsf[1].groups) { lab("tfsf_I"); L.push_back([this, par](cudaStream_t s) { launch1d(k_tfsf, pTfsfD[par][1], pTfsfD[par][1].groups, s); }); }
 		for (size_t a = sheet_dev.size(); a-- > 0;)
 			if (sheet_dev[a].i.count) {
 				lab("sheet_post_I");

@@ -53,6 +53,14 @@ struct DumpHost {
 	std::vector<void*> dev_allocs;
 };
 
+struct TfsfHost {     // Operator_Ext_TFSF tables, index (n*2+l)*2+c
+	bool on = false;
+	unsigned start[3], stop[3];
+	int active[3][2];
+	std::vector<unsigned> delay[2][12];
+	std::vector<float> dd[2][12], amp[2][12];
+};
+
 struct SheetHost {    // one local absorbing sheet (Operator_Ext_Absorbing_BC)
 	int ny, type, positive;
 	unsigned x0[3], x1[3];
@@ -118,6 +126,12 @@ public:
 	int add_absorbing_sheet(int ny, const unsigned x0[3], const unsigned x1[3], int positive, int type, const float* K1P,
 	                        const float* K1PP, const float* K2P, const float* K2PP);
 	int build_sheets();
+	int set_tfsf(const unsigned start[3], const unsigned stop[3], const int active[6], const unsigned* const* vdelay, const float* const* vdd,
+	             const float* const* vamp, const unsigned* const* cdelay, const float* const* cdd, const float* const* camp);
+	int build_tfsf();
+	TfsfHost h_tfsf;
+	TfsfParams pTfsf[2];          // voltage / current update lists
+	TfsfParams pTfsfD[2][2];      // per parity of the one-pass schedule (destination set)
 	std::vector<SheetHost> h_sheet;
 	std::vector<SheetDev> sheet_dev;
 	SheetParams pShV[2][8], pShI[2][8]; // per parity of the one-pass schedule: [0] works on the source set, [1] on the destination set

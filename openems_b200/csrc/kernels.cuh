@@ -562,6 +562,52 @@ __global__ void k_rlc_apply(const __grid_constant__ RlcParams p)
 }
 
 // ---------------------------------------------------------------------------------------
+// TFSF plane wave: Engine_Ext_TFSF::DoPostVoltageUpdates / DoPostCurrentUpdates
+// (engine_ext_tfsf.cpp:36-215).  The face loops of the reference are flattened at upload into one
+// ordered update list per field; updates of the same edge (box edges belong to two faces) are
+// grouped and applied by one thread in the reference's order.  Per update:
+//   X = float( X + (1.0 - dd)*amp*sig[lookup[d]] + dd*amp*sig[lookup[d+1]] )
+// with the C++ types of the reference: the first product chain in double, the second in float.
+// ---------------------------------------------------------------------------------------
+struct TfsfParams {
+	float* X;
+	const long long* tgt;      // [groups] field offset incl. component
+	const unsigned* gstart;    // [groups+1]
+	const unsigned* delay;     // m_VoltDelay / m_CurrDelay
+	const float* dd;           // m_VoltDelayDelta / m_CurrDelayDelta
+	const float* amp;          // m_VoltAmp / m_CurrAmp
+	const float* sig;          // current signal for the voltage update and vice versa
+	const unsigned* numTS;
+	unsigned groups, length, period;
+};
+__device__ __forceinline__ unsigned tfsf_lookup(unsigned numTS, unsigned n, unsigned length, unsigned p)
+{
+	unsigned v;
+	if (numTS < n) v = 0;                                  // engine_ext_tfsf.cpp:45-52
+	else if (numTS - n >= length && p == 0) v = 0;
+	else v = numTS - n;
+	if (p > 0) v %= p;
+	return v;
+}
+__global__ void k_tfsf(const __grid_constant__ TfsfParams p)
+{
+	const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= p.groups) return;
+	const unsigned numTS = *p.numTS;
+	float x = p.X[p.tgt[g]];
+	for (unsigned n = p.gstart[g]; n < p.gstart[g + 1]; ++n) {
+		const unsigned d = p.delay[n];
+		const float dd = p.dd[n], amp = p.amp[n];
+		const float s1 = p.sig[tfsf_lookup(numTS, d, p.length, p.period)];
+		const float s2 = p.sig[tfsf_lookup(numTS, d + 1, p.length, p.period)];
+		double acc = __dadd_rn((double)x, __dmul_rn(__dmul_rn(__dsub_rn(1.0, (double)dd), (double)amp), (double)s1));
+		acc = __dadd_rn(acc, (double)fmul(fmul(dd, amp), s2));
+		x = (float)acc;
+	}
+	p.X[p.tgt[g]] = x;
+}
+
+// ---------------------------------------------------------------------------------------
 // Local absorbing sheets: Engine_Ext_Absorbing_BC engine_ext_absorbing_bc.cpp:108-366 (1st order
 // Mur on a sheet inside the mesh, optionally with super-absorption on H).  One list entry per
 // sheet point and tangential component; pre/post/apply exactly as the reference's six hooks.

@@ -61,6 +61,7 @@ class Operator_CUDA:
         self.lorentz = []
         self.rlc = []
         self.sheets = []
+        self.tfsf = None
         self.steadystate = None
         self.mesh = None  # (x, y, z, gridDelta) for field probes / dumps
 
@@ -131,6 +132,12 @@ class Operator_CUDA:
             pos3 = np.array([[p[a] for p in pts for _ in range(3)] for a in range(3)], np.uint32)
             direction = np.array([d for _ in pts for d in range(3)], np.uint32)
         self.steadystate = (int(period_ts), _u32(pos3), _u32(direction))
+
+    def SetTFSF(self, start, stop, active, faces):
+        """Operator_Ext_TFSF tables: active[n][l]; faces[(which, n, l, c)] = (delay uint32, delay_delta f32, amp f32)
+        with which 0 = voltage, 1 = current"""
+        self.tfsf = (_u32(start), _u32(stop), np.ascontiguousarray(np.array(active, np.int32).reshape(6)),
+                     {k: (_u32(v[0]), _f32(v[1]), _f32(v[2])) for k, v in faces.items()})
 
     def AddAbsorbingSheet(self, ny, x0, x1, normal_positive, abc_type, K1P, K1PP, K2P=None, K2PP=None):
         """Operator_Ext_Absorbing_BC: sheet on mesh indices x0..x1 normal to ny, coefficient tables [nl0][nl1]"""
@@ -223,6 +230,21 @@ class Engine_CUDA:
                 self._ck(L.oems_cuda_add_lorentz(h, pos3.shape[1], _ptr(pos3, _up), *[_ptr(a, _fp) for a in co]))
             for d, pos3, co in op.rlc:
                 self._ck(L.oems_cuda_add_rlc(h, len(d), _ptr(d, _ip), _ptr(pos3, _up), *[_ptr(a, _fp) for a in co]))
+            if op.tfsf is not None:
+                st, sp, act, faces = op.tfsf
+                arr = {}
+                for which in (0, 1):
+                    for kind, ctype in ((0, _up), (1, _fp), (2, _fp)):
+                        a = (ctype * 12)()
+                        for n in range(3):
+                            for l in range(2):
+                                for c in range(2):
+                                    f = faces.get((which, n, l, c))
+                                    if f is not None:
+                                        a[(n * 2 + l) * 2 + c] = _ptr(f[kind], ctype)
+                        arr[(which, kind)] = a
+                self._ck(L.oems_cuda_set_tfsf(h, _ptr(st, _up), _ptr(sp, _up), act.ctypes.data_as(C.POINTER(C.c_int)),
+                                              arr[(0, 0)], arr[(0, 1)], arr[(0, 2)], arr[(1, 0)], arr[(1, 1)], arr[(1, 2)]))
             for ny, x0, x1, pos, ty, k1p, k1pp, k2p, k2pp in op.sheets:
                 self._ck(L.oems_cuda_add_absorbing_sheet(h, ny, _ptr(x0, _up), _ptr(x1, _up), pos, ty, _ptr(k1p, _fp), _ptr(k1pp, _fp),
                                                          None if k2p is None else _ptr(k2p, _fp), None if k2pp is None else _ptr(k2pp, _fp)))

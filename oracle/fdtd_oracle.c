@@ -1372,6 +1372,231 @@ static void add_ext(orc_sim* s, int prio, void* data, hook_fn preV, hook_fn post
 	e->preI = preI; e->postI = postI; e->applyI = applyI;
 }
 
+/* ---- TFSF plane wave ---------------------------------------------------------------------
+   Operator_Ext_TFSF::BuildExtension operator_ext_tfsf.cpp:86-406 for ONE plane-wave excitation
+   (excite type 10) on the box of mesh indices start..stop; Engine_Ext_TFSF engine_ext_tfsf.cpp:36-215.
+   frequency <= 0 only: the phase velocity is c0/n (line 160-161); the numeric phase velocity of
+   line 163 (Operator::CalcNumericPhaseVelocity) is not restated. */
+int orc_set_tfsf(orc_sim* s, const unsigned start[3], const unsigned stop[3], const double prop_dir[3], const double e_amp[3])
+{
+	if (s->built) return -1;
+	tfsf_t* t = &s->tfsf;
+	memset(t, 0, sizeof(*t));
+	for (int n = 0; n < 3; ++n) {
+		if (start[n] > stop[n] || stop[n] >= s->N[n]) return -2;
+		t->start[n] = start[n]; t->stop[n] = stop[n];
+		t->prop_dir[n] = prop_dir[n]; t->e_amp[n] = e_amp[n];
+	}
+	t->on = 1;
+	return 0;
+}
+#define PW_DIST(c, o, d) (fabs(((c)[0] - (o)[0]) * (d)[0]) + fabs(((c)[1] - (o)[1]) * (d)[1]) + fabs(((c)[2] - (o)[2]) * (d)[2]))
+static int build_tfsf(orc_sim* s)
+{
+	tfsf_t* t = &s->tfsf;
+	const double dT = s->dT;
+	const double ref_index = sqrt(s->bg[0] * s->bg[1]);
+	double dir_norm = sqrt(t->prop_dir[0] * t->prop_dir[0] + t->prop_dir[1] * t->prop_dir[1] + t->prop_dir[2] * t->prop_dir[2]);
+	if (dir_norm == 0) { t->on = 0; return 0; }                                     /* :134-139 */
+	for (int n = 0; n < 3; ++n) t->prop_dir[n] /= dir_norm;
+	t->ph_vel = C0 / ref_index;                                                       /* :160-161 */
+	double origin[3];
+	int inc_low[3];
+	for (int n = 0; n < 3; ++n) {                                                     /* :173-197 */
+		t->nl[n] = t->stop[n] - t->start[n] + 1;
+		inc_low[n] = t->prop_dir[n] >= 0;
+		t->active[n][0] = t->start[n] != 0;
+		t->active[n][1] = t->stop[n] != s->N[n] - 1;
+		unsigned ui = inc_low[n] ? t->start[n] - 1 : t->stop[n] + 1;
+		origin[n] = orc_disc_line(s, n, ui, 0);
+	}
+	double* E = t->e_amp;
+	double dotEk = E[0] * t->prop_dir[0] + E[1] * t->prop_dir[1] + E[2] * t->prop_dir[2];
+	double angle = acos(dotEk / (E[0] * E[0] + E[1] * E[1] + E[2] * E[2])) / M_PI * 180;
+	if (angle == 0) { t->on = 0; return 0; }                                          /* :202-207 */
+	if (angle != 90)
+		for (int n = 0; n < 3; ++n) E[n] -= t->prop_dir[n] * dotEk;                   /* :208-214 */
+	for (int n = 0; n < 3; ++n) {                                                     /* :217-223 */
+		int nP = (n + 1) % 3, nPP = (n + 2) % 3;
+		t->h_amp[n] = t->prop_dir[nP] * E[nPP] - t->prop_dir[nPP] * E[nP];
+		t->h_amp[n] /= Z0 * sqrt(s->bg[1] / s->bg[0]);
+	}
+	const double unit = s->grid_delta;
+	unsigned max_delay = 0;
+	double coord[3], dist, delay;
+	unsigned pos[3];
+	for (int n = 0; n < 3; ++n) {
+		int nP = (n + 1) % 3, nPP = (n + 2) % 3;
+		pos[n] = 0;
+		pos[nP] = t->start[nP];
+		unsigned numP = t->nl[nP] * t->nl[nPP];
+		if (!t->active[n][0] && !t->active[n][1]) continue;
+		for (int l = 0; l < 2; ++l)
+			for (int c = 0; c < 2; ++c)
+				if (t->active[n][l]) {
+					t->vdelay[n][l][c] = xcalloc(numP, sizeof(unsigned)); t->vdd[n][l][c] = xcalloc(numP, sizeof(float)); t->vamp[n][l][c] = xcalloc(numP, sizeof(float));
+					t->cdelay[n][l][c] = xcalloc(numP, sizeof(unsigned)); t->cdd[n][l][c] = xcalloc(numP, sizeof(float)); t->camp[n][l][c] = xcalloc(numP, sizeof(float));
+				}
+		unsigned ui_pos = 0;
+		for (unsigned i = 0; i < t->nl[nP]; ++i) {
+			pos[nPP] = t->start[nPP];
+			for (unsigned j = 0; j < t->nl[nPP]; ++j) {
+#define TF_SET(DEL, DD, AMP, l, c, extra, ampval) do { \
+	delay = dist * unit / t->ph_vel / dT + (extra); \
+	if ((unsigned)delay > max_delay) max_delay = (unsigned)delay; \
+	t->DEL[n][l][c][ui_pos] = (unsigned)floor(delay); \
+	t->DD[n][l][c][ui_pos] = (float)(delay - floor(delay)); \
+	t->AMP[n][l][c][ui_pos] = (float)(ampval); } while (0)
+				/* current updates :257-305 */
+				pos[n] = t->start[n];
+				if (t->active[n][0]) {
+					yee_coords(s, nP, pos, coord, 0); dist = PW_DIST(coord, origin, t->prop_dir);
+					TF_SET(cdelay, cdd, camp, 0, 1, 0.0, E[nP] * orc_edge_length(s, nP, pos, 0));
+					yee_coords(s, nPP, pos, coord, 0); dist = PW_DIST(coord, origin, t->prop_dir);
+					TF_SET(cdelay, cdd, camp, 0, 0, 0.0, E[nPP] * orc_edge_length(s, nPP, pos, 0));
+					--pos[n];
+					t->camp[n][0][0][ui_pos] *= s->iv[IDX(s, nP, pos[0], pos[1], pos[2])];
+					t->camp[n][0][1][ui_pos] *= s->iv[IDX(s, nPP, pos[0], pos[1], pos[2])];
+				}
+				if (t->active[n][1]) {
+					pos[n] = t->stop[n];
+					yee_coords(s, nP, pos, coord, 0); dist = PW_DIST(coord, origin, t->prop_dir);
+					TF_SET(cdelay, cdd, camp, 1, 1, 0.0, E[nP] * orc_edge_length(s, nP, pos, 0));
+					yee_coords(s, nPP, pos, coord, 0); dist = PW_DIST(coord, origin, t->prop_dir);
+					TF_SET(cdelay, cdd, camp, 1, 0, 0.0, E[nPP] * orc_edge_length(s, nPP, pos, 0));
+					t->camp[n][1][0][ui_pos] *= s->iv[IDX(s, nP, pos[0], pos[1], pos[2])];
+					t->camp[n][1][1][ui_pos] *= s->iv[IDX(s, nPP, pos[0], pos[1], pos[2])];
+				}
+				if (t->active[n][0]) t->camp[n][0][0][ui_pos] *= -1;
+				if (t->active[n][1]) t->camp[n][1][1][ui_pos] *= -1;
+				if (pos[nP] == t->stop[nP]) {
+					if (t->active[n][0]) t->camp[n][0][1][ui_pos] = 0;
+					if (t->active[n][1]) t->camp[n][1][1][ui_pos] = 0;
+				}
+				if (pos[nPP] == t->stop[nPP]) {
+					if (t->active[n][0]) t->camp[n][0][0][ui_pos] = 0;
+					if (t->active[n][1]) t->camp[n][1][0][ui_pos] = 0;
+				}
+				/* voltage updates :307-365 */
+				pos[n] = t->start[n] - 1;
+				if (t->active[n][0]) {
+					yee_coords(s, nP, pos, coord, 1); dist = PW_DIST(coord, origin, t->prop_dir);
+					TF_SET(vdelay, vdd, vamp, 0, 1, 1.0, t->h_amp[nP] * orc_edge_length(s, nP, pos, 1));
+					yee_coords(s, nPP, pos, coord, 1); dist = PW_DIST(coord, origin, t->prop_dir);
+					TF_SET(vdelay, vdd, vamp, 0, 0, 1.0, t->h_amp[nPP] * orc_edge_length(s, nPP, pos, 1));
+					++pos[n];
+					t->vamp[n][0][0][ui_pos] *= s->vi[IDX(s, nP, pos[0], pos[1], pos[2])];
+					t->vamp[n][0][1][ui_pos] *= s->vi[IDX(s, nPP, pos[0], pos[1], pos[2])];
+				}
+				pos[n] = t->stop[n];
+				if (t->active[n][1]) {
+					yee_coords(s, nP, pos, coord, 1); dist = PW_DIST(coord, origin, t->prop_dir);
+					TF_SET(vdelay, vdd, vamp, 1, 1, 1.0, t->h_amp[nP] * orc_edge_length(s, nP, pos, 1));
+					yee_coords(s, nPP, pos, coord, 1); dist = PW_DIST(coord, origin, t->prop_dir);
+					TF_SET(vdelay, vdd, vamp, 1, 0, 1.0, t->h_amp[nPP] * orc_edge_length(s, nPP, pos, 1));
+					t->vamp[n][1][0][ui_pos] *= s->vi[IDX(s, nP, pos[0], pos[1], pos[2])];
+					t->vamp[n][1][1][ui_pos] *= s->vi[IDX(s, nPP, pos[0], pos[1], pos[2])];
+				}
+				if (t->active[n][1]) t->vamp[n][1][0][ui_pos] *= -1;
+				if (t->active[n][0]) t->vamp[n][0][1][ui_pos] *= -1;
+				if (pos[nP] == t->stop[nP]) {
+					if (t->active[n][0]) t->vamp[n][0][0][ui_pos] = 0;
+					if (t->active[n][1]) t->vamp[n][1][0][ui_pos] = 0;
+				}
+				if (pos[nPP] == t->stop[nPP]) {
+					if (t->active[n][0]) t->vamp[n][0][1][ui_pos] = 0;
+					if (t->active[n][1]) t->vamp[n][1][1][ui_pos] = 0;
+				}
+				++pos[nPP];
+				++ui_pos;
+			}
+			++pos[nP];
+		}
+	}
+	t->max_delay = max_delay + 1;
+	t->lookup = xcalloc(t->max_delay + 1, sizeof(unsigned)); /* engine_ext_tfsf.cpp:25-27 */
+	return 1;
+}
+/* the delay lookup of DoPostVoltageUpdates / DoPostCurrentUpdates, engine_ext_tfsf.cpp:38-53 / :128-141
+   (the current version stops one entry earlier; that entry still holds the value the voltage hook of the
+   same timestep wrote, which is the same expression) */
+static void tfsf_lookup(orc_sim* s, tfsf_t* t, unsigned upto_incl)
+{
+	unsigned numTS = s->numTS, length = s->sig_len;
+	int p = s->exc_period > 0 ? (int)(s->exc_period / s->dT) : 0;
+	for (unsigned n = 0; n <= upto_incl; ++n) {
+		if (numTS < n) t->lookup[n] = 0;
+		else if (numTS - n >= length && p == 0) t->lookup[n] = 0;
+		else t->lookup[n] = numTS - n;
+		if (p > 0) t->lookup[n] = t->lookup[n] % p;
+	}
+}
+static void tfsf_postV(orc_sim* s, ext_t* e, int tid, int nth)
+{
+	(void)nth;
+	if (tid != 0) return;
+	tfsf_t* t = e->data;
+	tfsf_lookup(s, t, t->max_delay);
+	const float* signal = s->sig_i; /* "get the current signal since an H-field is added" */
+	unsigned pos[3];
+	for (int n = 0; n < 3; ++n) {
+		int nP = (n + 1) % 3, nPP = (n + 2) % 3;
+		for (int l = 0; l < 2; ++l) {
+			if (!t->active[n][l]) continue;
+			pos[nP] = t->start[nP];
+			unsigned u = 0;
+			for (unsigned i = 0; i < t->nl[nP]; ++i) {
+				pos[nPP] = t->start[nPP];
+				for (unsigned j = 0; j < t->nl[nPP]; ++j) {
+					pos[n] = l ? t->stop[n] : t->start[n];
+					VOLT(s, nP, pos) = (float)(VOLT(s, nP, pos)
+					    + (1.0 - t->vdd[n][l][0][u]) * t->vamp[n][l][0][u] * signal[t->lookup[t->vdelay[n][l][0][u]]]
+					    + t->vdd[n][l][0][u] * t->vamp[n][l][0][u] * signal[t->lookup[1 + t->vdelay[n][l][0][u]]]);
+					VOLT(s, nPP, pos) = (float)(VOLT(s, nPP, pos)
+					    + (1.0 - t->vdd[n][l][1][u]) * t->vamp[n][l][1][u] * signal[t->lookup[t->vdelay[n][l][1][u]]]
+					    + t->vdd[n][l][1][u] * t->vamp[n][l][1][u] * signal[t->lookup[1 + t->vdelay[n][l][1][u]]]);
+					++pos[nPP];
+					++u;
+				}
+				++pos[nP];
+			}
+		}
+	}
+}
+static void tfsf_postI(orc_sim* s, ext_t* e, int tid, int nth)
+{
+	(void)nth;
+	if (tid != 0) return;
+	tfsf_t* t = e->data;
+	if (t->max_delay > 0) tfsf_lookup(s, t, t->max_delay - 1);
+	const float* signal = s->sig_v;
+	unsigned pos[3];
+	for (int n = 0; n < 3; ++n) {
+		if (!t->active[n][0] && !t->active[n][1]) continue;
+		int nP = (n + 1) % 3, nPP = (n + 2) % 3;
+		for (int l = 0; l < 2; ++l) {
+			if (!t->active[n][l]) continue;
+			pos[nP] = t->start[nP];
+			unsigned u = 0;
+			for (unsigned i = 0; i < t->nl[nP]; ++i) {
+				pos[nPP] = t->start[nPP];
+				for (unsigned j = 0; j < t->nl[nPP]; ++j) {
+					pos[n] = l ? t->stop[n] : t->start[n] - 1;
+					CURR(s, nP, pos) = (float)(CURR(s, nP, pos)
+					    + (1.0 - t->cdd[n][l][0][u]) * t->camp[n][l][0][u] * signal[t->lookup[t->cdelay[n][l][0][u]]]
+					    + t->cdd[n][l][0][u] * t->camp[n][l][0][u] * signal[t->lookup[1 + t->cdelay[n][l][0][u]]]);
+					CURR(s, nPP, pos) = (float)(CURR(s, nPP, pos)
+					    + (1.0 - t->cdd[n][l][1][u]) * t->camp[n][l][1][u] * signal[t->lookup[t->cdelay[n][l][1][u]]]
+					    + t->cdd[n][l][1][u] * t->camp[n][l][1][u] * signal[t->lookup[1 + t->cdelay[n][l][1][u]]]);
+					++pos[nPP];
+					++u;
+				}
+				++pos[nP];
+			}
+		}
+	}
+}
+
 /* ---- local absorbing sheets --------------------------------------------------------------
    openEMS::SetupAbsorbingSheets openems.cpp:411-441 (one extension per primitive, added after
    the lumped RLC extension, :1242-1243), Operator_Ext_Absorbing_BC::SetInitParams / BuildExtension
@@ -1594,6 +1819,8 @@ int orc_build(orc_sim* s, unsigned max_ts)
 	s->nexts = 0;
 	build_excitation(s);
 	add_ext(s, PRIO_EXCITATION, NULL, NULL, NULL, exc_applyV, NULL, NULL, exc_applyI);
+	/* Operator_Ext_TFSF is the second extension (openems.cpp:1187-1188); it stays inactive without a plane wave */
+	if (s->tfsf.on && build_tfsf(s)) add_ext(s, PRIO_TFSF, &s->tfsf, NULL, tfsf_postV, NULL, NULL, tfsf_postI, NULL);
 	s->nmur = 0;
 	for (int n = 0; n < 6; ++n)
 		if (s->bc[n] == 2) {
@@ -2036,4 +2263,23 @@ void orc_abc_coeff(const orc_sim* s, int a, float* K1P, float* K1PP, float* K2P,
 	const size_t n = (size_t)A->nl[0] * A->nl[1];
 	memcpy(K1P, A->K1P, n * sizeof(float)); memcpy(K1PP, A->K1PP, n * sizeof(float));
 	memcpy(K2P, A->K2P, n * sizeof(float)); memcpy(K2PP, A->K2PP, n * sizeof(float));
+}
+
+
+/* TFSF tables for the engine upload: which = 0 voltage, 1 current; returns the point count of face (n, l) */
+int orc_tfsf_on(const orc_sim* s) { return s->tfsf.on && s->tfsf.lookup != NULL; }
+unsigned orc_tfsf_max_delay(const orc_sim* s) { return s->tfsf.max_delay; }
+void orc_tfsf_box(const orc_sim* s, unsigned start[3], unsigned stop[3], int active[6])
+{
+	for (int n = 0; n < 3; ++n) { start[n] = s->tfsf.start[n]; stop[n] = s->tfsf.stop[n]; active[2 * n] = s->tfsf.active[n][0]; active[2 * n + 1] = s->tfsf.active[n][1]; }
+}
+unsigned orc_tfsf_face(const orc_sim* s, int which, int n, int l, int c, unsigned* delay, float* delta, float* amp)
+{
+	const tfsf_t* t = &s->tfsf;
+	if (!t->active[n][l]) return 0;
+	const unsigned numP = t->nl[(n + 1) % 3] * t->nl[(n + 2) % 3];
+	memcpy(delay, which ? t->cdelay[n][l][c] : t->vdelay[n][l][c], numP * sizeof(unsigned));
+	memcpy(delta, which ? t->cdd[n][l][c] : t->vdd[n][l][c], numP * sizeof(float));
+	memcpy(amp, which ? t->camp[n][l][c] : t->vamp[n][l][c], numP * sizeof(float));
+	return numP;
 }

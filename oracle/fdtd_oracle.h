@@ -138,6 +138,13 @@ void orc_fd_accumulate(float* acc, const float* td, size_t n, const float w[2]);
 /* ProcessModeMatch::CalcMultipleIntegrals Common/processmodematch.cpp:222-266; out2 = {value, purity ratio} */
 void orc_mode_match(const orc_sim* s, int is_H, int ny, const unsigned start[3], const unsigned stop[3],
                     const double* dist0, const double* dist1, double out2[2]);
+/* TFSF plane wave (Operator_Ext_TFSF / Engine_Ext_TFSF) on the box of mesh indices start..stop, frequency <= 0
+   (phase velocity c0/n); call before orc_build.  Tables: which 0 = voltage, 1 = current, face (n, l), component c */
+int orc_set_tfsf(orc_sim* s, const unsigned start[3], const unsigned stop[3], const double prop_dir[3], const double e_amp[3]);
+int orc_tfsf_on(const orc_sim* s);
+unsigned orc_tfsf_max_delay(const orc_sim* s);
+void orc_tfsf_box(const orc_sim* s, unsigned start[3], unsigned stop[3], int active[6]);
+unsigned orc_tfsf_face(const orc_sim* s, int which, int n, int l, int c, unsigned* delay, float* delta, float* amp);
 /* local absorbing sheets (Operator_Ext_Absorbing_BC / Engine_Ext_Absorbing_BC); x0/x1 mesh indices
    of the sheet, type 1 = MUR_1ST, 2 = MUR_1ST_SA, phase_velocity 0 -> C0; call before orc_build */
 int orc_add_absorbing_sheet(orc_sim* s, const unsigned x0[3], const unsigned x1[3], int normal_positive, int type,

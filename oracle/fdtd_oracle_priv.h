@@ -45,6 +45,18 @@ typedef struct {
 	float *vP, *vPP;       /* engine state */
 } mur_t;
 
+/* Operator_Ext_TFSF / Engine_Ext_TFSF: total-field / scattered-field plane wave box */
+typedef struct {
+	int on;
+	unsigned start[3], stop[3], nl[3];
+	double prop_dir[3], e_amp[3], h_amp[3], ph_vel;
+	int active[3][2];
+	unsigned max_delay;
+	unsigned* vdelay[3][2][2]; float* vdd[3][2][2]; float* vamp[3][2][2];
+	unsigned* cdelay[3][2][2]; float* cdd[3][2][2]; float* camp[3][2][2];
+	unsigned* lookup;
+} tfsf_t;
+
 /* Operator_Ext_Absorbing_BC / Engine_Ext_Absorbing_BC: local absorbing sheet */
 typedef struct {
 	int ny, nyP, nyPP, type, positive;     /* type 1: MUR_1ST, 2: MUR_1ST_SA */
@@ -90,6 +102,7 @@ typedef struct ext_s {
 /* FDTD/extensions/engine_extension.h:21-29 */
 #define PRIO_DEFAULT 0
 #define PRIO_UPML 1000000
+#define PRIO_TFSF 50000
 #define PRIO_EXCITATION (-1000)
 #define PRIO_STEADYSTATE 2000000
 
@@ -125,6 +138,7 @@ struct orc_sim {
 	rlc_t* rlc; int nrlc;
 	ss_t* ss;
 	abc_t abc[8]; int nabc;
+	tfsf_t tfsf;
 
 	/* engine */
 	float *volt, *curr;

@@ -57,6 +57,11 @@ def lib():
         "orc_add_lumped_rc": (C.c_int, [vp, _d3, _d3, C.c_int, C.c_double, C.c_double, C.c_int]),
         "orc_add_rlc_raw": (C.c_int, [vp, C.c_uint, C.POINTER(C.c_int), _up] + [_fp] * 9),
         "orc_add_steadystate": (C.c_int, [vp, C.c_uint, C.c_uint, _up, C.POINTER(C.c_int)]),
+        "orc_set_tfsf": (C.c_int, [vp, _u3, _u3, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "orc_tfsf_on": (C.c_int, [vp]),
+        "orc_tfsf_max_delay": (C.c_uint, [vp]),
+        "orc_tfsf_box": (None, [vp, _u3, _u3, C.POINTER(C.c_int)]),
+        "orc_tfsf_face": (C.c_uint, [vp, C.c_int, C.c_int, C.c_int, C.c_int, _up, _fp, _fp]),
         "orc_add_absorbing_sheet": (C.c_int, [vp, _u3, _u3, C.c_int, C.c_int, C.c_double]),
         "orc_abc_count": (C.c_int, [vp]),
         "orc_abc_info": (None, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _u3, _u3]),
@@ -272,6 +277,36 @@ class OracleSim:
         shape = (3, nl[0], nl[1], nl[2])
         return np.ctypeslib.as_array(lib().orc_upml_flux(self._h, b, int(is_curr)),
                                      shape=(int(np.prod(shape)),)).reshape(shape)
+
+    def set_tfsf(self, start, stop, prop_dir, e_amp):
+        """plane-wave (TFSF) excitation on the box of mesh indices start..stop"""
+        pd = (C.c_double * 3)(*prop_dir)
+        ea = (C.c_double * 3)(*e_amp)
+        rc = lib().orc_set_tfsf(self._h, _u3(*start), _u3(*stop), pd, ea)
+        if rc:
+            raise RuntimeError("orc_set_tfsf rc=%d" % rc)
+
+    def tfsf(self):
+        """tables of Operator_Ext_TFSF after build: dict or None"""
+        if not lib().orc_tfsf_on(self._h):
+            return None
+        start, stop = (C.c_uint * 3)(), (C.c_uint * 3)()
+        act = (C.c_int * 6)()
+        lib().orc_tfsf_box(self._h, start, stop, act)
+        nl = [stop[n] - start[n] + 1 for n in range(3)]
+        faces = {}
+        for which in (0, 1):
+            for n in range(3):
+                numP = nl[(n + 1) % 3] * nl[(n + 2) % 3]
+                for l in range(2):
+                    if not act[2 * n + l]:
+                        continue
+                    for c in range(2):
+                        d = np.zeros(numP, np.uint32); dd = np.zeros(numP, np.float32); a = np.zeros(numP, np.float32)
+                        lib().orc_tfsf_face(self._h, which, n, l, c, d.ctypes.data_as(_up), dd.ctypes.data_as(_fp), a.ctypes.data_as(_fp))
+                        faces[(which, n, l, c)] = (d, dd, a)
+        return dict(start=tuple(start), stop=tuple(stop), active=[[act[2 * n], act[2 * n + 1]] for n in range(3)],
+                    max_delay=lib().orc_tfsf_max_delay(self._h), faces=faces)
 
     def add_absorbing_sheet(self, x0, x1, normal_positive, abc_type, phase_velocity=0.0):
         """local absorbing sheet on mesh indices x0..x1 (one direction single-line); type 1 Mur 1st order,

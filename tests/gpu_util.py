@@ -4,7 +4,7 @@ import numpy as np
 from openems_b200 import Operator_CUDA
 
 
-def operator_from_oracle(s, include=("exc", "mur", "upml", "lorentz", "sheets")):
+def operator_from_oracle(s, include=("exc", "mur", "upml", "lorentz", "sheets", "tfsf")):
     """copies the host-side operator data of an OracleSim into an Operator_CUDA, exactly the
     data Operator_CUDA::CreateEngine would read from the reference's Operator/Operator_Ext_*"""
     op = Operator_CUDA(s.N)
@@ -23,6 +23,9 @@ def operator_from_oracle(s, include=("exc", "mur", "upml", "lorentz", "sheets"))
     if "upml" in include:
         for b in s.upml_boxes():
             op.AddUPML(b["start"], b["n"], b["vv"], b["vvfn"], b["vvfo"], b["ii"], b["iifn"], b["iifo"])
+    if "tfsf" in include and s.tfsf() is not None:
+        t = s.tfsf()
+        op.SetTFSF(t["start"], t["stop"], t["active"], t["faces"])
     if "sheets" in include:
         for a in s.absorbing_sheets():
             sa = a["type"] == 2

@@ -181,3 +181,29 @@ def test_local_absorbing_sheets(case):
     eng = run_both(s, steps=steps, what="absorbing sheets " + case)
     names = [n for n, _ in eng.TimeSchedule(0)]
     assert "fused_EH" in names and "sheet_apply_V" in names and "sheet_apply_I" in names
+
+
+@pytest.mark.parametrize("prop_dir,e_amp,periodic", [((1, 0.3, 0.2), (0, 0, 1), False), ((0, 0, -1), (1, 1, 0), False), ((-0.4, 1, 0), (0, 0, 2), True)])
+def test_tfsf_plane_wave(prop_dir, e_amp, periodic):
+    """Engine_Ext_TFSF (engine_ext_tfsf.cpp:36-215, tables of operator_ext_tfsf.cpp:86-406)
+    -- plane-wave injection on the six faces of a box inside an all-UPML mesh: oblique, axial and
+    periodic (sinusoidal) cases; shared box edges get their two updates in the reference's order"""
+    from oracle.pyoracle import OracleSim
+    x, y, z = np.arange(38) * 1e-3, np.cumsum(np.r_[0, np.linspace(1, 1.3, 33)]) * 1e-3, np.arange(36) * 1e-3
+    s = OracleSim(x, y, z, 1.0)
+    s.set_bc([BC_PML] * 6, (6,) * 6)
+    if periodic:
+        s.set_excite_sinus(6e9)
+    else:
+        s.set_excite_gauss(5e9, 4e9)
+    s.set_tfsf((10, 9, 10), (27, 24, 25), prop_dir, e_amp)
+    s.build()
+    t = s.tfsf()
+    assert t is not None and t["max_delay"] > 5 and len(t["faces"]) == 24
+    eng = run_both(s, steps=(1, 7, 60, 150), what="TFSF %s" % (prop_dir,))
+    names = [n for n, _ in eng.TimeSchedule(0)]
+    assert "fused_EH" in names and "tfsf_V" in names and "tfsf_I" in names
+    v = s.volt
+    inside = np.abs(v[:, 13:25, 12:22, 13:23]).max()
+    outside = max(np.abs(v[:, 7:9]).max(), np.abs(v[:, 30:32]).max())
+    assert inside > 1e-4 and outside < 0.02 * inside  # total field inside, (almost) nothing scattered outside
