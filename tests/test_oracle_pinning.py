@@ -167,3 +167,49 @@ def test_fd_dump_restatement_matches_numpy_complex64():
         OracleSim.fd_accumulate(acc, td, w)
         ref = (ref + (td * np.float32(w.real) + 1j * (td * np.float32(w.imag))).astype(np.complex64)).astype(np.complex64)
     assert np.array_equal(acc.view(np.uint32), ref.view(np.uint32))
+
+
+def test_absorbing_sheet_restatement_absorbs():
+    """Engine_Ext_Absorbing_BC restated (no reference fixture exists for it): physical pin -- the sheets of
+    python/Tests/Rect_Waveguide_W_Local_Absorbers.py in small remove the pulse from a TEM line that a
+    PEC-terminated line keeps, with and without super-absorption"""
+    from oracle.pyoracle import OracleSim, BC_PEC, BC_PMC, EXC_E_SOFT
+    x, y, z = np.arange(8) * 1e-3, np.arange(8) * 1e-3, np.arange(80) * 1e-3
+
+    def run(sheets):
+        s = OracleSim(x, y, z, 1.0)
+        s.set_bc([BC_PEC, BC_PEC, BC_PMC, BC_PMC, BC_PEC, BC_PEC])
+        s.set_excite_gauss(8e9, 3e9)
+        s.add_excitation((x[0], y[0], z[40]), (x[-1], y[-1], z[40]), EXC_E_SOFT, (1, 0, 0))
+        for a in sheets:
+            s.add_absorbing_sheet(*a)
+        s.build()
+        s.iterate(250)
+        e0 = s.energy()
+        s.iterate(350)
+        return e0, s.energy()
+    e0, e1 = run([])
+    assert e1 > 0.5 * e0
+    for ty in (1, 2):
+        a0, a1 = run([((0, 0, 2), (7, 7, 2), True, ty), ((0, 0, 77), (7, 7, 77), False, ty)])
+        assert a0 > 0.5 * e0 and a1 < 1e-4 * a0
+        k = None
+
+
+def test_tfsf_restatement_injects_a_plane_wave():
+    """Operator_Ext_TFSF / Engine_Ext_TFSF restated (frequency <= 0 tables): physical pin -- unit E amplitude
+    inside the box (edge voltage = E * 1 mm), less than 1 % of it scattered outside, axial incidence"""
+    from oracle.pyoracle import OracleSim, BC_PML
+    x = y = z = np.arange(36) * 1e-3
+    s = OracleSim(x, y, z, 1.0)
+    s.set_bc([BC_PML] * 6, (6,) * 6)
+    s.set_excite_gauss(0.0, 6e9)
+    s.set_tfsf((9, 9, 9), (26, 26, 26), (0, 0, 1), (1, 0, 0))
+    s.build()
+    peak_in, peak_out = 0.0, 0.0
+    for _ in range(30):
+        s.iterate(8)
+        v = s.volt
+        peak_in = max(peak_in, float(np.abs(v[0, 12:24, 12:24, 12:24]).max()))
+        peak_out = max(peak_out, float(np.abs(v[:, 7:9]).max()), float(np.abs(v[:, :, :, 28:30]).max()))
+    assert 0.9e-3 < peak_in < 1.1e-3 and peak_out < 0.01 * peak_in
