@@ -15,6 +15,9 @@
 #include "extensions/operator_ext_conductingsheet.h"
 #include "extensions/operator_ext_lumpedRLC.h"
 #include "extensions/operator_ext_steadystate.h"
+#include "extensions/engine_ext_steadystate.h"
+#include "extensions/operator_ext_tfsf.h"
+#include "extensions/operator_ext_absorbing_bc.h"
 #include "extensions/engine_extension.h"
 #include "excitation.h"
 
@@ -31,7 +34,7 @@ Engine_CUDA* Engine_CUDA::New(const Operator_CUDA* op)
 	return e;
 }
 
-Engine_CUDA::Engine_CUDA(const Operator_CUDA* op) : Engine(op), m_Op_CUDA(op), m_h(NULL)
+Engine_CUDA::Engine_CUDA(const Operator_CUDA* op) : Engine(op), m_Op_CUDA(op), m_h(NULL), m_SSD(NULL)
 {
 	m_type = UNKNOWN; // neither BASIC nor SSE: stock extensions must not dispatch on this engine
 }
@@ -165,39 +168,66 @@ void Engine_CUDA::InitExtensions()
 				r->v_RLC_vj1, r->v_RLC_vj2, r->v_RLC_ib0, r->v_RLC_b1, r->v_RLC_b2), "add_rlc" );
 			continue;
 		}
-		if (dynamic_cast<Operator_Ext_SteadyState*>(op_ext))
+		if (Operator_Ext_SteadyState* ss = dynamic_cast<Operator_Ext_SteadyState*>(op_ext))
 		{
-			// engine-agnostic stock extension (virtual GetVolt only, engine_ext_steadystate.cpp:50-61);
-			// the driver dereferences it without a NULL check (openems.cpp:1318-1322), so create it.
-			Engine_Extension* eng_ext = op_ext->CreateEngineExtention();
-			if (eng_ext)
-			{
-				eng_ext->SetEngine(this);
-				m_Eng_exts.push_back(eng_ext);
-			}
+			// recorded and evaluated on the device (oems_cuda_add_steadystate); the stock engine extension is
+			// still created because the driver dereferences it without a NULL check (openems.cpp:1318-1322) and
+			// reads GetLastDiff() from it (:1465) -- IterateTS stores the device result there, its own
+			// Apply2Voltages (one GetVolt per probe and timestep) is never called.
+			const unsigned int cnt = ss->m_E_probe_dir.size();
+			std::vector<unsigned int> pos3(3*(size_t)cnt);
+			for (int a=0; a<3; ++a)
+				for (unsigned int i=0; i<cnt; ++i) pos3[(size_t)a*cnt+i] = ss->m_E_probe_pos[a].at(i);
+			Check( oems_cuda_add_steadystate(m_h, ss->m_TS_period, cnt, pos3.data(), ss->m_E_probe_dir.data()), "add_steadystate" );
+			m_SSD = dynamic_cast<Engine_Ext_SteadyState*>(op_ext->CreateEngineExtention());
+			if (m_SSD)
+				m_SSD->SetEngine(this);
+			continue;
+		}
+		if (Operator_Ext_TFSF* t = dynamic_cast<Operator_Ext_TFSF*>(op_ext))
+		{
+			if (!t->IsActive()) continue; // no plane-wave excitation in this setup (operator_ext_tfsf.cpp:103-108)
+			int active[6];
+			const unsigned int* vd[12]; const FDTD_FLOAT* vdd[12]; const FDTD_FLOAT* va[12];
+			const unsigned int* cd[12]; const FDTD_FLOAT* cdd[12]; const FDTD_FLOAT* ca[12];
+			for (int n=0; n<3; ++n)
+				for (int l=0; l<2; ++l)
+				{
+					active[2*n+l] = t->m_ActiveDir[n][l];
+					for (int c=0; c<2; ++c)
+					{
+						const int q = (n*2+l)*2+c;
+						vd[q] = t->m_VoltDelay[n][l][c]; vdd[q] = t->m_VoltDelayDelta[n][l][c]; va[q] = t->m_VoltAmp[n][l][c];
+						cd[q] = t->m_CurrDelay[n][l][c]; cdd[q] = t->m_CurrDelayDelta[n][l][c]; ca[q] = t->m_CurrAmp[n][l][c];
+					}
+				}
+			Check( oems_cuda_set_tfsf(m_h, t->m_Start, t->m_Stop, active, vd, vdd, va, cd, cdd, ca), "set_tfsf" );
+			continue;
+		}
+		if (Operator_Ext_Absorbing_BC* a = dynamic_cast<Operator_Ext_Absorbing_BC*>(op_ext))
+		{
+			const bool sa = a->m_ABCtype==Operator_Ext_Absorbing_BC::MUR_1ST_SA;
+			// ArrayIJ<FDTD_FLOAT> is one contiguous [i][j] block (tools/arraylib/array_ij.h)
+			Check( oems_cuda_add_absorbing_sheet(m_h, a->m_ny, a->m_sheetX0, a->m_sheetX1, a->m_normalSignPositive, (int)a->m_ABCtype,
+				&a->m_K1_nyP(0,0), &a->m_K1_nyPP(0,0), sa ? &a->m_K2_nyP(0,0) : NULL, sa ? &a->m_K2_nyPP(0,0) : NULL), "add_absorbing_sheet" );
 			continue;
 		}
 		cerr << "Engine_CUDA::InitExtensions: extension \"" << op_ext->GetExtensionName()
-		     << "\" has no device implementation yet (TFSF, local absorbing BC, cylinder: see DESIGN.md), aborting" << endl;
+		     << "\" has no device implementation (cylinder extensions: see DESIGN.md), aborting" << endl;
 		exit(2);
 	}
 }
 
 bool Engine_CUDA::IterateTS(unsigned int iterTS)
 {
-	if (m_Eng_exts.empty())
+	Check( oems_cuda_iterate(m_h, iterTS), "IterateTS" );
+	numTS += iterTS;
+	if (m_SSD)
 	{
-		Check( oems_cuda_iterate(m_h, iterTS), "IterateTS" );
-		numTS += iterTS;
-		return true;
-	}
-	// steady-state detection samples voltages every timestep: step one by one
-	for (unsigned int iter=0; iter<iterTS; ++iter)
-	{
-		Check( oems_cuda_iterate(m_h, 1), "IterateTS" );
-		for (size_t n=0; n<m_Eng_exts.size(); ++n)
-			m_Eng_exts.at(n)->Apply2Voltages();
-		++numTS;
+		// what Engine_Ext_SteadyState::Apply2Voltages would have left behind (engine_ext_steadystate.cpp:50-107)
+		double diff = 1; unsigned int checks = 0;
+		Check( oems_cuda_steadystate_check(m_h, &diff, &checks), "steadystate_check" );
+		m_SSD->m_last_max_diff = diff;
 	}
 	return true;
 }

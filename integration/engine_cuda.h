@@ -43,6 +43,7 @@ protected:
 	void Check(int rc, const char* what) const;
 
 	const Operator_CUDA* m_Op_CUDA;
+	class Engine_Ext_SteadyState* m_SSD; //!< stock extension object, kept only as the holder of GetLastDiff()
 	oems_cuda_engine* m_h;
 };
 
