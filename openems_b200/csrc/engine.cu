@@ -995,9 +995,11 @@ void Engine::build_schedule()
 {
 	step.clear();
 	labels.clear();
-	// one-pass schedule whenever it is possible (second field set allocated, no Lorentz/RLC hooks,
-	// UPML edge path not in use) unless the two-pass schedule was requested
-	fused_active = fused_possible && !edge_dirty && fused_req != 0;
+	// one-pass schedule when it is possible (second field set allocated, no Lorentz/RLC hooks, UPML edge
+	// path not in use) and either requested or -- automatic choice -- the mesh is big enough to fill the
+	// GPU with z-marching blocks: below ~160^3 cells the two-pass kernels, which have a thread per cell
+	// column and z chunk, are faster (tools/size_sweep.py, profiles/experiments_r01.md #13)
+	fused_active = fused_possible && !edge_dirty && (fused_req == 1 || (fused_req < 0 && fused_auto_choice()));
 	const bool i16 = index_bytes == 2;
 	const dim3 block(32, tune_rows);
 	auto stencil_grid = [&](const StencilParams& p, int rows_total) {
@@ -1299,7 +1301,11 @@ void Engine::build_schedule_fused()
 		F.zchunk = has_pml ? std::min(pE.zchunk, 63) : pE.zchunk; // the kernel keeps one shell bit per plane of a chunk
 		// TMA-staged kernel: short marches keep the concurrently running blocks on the same few planes
 		// (measured optimum 16..24 planes at 1024^3, profiles/experiments_r01.md)
-		if (tma_req && tune_zchunk <= 0) F.zchunk = std::min(F.zchunk, 16);
+		if (tma_req && tune_zchunk <= 0) {
+			const long long tiles = (long long)((pitch / 4 + 31) / 32) * ((gn[1] + FUSED_TY - 1) / FUSED_TY);
+			const int planes = std::max(1, F.kE1 - F.kE0);
+			F.zchunk = (tiles * ((planes + 15) / 16) >= 27 * 296) ? 16 : 8; // mid-size meshes: more, shorter marches
+		}
 		// UPML shell: all boxes of a half-step in one launch (kernels_fused.cuh)
 		ShellParams& SE = pShE[par];
 		ShellParams& SH = pShH[par];
@@ -1565,11 +1571,16 @@ int Engine::rebuild_schedule()
 	return 0;
 }
 
+bool Engine::fused_auto_choice() const
+{
+	return (long long)gn[0] * gn[1] * (long long)(ze - zb) >= 4000000ll;
+}
+
 // switching between the one-pass and the two-pass schedule keeps the current fields: the two-pass
 // kernels work in place on set 0
 int Engine::set_fused_active(int req)
 {
-	const bool on = fused_possible && !edge_dirty && req != 0;
+	const bool on = fused_possible && !edge_dirty && (req == 1 || (req < 0 && fused_auto_choice()));
 	CK(cudaStreamSynchronize(stream));
 	if (fused_active) flux_sets_sync(true);
 	if (fused_active && !on && (numTS_host & 1u)) {

@@ -265,6 +265,7 @@ private:
 	int build_fix_list();
 	void build_schedule_fused();
 	int set_fused_active(int req);
+	bool fused_auto_choice() const;
 	float *peer_lo_Vs[2] = {nullptr, nullptr}, *peer_hi_Is[2] = {nullptr, nullptr};
 
 	// multi-GPU

@@ -12,10 +12,11 @@ pytestmark = pytest.mark.gpu
 
 
 def run_both(s, steps=(1, 2, 17, 80), what="", **kw):
-    """the oracle against BOTH timestep schedules of the CUDA engine (default = one-pass where the
-    hook set allows it, and the two-pass schedule forced); returns the default-schedule engine"""
+    """the oracle against BOTH timestep schedules of the CUDA engine (one-pass requested -- it runs
+    where the hook set allows it -- and the two-pass schedule forced); returns the one-pass engine"""
     op = operator_from_oracle(s)
     eng = op.CreateEngine()
+    eng.SetOption("fused", 1)
     eng2 = op.CreateEngine()
     eng2.SetOption("fused", 0)
     assert "fused_EH" not in [n for n, _ in eng2.TimeSchedule(0)]
@@ -27,7 +28,7 @@ def run_both(s, steps=(1, 2, 17, 80), what="", **kw):
     for n in steps:
         s.iterate(n)
         total += n
-        for e, name in ((eng, "default schedule"), (eng2, "two-pass")):
+        for e, name in ((eng, "one-pass requested"), (eng2, "two-pass")):
             e.IterateTS(n)
             assert e.GetNumberOfTimesteps() == s.num_ts == total
             mv, mc = assert_fields_equal(e, s, "%s (%s) after %d steps" % (what, name, total))
@@ -78,17 +79,28 @@ def test_materials_and_metal():
 
 
 def test_one_pass_and_two_pass_schedules_agree_and_are_used():
-    """the fused one-pass timestep is the default when the hook set allows it; switching it off
-    gives the two-pass schedule; both match the oracle bit for bit, also when toggled mid-run"""
+    """the one-pass timestep is the automatic choice for meshes of 4 M cells and more when the hook set
+    allows it (smaller ones run faster two-pass), the option forces either; both match the oracle bit
+    for bit, also when toggled mid-run"""
     s = cases.engine_cavity()
     op = operator_from_oracle(s)
     eng = op.CreateEngine()
-    # automatic choice: one-pass, with the UPML boxes on the two-pass shell around it
+    assert eng.GetOption("fused") == 0          # automatic choice on a small mesh
+    big = cases.uniform_box(n=(200, 170, 130), bc=(BC_PML,) * 6, pml=8)
+    eb = operator_from_oracle(big).CreateEngine()
+    assert eb.GetOption("fused") == 1 and eb.GetOption("tma") == 1   # 4.4 M cells: one-pass, TMA-staged
+    big.iterate(12)
+    eb.IterateTS(12)
+    assert_fields_equal(eb, big, "automatic one-pass on a 4.4 M cell mesh")
+    eb.close()
+    # requested: one-pass, with the UPML boxes on the two-pass shell around it
+    eng.SetOption("fused", 1)
     names = [n for n, _ in eng.TimeSchedule(0)]
     assert "fused_EH" in names and "shell_E" in names and "shell_H" in names
     assert eng.GetOption("fused") == 1 and eng.GetOption("tma") == 1  # TMA-staged kernel, not the fallback
     s2 = cases.uniform_box(n=(27, 11, 33), bc=(BC_MUR, BC_MUR, BC_PMC, BC_PEC, BC_PEC, BC_MUR))
     e2 = operator_from_oracle(s2).CreateEngine()
+    e2.SetOption("fused", 1)
     assert "fused_EH" in [n for n, _ in e2.TimeSchedule(0)]
     s2.iterate(90)
     e2.IterateTS(90)
@@ -134,6 +146,7 @@ def test_x_slab_boxes_inside_the_one_pass_kernel(n, pml):
     and three x tiles; toggled mid-run at odd and even timestep counts; flux compared as well"""
     s = cases.uniform_box(n=n, bc=(BC_PML,) * 6, pml=pml)
     eng = operator_from_oracle(s).CreateEngine()
+    eng.SetOption("fused", 1)
     eng.SetOption("xslab", 1)
     assert eng.GetOption("xslab") == 2 and eng.GetOption("tma") == 1
     total = 0

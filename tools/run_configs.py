@@ -18,10 +18,17 @@ for name, make, steps in (("C1_parallel_plate_waveguide_21x21x41", configs.c1_pa
     s = r[0] if isinstance(r, tuple) else r
     cells = s.N[0] * s.N[1] * s.N[2]
     eng = operator_from_oracle(s).CreateEngine()
+    sched = "one-pass" if eng.GetOption("fused") else "two-pass"
     eng.IterateTS(20)
     ms = eng.IterateTimed(steps)
     st = eng.GetStats()
     gpu = cells * steps / (ms * 1e-3) / 1e6
+    ms2 = None
+    if sched == "one-pass":  # the other schedule, for comparison
+        eng.SetOption("fused", 0)
+        eng.IterateTS(20)
+        ms2 = eng.IterateTimed(steps)
+        eng.SetOption("fused", -1)
     best = 0.0
     for th in sorted({1, min(4, threads), threads}):
         cpu = OracleSSE(s, threads=th)
@@ -33,7 +40,8 @@ for name, make, steps in (("C1_parallel_plate_waveguide_21x21x41", configs.c1_pa
             best, best_th = v, th
         cpu.close()
     out[name] = dict(cells=cells, steps=steps, gpu_mcells_s=round(gpu, 1), gpu_us_per_step=round(ms * 1e3 / steps, 2),
-                     kernels_per_step=st["kernels_per_step"], cpu_mcells_s=round(best, 1), cpu_threads=best_th,
+                     kernels_per_step=st["kernels_per_step"], schedule=sched,
+                     two_pass_us_per_step=None if ms2 is None else round(ms2 * 1e3 / steps, 2), cpu_mcells_s=round(best, 1), cpu_threads=best_th,
                      n_unique=st["n_unique"])
     print(name, out[name], flush=True)
     eng.close()
