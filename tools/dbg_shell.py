@@ -6,6 +6,9 @@ from oracle.pyoracle import BC_PML, BC_PEC
 for n, bc, pml in (((23, 26, 21), (BC_PML,) * 6, 4), ((23, 26, 21), (BC_PML, BC_PML, 0, 0, 0, 0), 4), ((23, 26, 21), (0, 0, BC_PML, BC_PML, 0, 0), 4), ((23, 26, 21), (0, 0, 0, 0, BC_PML, BC_PML), 4), ((23, 26, 21), (0, 0,BC_PML, 0, BC_PML, 0), 4)):
     s = cases.uniform_box(n=n, bc=bc, pml=pml)
     eng = operator_from_oracle(s).CreateEngine()
+    eng.SetOption("fused", 1)
+    if len(sys.argv) > 1:
+        eng.SetOption("tma", int(sys.argv[1]))
     print(n, bc, [x for x, _ in eng.TimeSchedule(0)])
     for it in range(30):
         s.iterate(1); eng.IterateTS(1)
