@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_E(const __grid_
 		const long long om = (long long)k * p.plane + rowm;
 		unsigned e[4];
 		Idx4<IdxT>::load(p.idx, o, e);
-		if (k + 1 < ke && active && (sub & 7) == 0) {
+		if (XL >= 16 && k + 1 < ke && active && (sub & 7) == 0) { // thin boxes: a line prefetch would fetch 128 B for the 48 B they use
 			const long long of = o + p.plane;
 			prefetch_l2(I0 + of); prefetch_l2(I1 + of); prefetch_l2(I2 + of);
 			prefetch_l2(V0 + of); prefetch_l2(V1 + of); prefetch_l2(V2 + of);
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_H(const __grid_
 		const long long on = o + p.plane; // plane k+1 is always held: k1 <= held planes - 1
 		unsigned e[4];
 		Idx4<IdxT>::load(p.idx, o, e);
-		if (k + 1 < ke && active && (sub & 7) == 0) {
+		if (XL >= 16 && k + 1 < ke && active && (sub & 7) == 0) { // thin boxes: a line prefetch would fetch 128 B for the 48 B they use
 			const long long of = on + p.plane;
 			prefetch_l2(V0 + of); prefetch_l2(V1 + of); prefetch_l2(V2 + on);
 			prefetch_l2(I0 + on); prefetch_l2(I1 + on); prefetch_l2(I2 + on);
