@@ -220,3 +220,28 @@ def test_tfsf_plane_wave(prop_dir, e_amp, periodic):
     inside = np.abs(v[:, 13:25, 12:22, 13:23]).max()
     outside = max(np.abs(v[:, 7:9]).max(), np.abs(v[:, 30:32]).max())
     assert inside > 1e-4 and outside < 0.02 * inside  # total field inside, (almost) nothing scattered outside
+
+
+@pytest.mark.parametrize("name", ["cavity_mur_pml_pmc", "uniform_allpml_40x36x44"])
+@pytest.mark.parametrize("fused", [0, 1])
+def test_engine_reproduces_committed_golden_vectors(name, fused):
+    """the CUDA engine against the committed fixtures of tests/golden (oracle-generated, see
+    make_golden.py): probe series bit for bit, field digests at three timesteps, both schedules"""
+    import os
+    from tests.golden import make_golden as G
+    g = np.load(os.path.join(os.path.dirname(G.__file__), name + ".npz"))
+    s = G.cavity_case() if name.startswith("cavity") else G.allpml_case()
+    eng = operator_from_oracle(s).CreateEngine()
+    eng.SetOption("fused", fused)
+    probes = [tuple(map(tuple, p)) for p in g["probes"].tolist()]
+    ids = [eng.AddVoltageProbe(a, b) for a, b in probes]
+    steps = int(g["steps"])
+    want = {int(t): (int(dv), int(di)) for t, dv, di in g["digests"].tolist()}
+    series = np.zeros((steps, len(probes)))
+    for t in range(steps):
+        eng.IterateTS(1)
+        u = eng.ReadProbes()
+        series[t] = [u[i] for i in ids]
+        if t + 1 in want:
+            assert (int(G.field_digest(eng.GetFields(0))), int(G.field_digest(eng.GetFields(1)))) == want[t + 1], "fields at step %d" % (t + 1)
+    assert np.array_equal(series.view(np.uint64), g["series"].view(np.uint64))

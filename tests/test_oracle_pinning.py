@@ -213,3 +213,19 @@ def test_tfsf_restatement_injects_a_plane_wave():
         peak_in = max(peak_in, float(np.abs(v[0, 12:24, 12:24, 12:24]).max()))
         peak_out = max(peak_out, float(np.abs(v[:, 7:9]).max()), float(np.abs(v[:, :, :, 28:30]).max()))
     assert 0.9e-3 < peak_in < 1.1e-3 and peak_out < 0.01 * peak_in
+
+
+@pytest.mark.parametrize("name", ["cavity_mur_pml_pmc", "uniform_allpml_40x36x44"])
+def test_oracle_reproduces_committed_golden_vectors(name):
+    """tests/golden/*.npz were written by tests/golden/make_golden.py FROM THE ORACLE (the reference cannot
+    run here): they freeze probe series and field digests so that a change of the oracle or of a case
+    builder is noticed; the GPU suite checks the CUDA engine against the same files"""
+    import os
+    from tests.golden import make_golden as G
+    g = np.load(os.path.join(os.path.dirname(G.__file__), name + ".npz"))
+    s = G.cavity_case() if name.startswith("cavity") else G.allpml_case()
+    assert s.dT == float(g["dT"])
+    probes = [tuple(map(tuple, p)) for p in g["probes"].tolist()]
+    series, digests = G.record(s, int(g["steps"]), probes)
+    assert np.array_equal(series.view(np.uint64), g["series"].view(np.uint64))
+    assert np.array_equal(digests, g["digests"])
