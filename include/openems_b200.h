@@ -67,7 +67,10 @@ int oems_cuda_set_slab(oems_cuda_engine* h, unsigned z_begin, unsigned z_end);
 int oems_cuda_set_operator_dense(oems_cuda_engine* h, const float* vv, const float* vi,
                                  const float* ii, const float* iv);
 /* already compressed operator: table[n_unique] + per-cell index [nz][ny][nx] (x fastest),
-   index_bytes 2 or 4.  Used when the dense arrays do not fit the host (1024^3 and up). */
+   index_bytes 2 or 4.  Used when the dense arrays do not fit the host (1024^3 and up).
+   A pageable index is staged and copied before the call returns; a PAGE-LOCKED index
+   (cudaHostRegister / cudaMallocHost, e.g. oems_synth_pin) is sent by one asynchronous DMA that
+   overlaps the allocations of oems_cuda_finalize: keep that buffer alive until finalize returns. */
 int oems_cuda_set_operator_compressed(oems_cuda_engine* h, unsigned n_unique,
                                       const oems_coeff_entry* table, const void* index,
                                       int index_bytes);

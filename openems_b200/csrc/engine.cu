@@ -141,7 +141,8 @@ int Engine::set_operator_compressed(unsigned nu, const oems_coeff_entry* table, 
 		// page-locked source (oems_synth_pin, cudaHostRegister / cudaMallocHost by the caller): one DMA
 		const size_t row_bytes = (size_t)gn[0] * ib;
 		CK(cudaMemcpy2DAsync(p, (size_t)pitch * ib, src, row_bytes, row_bytes, (size_t)gn[1] * nzl, cudaMemcpyHostToDevice, stream));
-		CK(cudaStreamSynchronize(stream));
+		// not waited for here: the copy runs while finalize() allocates and clears the field sets; the caller
+		// keeps the (page-locked) buffer alive until oems_cuda_finalize has returned (include/openems_b200.h)
 	} else {
 		// double-buffered pinned staging: the caller's buffer is pageable, a direct copy would run
 		// at a fraction of the PCIe rate
