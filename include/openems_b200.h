@@ -250,7 +250,7 @@ int oems_cuda_set_option(oems_cuda_engine* h, const char* key, long long value);
 /* "tma" = 1 / 0: the one-pass kernel stages its inputs in shared memory through TMA bulk tensor
    copies (default) or loads them into registers itself (k_fused_EH); identical results.
    "xslab" = 1 / 0 (default 0, experimental): UPML boxes that are thin in x and sit at the x ends
-   of the mesh are updated inside the TMA one-pass kernel instead of by the shell launches.
+   of the mesh are updated by their own one-pass kernel (k_xslab_EH) instead of the shell launches.
    oems_cuda_get_option reports what is ACTIVE ("fused", "tma": 0 / 1; "xslab": boxes inlined). */
 int oems_cuda_get_option(oems_cuda_engine* h, const char* key, long long* value);
 

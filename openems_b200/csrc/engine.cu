@@ -1218,12 +1218,10 @@ int Engine::make_tma_maps(int par)
 		if (!attr_done) {
 			attr_done = true;
 			const int s16 = ft_smem_bytes<uint16_t, FT_STAGES>(), s32 = ft_smem_bytes<uint32_t, FT_STAGES>();
-			cudaFuncSetAttribute(k_fused_tma<uint16_t, true, FT_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
-			cudaFuncSetAttribute(k_fused_tma<uint16_t, true, FT_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
-			cudaFuncSetAttribute(k_fused_tma<uint16_t, false, FT_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
-			cudaFuncSetAttribute(k_fused_tma<uint32_t, true, FT_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
-			cudaFuncSetAttribute(k_fused_tma<uint32_t, true, FT_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
-			cudaFuncSetAttribute(k_fused_tma<uint32_t, false, FT_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
+			cudaFuncSetAttribute(k_fused_tma<uint16_t, true, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
+			cudaFuncSetAttribute(k_fused_tma<uint16_t, false, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
+			cudaFuncSetAttribute(k_fused_tma<uint32_t, true, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
+			cudaFuncSetAttribute(k_fused_tma<uint32_t, false, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
 			if (cudaGetLastError() != cudaSuccess) { encode = nullptr; return 1; }
 		}
 	}
@@ -1254,19 +1252,19 @@ void Engine::build_schedule_fused()
 	labelsf.clear();
 	// TMA descriptors of both source sets; without them the register-staged kernel is used
 	tma_active = tma_req != 0 && make_tma_maps(0) == 0 && make_tma_maps(1) == 0;
-	// UPML boxes the one-pass kernel updates itself ("x slabs"): thin in x, at the low end of the mesh
-	// or inside the last x tile (not starting on its first line: the tile before computes that line as its
-	// halo column with the plain formula), at most one per end, and with no H cell of the fix-up list
-	// inside (those are recomputed from the hooks' final E, which an in-place flux cannot redo)
+	// UPML boxes updated by their own one-pass kernel k_xslab_EH ("x slabs", kernels_xslab.cuh): thin in x, at
+	// the low or the high end of the mesh, the float4 chunks they touch (+ the halo column on the low side)
+	// fit a 16-line window, at most one per end, no H cell of the fix-up list inside (those are recomputed
+	// from the hooks' final E, which an in-place flux cannot redo), and -- high end -- the box must not start on a
+	// chunk boundary: the big kernel computes the first line of that chunk with the plain formula for its own
+	// last H line
 	xs_box[0] = xs_box[1] = -1;
 	if (tma_active && xslab_req) {
-		const int x0_last = 128 * ((pitch / 4 + 31) / 32 - 1);
 		for (int b = 0; b < pE.nboxes; ++b) {
 			const PmlBox& B = pE.box[b];
-			if (B.n[0] > 16) continue;
 			int g = -1;
-			if (B.s[0] == 0) g = 0;
-			else if (B.s[0] + B.n[0] == (int)gn[0] && B.s[0] > x0_last) g = 1;
+			if (B.s[0] == 0 && (B.n[0] + 3) / 4 * 4 + 1 <= 16 && (B.n[0] + 3) / 4 * 4 < (int)gn[0]) g = 0;
+			else if (B.s[0] + B.n[0] == (int)gn[0] && B.s[0] % 4 != 0 && (int)gn[0] - B.s[0] / 4 * 4 <= 16 && B.s[0] / 4 * 4 > 0) g = 1;
 			if (g < 0 || xs_box[g] >= 0) continue;
 			bool hit = false;
 			for (long long q = 0; q < fix_count && !hit; ++q) {
@@ -1275,6 +1273,8 @@ void Engine::build_schedule_fused()
 			}
 			if (!hit) xs_box[g] = b;
 		}
+		// both windows in one mesh that is narrower than the two of them: keep the low one
+		if (xs_box[0] >= 0 && xs_box[1] >= 0 && (pE.box[xs_box[0]].n[0] + 3) / 4 * 4 + 1 > pE.box[xs_box[1]].s[0] / 4 * 4) xs_box[1] = -1;
 		if ((xs_box[0] >= 0 || xs_box[1] >= 0) && !d_flux_v2) {
 			d_flux_v2 = dalloc<float>((size_t)flux_floats);
 			if (!d_flux_v2) { cudaGetLastError(); xs_box[0] = xs_box[1] = -1; }
@@ -1322,17 +1322,32 @@ void Engine::build_schedule_fused()
 		float* const fluxV[2] = {d_flux_v, d_flux_v2};
 		FusedTmaParams& FT = pFT[par];
 		memset(FT.xs, 0, sizeof(FT.xs));
-		FT.bx_off = 0; FT.bx_stride = 1;
-		FT.eP0 = d_tab[2]; FT.eP1 = d_tab[3]; FT.eP2 = d_tab[4];
-		FT.hP0 = d_tab[7]; FT.hP1 = d_tab[8]; FT.hP2 = d_tab[9];
+		XSlabParams& XP = pXs[par];
+		memset(&XP, 0, sizeof(XP));
+		XP.Vs = sV[S]; XP.Is = sI[S]; XP.Vd = sV[D]; XP.Id = sI[D];
+		XP.idx = d_idx;
+		XP.eA = d_tab[0]; XP.eB = d_tab[1]; XP.eP0 = d_tab[2]; XP.eP1 = d_tab[3]; XP.eP2 = d_tab[4];
+		XP.hA = d_tab[5]; XP.hB = d_tab[6]; XP.hP0 = d_tab[7]; XP.hP1 = d_tab[8]; XP.hP2 = d_tab[9];
+		XP.nx = (int)gn[0]; XP.ny = (int)gn[1]; XP.nz = nzl;
+		XP.pitch = pitch; XP.plane = plane; XP.comp = comp;
+		XP.kE0 = F.kE0; XP.kE1 = F.kE1; XP.kH1 = F.kH1; XP.kHc1 = F.kHc1;
+		XP.zchunk = 16;
+		nxs = 0;
 		for (int b = 0; b < pE.nboxes; ++b) {
 			const PmlBox& B = pE.box[b];
 			if (b == xs_box[0] || b == xs_box[1]) {
-				XSlab& X = FT.xs[b == xs_box[0] ? 0 : 1];
-				X.n0 = B.n[0]; X.x_first = B.s[0];
-				X.s1 = B.s[1]; X.n1 = B.n[1]; X.s2 = B.s[2]; X.n2 = B.n[2];
-				X.cs = (long long)B.n[0] * B.n[1] * B.n[2];
-				X.fVs = fluxV[S] + B.off; X.fVd = fluxV[D] + B.off; X.fI = d_flux_i + B.off;
+				const int g = b == xs_box[0] ? 0 : 1;
+				const int c0 = B.s[0] / 4, c1 = (B.s[0] + B.n[0] - 1) / 4; // chunks the box touches
+				XSlabFoot& X = FT.xs[g];
+				X.on = 1; X.c0 = c0; X.cn = c1 - c0 + 1;
+				X.j0 = B.s[1]; X.jn = B.n[1]; X.k0 = B.s[2]; X.kn = B.n[2];
+				X.x0 = B.s[0]; X.x1 = B.s[0] + B.n[0];
+				XSlabBox& Q = XP.box[nxs++];
+				Q.w0 = c0 * 4; Q.own0 = c0 * 4; Q.own1 = std::min((c1 + 1) * 4, (int)gn[0]);
+				Q.bs0 = B.s[0]; Q.bn0 = B.n[0];
+				Q.s1 = B.s[1]; Q.n1 = B.n[1]; Q.s2 = B.s[2]; Q.n2 = B.n[2];
+				Q.cs = (long long)B.n[0] * B.n[1] * B.n[2];
+				Q.fVs = fluxV[S] + B.off; Q.fVd = fluxV[D] + B.off; Q.fI = d_flux_i + B.off;
 				continue;
 			}
 			F.sh[ns].c0 = B.s[0] / 4; F.sh[ns].cn = (B.s[0] + B.n[0] - 1) / 4 - F.sh[ns].c0 + 1;
@@ -1365,6 +1380,8 @@ void Engine::build_schedule_fused()
 			++ns;
 		}
 		F.nsh = SE.nboxes = SH.nboxes = ns;
+		XP.nsh = ns;
+		for (int q = 0; q < ns; ++q) { XP.sh[q].c0 = F.sh[q].c0; XP.sh[q].cn = F.sh[q].cn; XP.sh[q].j0 = F.sh[q].j0; XP.sh[q].jn = F.sh[q].jn; XP.sh[q].k0 = F.sh[q].k0; XP.sh[q].kn = F.sh[q].kn; }
 		for (ShellParams* w : {&SE, &SH}) {
 			unsigned nb = 0;
 			for (int b = 0; b < w->nboxes; ++b) {
@@ -1423,6 +1440,18 @@ void Engine::build_schedule_fused()
 				if (i16) k_shell_E<uint16_t><<<q.nblocks, dim3(32, 8), 0, s>>>(q); else k_shell_E<uint32_t><<<q.nblocks, dim3(32, 8), 0, s>>>(q);
 			});
 		}
+		if (nxs) {
+			// x slabs: E and H in one pass, source -> destination set (after the shells of the other boxes: it
+			// takes their E_new as neighbour values; before or after the big kernel makes no difference)
+			lab("xslab_EH");
+			L.push_back([this, par, i16](cudaStream_t s) {
+				const XSlabParams& q = pXs[par];
+				int rows = 0, planes = 0;
+				for (int b = 0; b < nxs; ++b) { rows = std::max(rows, q.box[b].n1); planes = std::max(planes, q.box[b].n2); }
+				const dim3 g((unsigned)((rows + XSLAB_ROWS - 1) / XSLAB_ROWS), (unsigned)((planes + q.zchunk - 1) / q.zchunk), (unsigned)nxs);
+				if (i16) k_xslab_EH<uint16_t><<<g, dim3(16, 16), 0, s>>>(q); else k_xslab_EH<uint32_t><<<g, dim3(16, 16), 0, s>>>(q);
+			});
+		}
 		lab("fused_EH");
 		L.push_back([this, par, i16](cudaStream_t s) {
 			const FusedParams& q = pF[par];
@@ -1430,21 +1459,10 @@ void Engine::build_schedule_fused()
 			const dim3 g((unsigned)((pitch / 4 + 31) / 32), (unsigned)((q.ny + FUSED_TY - 1) / FUSED_TY),
 			             (unsigned)std::max(1, (q.kE1 - q.kE0 + q.zchunk - 1) / q.zchunk));
 			if (tma_active) {
-				FusedTmaParams t = pFT[par];
+				const FusedTmaParams& t = pFT[par];
 				const int sm = i16 ? ft_smem_bytes<uint16_t, FT_STAGES>() : ft_smem_bytes<uint32_t, FT_STAGES>();
-				auto launch = [&](dim3 gg, bool xs) {
-					if (gg.x == 0) return;
-					if (i16) {
-						if (xs) k_fused_tma<uint16_t, true, FT_STAGES, true><<<gg, block, sm, s>>>(t);
-						else if (has_pml) k_fused_tma<uint16_t, true, FT_STAGES, false><<<gg, block, sm, s>>>(t);
-						else k_fused_tma<uint16_t, false, FT_STAGES, false><<<gg, block, sm, s>>>(t);
-					} else {
-						if (xs) k_fused_tma<uint32_t, true, FT_STAGES, true><<<gg, block, sm, s>>>(t);
-						else if (has_pml) k_fused_tma<uint32_t, true, FT_STAGES, false><<<gg, block, sm, s>>>(t);
-						else k_fused_tma<uint32_t, false, FT_STAGES, false><<<gg, block, sm, s>>>(t);
-					}
-				};
-				launch(g, xs_box[0] >= 0 || xs_box[1] >= 0);
+				if (i16) { if (has_pml) k_fused_tma<uint16_t, true, FT_STAGES><<<g, block, sm, s>>>(t); else k_fused_tma<uint16_t, false, FT_STAGES><<<g, block, sm, s>>>(t); }
+				else { if (has_pml) k_fused_tma<uint32_t, true, FT_STAGES><<<g, block, sm, s>>>(t); else k_fused_tma<uint32_t, false, FT_STAGES><<<g, block, sm, s>>>(t); }
 				return;
 			}
 			if (i16) { if (has_pml) k_fused_EH<uint16_t, true><<<g, block, 0, s>>>(q); else k_fused_EH<uint16_t, false><<<g, block, 0, s>>>(q); }
@@ -1663,8 +1681,8 @@ int Engine::set_option(const char* key, long long value)
 		return 0;
 	}
 	if (k == "xslab") {
-		// 1: thin UPML boxes at the x ends are updated inside the one-pass kernel, 0: shell launches (default:
-		// measured faster, profiles/experiments_r01.md #12)
+		// 1: thin UPML boxes at the x ends are updated by their own one-pass kernel k_xslab_EH, 0: shell launches
+		// (default: measured faster, profiles/experiments_r01.md #12, #15)
 		xslab_req = value != 0;
 		if (finalized) return rebuild_schedule();
 		return 0;

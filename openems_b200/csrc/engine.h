@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_fused_tma.cuh"
+#include "kernels_xslab.cuh"
 
 struct UpmlBoxHost {
 	unsigned start[3], n[3];          // global
@@ -249,7 +250,9 @@ private:
 	bool tma_active = false;
 	// UPML boxes updated inside the one-pass kernel ("x slabs", kernels_fused_tma.cuh): index into pE.box, -1 none
 	int xs_box[2] = {-1, -1};
-	int xslab_req = 0;           // option "xslab" (off: slower than the shell so far, profiles/experiments_r01.md #12)
+	int xslab_req = 0;           // option "xslab": thin UPML boxes at the x ends get their own one-pass kernel (off: not faster yet, experiments_r01.md #15)
+	XSlabParams pXs[2];          // per parity
+	int nxs = 0;                 // x slabs in pXs
 	float* d_flux_v2 = nullptr;  // second voltage-flux set (only the x-slab boxes use it)
 	std::vector<int> h_fix_cells;
 	void flux_sets_sync(bool to_set0);

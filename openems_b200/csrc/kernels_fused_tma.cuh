@@ -27,27 +27,21 @@
 #define FT_ROWS_I (FUSED_TY + 2)      // H rows j0-1 .. j0+TY
 #define FT_ROWS_V (FUSED_TY + 1)      // E / index rows j0 .. j0+TY
 
-// UPML box that is thin in x and lies at the low / high end of the mesh ("x slab"): its cells are
-// updated INSIDE the one-pass kernel by the end tiles, one cell per lane (lanes 0-15: low slab,
-// 16-31: high slab), from the staged tile -- as a shell launch the same cells cost 64-byte
-// pieces of every 4 KB row, which HBM serves at a fraction of its streaming rate.
-struct XSlab {
-	int n0;              // lines in x, <= 16 (0: no such slab)
-	int x_first;         // first line
-	int s1, n1, s2, n2;  // y range, local z range
-	long long cs;        // flux component stride
-	const float* fVs;    // voltage flux of timestep n, component 0 (ping-pong like the fields: the
-	float* fVd;          //   halo-row warp and the chunk's extra plane recompute E of cells other blocks own)
-	float* fI;           // current flux, in place (every H is computed exactly once)
+// UPML box that is thin in x and sits at the low / high end of the mesh ("x slab"), updated by its own
+// one-pass kernel k_xslab_EH (kernels_xslab.cuh) instead of the shell launches.  For the big kernel
+// these are cells it must not store: fp* = the footprint (whole float4 chunks, rows, local planes).
+struct XSlabFoot {
+	int on;
+	int c0, cn;          // float4 chunks of the footprint
+	int j0, jn, k0, kn;  // rows / local planes of the box
+	int x0, x1;          // lines of the box itself [x0, x1)
 };
 
 struct alignas(64) FusedTmaParams {
-	XSlab xs[2];
-	int bx_off, bx_stride; // x tile of a block = bx_off + blockIdx.x * bx_stride
+	XSlabFoot xs[2];
 	CUtensorMap mI;   // H_old of the source set: (x, y, z, component) float, box 136 x 9 x 1 x 3
 	CUtensorMap mV;   // E_old of the source set (shell cells: already E_new), box 136 x 8 x 1 x 3
 	CUtensorMap mX;   // operator index (x, y, z), box 136 x 8 x 1
-	const float4 *eP0, *eP1, *eP2, *hP0, *hP1, *hP2; // UPML auxiliary tables (x slabs)
 	FusedParams f;
 };
 
@@ -62,7 +56,7 @@ template <typename IdxT> struct FtStage {
 };
 template <typename IdxT, int STAGES> constexpr int ft_smem_bytes()
 {
-	return STAGES * FtStage<IdxT>::BYTES + 3 * 3 * (FUSED_TY + 1) * 32 * 16 + 64; // stages, E_new ring (V0, V2, V1), mbarriers
+	return STAGES * FtStage<IdxT>::BYTES + 2 * 3 * (FUSED_TY + 1) * 32 * 16 + 64;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,15 +91,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-// lane that holds the x-slab result of mesh line x (-1: x is in no x slab)
-__device__ __forceinline__ int xslab_lane(const FusedTmaParams& P, int x)
-{
-	const int a = x - P.xs[0].x_first, b = x - P.xs[1].x_first;
-	if ((unsigned)a < (unsigned)P.xs[0].n0) return a;
-	if ((unsigned)b < (unsigned)P.xs[1].n0) return 16 + b;
-	return -1;
-}
-
 template <typename IdxT> struct SIdx4;
 template <> struct SIdx4<uint16_t> {
 	__device__ __forceinline__ static void load(const unsigned char* row, int lane, unsigned e[4])
@@ -122,7 +107,7 @@ template <> struct SIdx4<uint32_t> {
 	}
 };
 
-template <typename IdxT, bool HAS_PML, int STAGES, bool XS>
+template <typename IdxT, bool HAS_PML, int STAGES>
 __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tma(const __grid_constant__ FusedTmaParams P)
 {
 	extern __shared__ __align__(128) unsigned char ft_smem[];
@@ -130,11 +115,10 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 	const FusedParams& p = P.f;
 	float4 (*xV0)[FUSED_TY + 1][32] = reinterpret_cast<float4 (*)[FUSED_TY + 1][32]>(ft_smem + STAGES * ST::BYTES);
 	float4 (*xV2)[FUSED_TY + 1][32] = xV0 + 3;
-	float4 (*xV1)[FUSED_TY + 1][32] = xV0 + 6; // only the x-slab lanes read V1 from the ring
-	const uint32_t bar0 = smem_u32(ft_smem + STAGES * ST::BYTES + 3 * 3 * (FUSED_TY + 1) * 32 * 16);
+	const uint32_t bar0 = smem_u32(ft_smem + STAGES * ST::BYTES + 2 * 3 * (FUSED_TY + 1) * 32 * 16);
 
 	const int lane = threadIdx.x, ty = threadIdx.y;
-	const int x0 = (P.bx_off + (int)blockIdx.x * P.bx_stride) * 128, j0 = blockIdx.y * FUSED_TY;
+	const int x0 = blockIdx.x * 128, j0 = blockIdx.y * FUSED_TY;
 	const int i0 = x0 + lane * 4;
 	const int j = j0 + ty;
 	const bool halo_row = ty == FUSED_TY;
@@ -187,26 +171,20 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 			if (right) shxb |= m;
 		}
 	}
-	bool shk = false;
-
-	// x-slab lanes: one cell of the row per lane
-	const XSlab& X = P.xs[lane >> 4];
-	const int xsx = X.x_first + (lane & 15);          // my slab cell
-	const int xl = xsx - x0;                          // tile-relative column
-	const int ljs = j - X.s1;
-	// block-uniform: this tile holds x-slab cells (all tiles run the same kernel: launching the end
-	// tiles on their own would read 544-byte pieces of 4 KB rows, which HBM serves poorly)
-	const bool xs_tile = XS && ((P.xs[0].n0 > 0 && x0 == 0) || (P.xs[1].n0 > 0 && P.xs[1].x_first >= x0 && P.xs[1].x_first < x0 + 128));
-	const bool xs_row = xs_tile && (lane & 15) < X.n0 && xl >= 0 && xl < 128 && row_ok && (unsigned)ljs < (unsigned)X.n1;
-	float hs0 = 0.0f, hs1 = 0.0f, hs2 = 0.0f;         // H_old(k) of the slab cell
-	unsigned es_idx = 0;
-	bool xs_k = false;                                // slab cell updated as UPML at plane k
-	if (xs_row) {
-		const int km = kb - (kb > 0);
-		const long long o = (long long)km * p.plane + (long long)j * p.pitch + xsx;
-		hs0 = p.Is[o];
-		hs1 = p.Is[p.comp + o];
+	// x-slab footprints: cells the x-slab kernel stores (one bit per plane of the march, like shb)
+	unsigned long long xhb = 0;
+	if (HAS_PML) {
+		const int chunk = ic >> 2;
+		const int jc = row_ok ? j : p.ny - 1;
+		for (int g = 0; g < 2; ++g) {
+			const XSlabFoot& X = P.xs[g];
+			if (!X.on || (unsigned)(chunk - X.c0) >= (unsigned)X.cn || (unsigned)(jc - X.j0) >= (unsigned)X.jn) continue;
+			const int a = max(X.k0, kb) - kb, z = min(X.k0 + X.kn, e_last + 1) - kb;
+			if (z <= a) continue;
+			xhb |= (z - a >= 64 ? ~0ull : ((1ull << (z - a)) - 1ull)) << a;
+		}
 	}
+	bool shk = false, xsk = false;
 
 	float4 ek0 = make_float4(0, 0, 0, 0), ek1 = ek0, ek2 = ek0;
 	float4 hk0 = ek0, hk1 = ek0, hk2 = ek0;
@@ -223,20 +201,13 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 	for (int kk = kb; kk <= e_last; ++kk) {
 		// ------------------------------------------------------------ E_new(kk)
 		const int s = (kk - kb) % STAGES;
-		// x-slab lanes: the flux loads do not depend on the staged tile -- issue them before the wait
-		float fv0 = 0.0f, fv1 = 0.0f, fv2 = 0.0f, fi0 = 0.0f, fi1 = 0.0f, fi2 = 0.0f;
-		const bool xs_zin = XS && xs_row && (unsigned)(kk - X.s2) < (unsigned)X.n2;
-		const bool xs_h = XS && xs_k && !halo_row && kk - 1 < he && j < p.ny - 1 && xsx < p.nx - 1; // xs_k implies kk-1 >= kb
-		const long long foV = ((long long)(kk - X.s2) * X.n1 + ljs) * X.n0 + (lane & 15);
-		const long long foI = foV - (long long)X.n1 * X.n0;
-		if (xs_zin) { fv0 = X.fVs[foV]; fv1 = X.fVs[foV + X.cs]; fv2 = X.fVs[foV + 2 * X.cs]; }
-		if (xs_h) { fi0 = X.fI[foI]; fi1 = X.fI[foI + X.cs]; fi2 = X.fI[foI + 2 * X.cs]; }
 		mbar_wait(bar0 + 8 * s, ((kk - kb) / STAGES) & 1);
 		const unsigned char* stg = ft_smem + s * ST::BYTES;
 		const float* sI = reinterpret_cast<const float*>(stg);
 		const float* sV = reinterpret_cast<const float*>(stg + ST::V_OFF);
 		const unsigned char* sX = stg + ST::X_OFF;
 		const bool sh = HAS_PML && (shb >> (kk - kb) & 1ull), shx = HAS_PML && (shxb >> (kk - kb) & 1ull);
+		const bool xsc = HAS_PML && (xhb >> (kk - kb) & 1ull);
 		const int cI = FT_ROWS_I * FT_W, cV = FT_ROWS_V * FT_W; // component strides inside a stage
 		const int oI = rI * FT_W + 4 + lane * 4, oIm = rIm * FT_W + 4 + lane * 4, oV = rV * FT_W + 4 + lane * 4;
 		unsigned e[4];
@@ -267,50 +238,13 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 				setcomp(v1, c, sh ? comp(v1, c) : n1);
 				setcomp(v2, c, sh ? comp(v2, c) : n2);
 			}
-		}
-		// ---- x-slab cells of this row: UPML update, one cell per lane, merged into the row's float4s
-		float h0n = 0.0f, h1n = 0.0f, h2n = 0.0f;
-		unsigned eidx = 0;
-		bool xs_kk = false;
-		if (xs_tile) {
-			float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
-			if (xs_row) {
-				const int col = 4 + xl;
-				h0n = sI[rI * FT_W + col]; h1n = sI[cI + rI * FT_W + col]; h2n = sI[2 * cI + rI * FT_W + col];
-				eidx = reinterpret_cast<const IdxT*>(sX)[rV * FT_W + xl];
-				if (xs_zin) {
-					const float4 A = __ldg(p.eA + eidx);
-					if (A.w != 0.0f) {
-						const float4 B = __ldg(p.eB + eidx), P0 = __ldg(P.eP0 + eidx), P1 = __ldg(P.eP1 + eidx), P2 = __ldg(P.eP2 + eidx);
-						const float j0m = sI[rIm * FT_W + col], j2m = sI[2 * cI + rIm * FT_W + col];
-						const float x1m = xsx > 0 ? sI[cI + rI * FT_W + col - 1] : h1n, x2m = xsx > 0 ? sI[2 * cI + rI * FT_W + col - 1] : h2n;
-						const float curl0 = fadd(fsub(fsub(h2n, j2m), h1n), hs1);
-						const float curl1 = fadd(fsub(fsub(h0n, hs0), h2n), x2m);
-						const float curl2 = fadd(fsub(fsub(h1n, x1m), h0n), j0m);
-						float f0, f1, f2;
-						r0 = leap_pml_oop(sV[rV * FT_W + col], A.x, B.x, curl0, P0.x, P1.x, P2.x, fv0, f0);
-						r1 = leap_pml_oop(sV[cV + rV * FT_W + col], A.y, B.y, curl1, P0.y, P1.y, P2.y, fv1, f1);
-						r2 = leap_pml_oop(sV[2 * cV + rV * FT_W + col], A.z, B.z, curl2, P0.z, P1.z, P2.z, fv2, f2);
-						if (!halo_row && kk < ke) { X.fVd[foV] = f0; X.fVd[foV + X.cs] = f1; X.fVd[foV + 2 * X.cs] = f2; }
-						xs_kk = true;
-					}
-				}
-			}
-			const unsigned bal = __ballot_sync(0xffffffffu, xs_kk);
-#pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				const int src = xslab_lane(P, ic + c);
-				const int sl = src < 0 ? lane : src;
-				const float t0 = __shfl_sync(0xffffffffu, r0, sl), t1 = __shfl_sync(0xffffffffu, r1, sl), t2 = __shfl_sync(0xffffffffu, r2, sl);
-				if (src >= 0 && (bal >> src & 1u)) { setcomp(v0, c, t0); setcomp(v1, c, t1); setcomp(v2, c, t2); }
-			}
-		}
-		if (active) {
 			if (!halo_row && kk < ke) {
 				const long long o = (long long)kk * p.plane + row;
-				st4(p.Vd + o, v0);
-				st4(p.Vd + p.comp + o, v1);
-				st4(p.Vd + 2 * p.comp + o, v2);
+				if (!xsc) { // x-slab chunks are stored by k_xslab_EH
+					st4(p.Vd + o, v0);
+					st4(p.Vd + p.comp + o, v1);
+					st4(p.Vd + 2 * p.comp + o, v2);
+				}
 			}
 			if (hcol) {
 				// V1, V2 of cell (xe, j, kk): engine.cpp:148-166 with the x-1 neighbour = my last cell
@@ -328,7 +262,6 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 		}
 		xV0[kk % 3][ty][lane] = v0;
 		xV2[kk % 3][ty][lane] = v2;
-		if (xs_tile) xV1[kk % 3][ty][lane] = v1;
 		__syncthreads();
 		// every thread has taken what it needs of stage s into registers: refill it
 		if (producer && kk + STAGES <= e_last) issue(kk + STAGES);
@@ -338,49 +271,10 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 		float r1 = __shfl_down_sync(0xffffffffu, ek1.x, 1);
 		float r2 = __shfl_down_sync(0xffffffffu, ek2.x, 1);
 		if (lane == 31) { r1 = hcV1; r2 = hcV2; }
-		// x-slab cells: H_new(k) from the E_new ring
-		float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f;
-		unsigned balh = 0;
-		if (xs_tile && !halo_row && k >= kb) { // warp-uniform
-			bool hb = false;
-			if (xs_h) {
-				const float* a0 = reinterpret_cast<const float*>(&xV0[k % 3][ty][0]) + xl;
-				const float* a1 = reinterpret_cast<const float*>(&xV1[k % 3][ty][0]) + xl;
-				const float* a2 = reinterpret_cast<const float*>(&xV2[k % 3][ty][0]) + xl;
-				const float w0 = a0[0], w1 = a1[0], w2 = a2[0];
-				const float w0jp = a0[32 * 4], w2jp = a2[32 * 4];   // row ty+1 of the ring
-				const float w1xp = a1[1], w2xp = a2[1];
-				const float w0n = reinterpret_cast<const float*>(&xV0[kk % 3][ty][0])[xl], w1n = reinterpret_cast<const float*>(&xV1[kk % 3][ty][0])[xl];
-				const float curl0 = fadd(fsub(fsub(w2, w2jp), w1), w1n);
-				const float curl1 = fadd(fsub(fsub(w0, w0n), w2), w2xp);
-				const float curl2 = fadd(fsub(fsub(w1, w1xp), w0), w0jp);
-				const float4 A = __ldg(p.hA + es_idx), B = __ldg(p.hB + es_idx), P0 = __ldg(P.hP0 + es_idx), P1 = __ldg(P.hP1 + es_idx), P2 = __ldg(P.hP2 + es_idx);
-				float f0, f1, f2;
-				q0 = leap_pml_oop(hs0, A.x, B.x, curl0, P0.x, P1.x, P2.x, fi0, f0);
-				q1 = leap_pml_oop(hs1, A.y, B.y, curl1, P0.y, P1.y, P2.y, fi1, f1);
-				q2 = leap_pml_oop(hs2, A.z, B.z, curl2, P0.z, P1.z, P2.z, fi2, f2);
-				X.fI[foI] = f0; X.fI[foI + X.cs] = f1; X.fI[foI + 2 * X.cs] = f2;
-				hb = true;
-			}
-			balh = __ballot_sync(0xffffffffu, hb);
-		}
-		float4 m0 = make_float4(0, 0, 0, 0), m1 = m0, m2 = m0;
-		unsigned mm = 0;
-		if (xs_tile && !halo_row && k >= kb) {
-#pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				const int src = xslab_lane(P, ic + c);
-				const int sl = src < 0 ? lane : src;
-				setcomp(m0, c, __shfl_sync(0xffffffffu, q0, sl));
-				setcomp(m1, c, __shfl_sync(0xffffffffu, q1, sl));
-				setcomp(m2, c, __shfl_sync(0xffffffffu, q2, sl));
-				if (src >= 0 && (balh >> src & 1u)) mm |= 1u << c;
-			}
-		}
 		if (k >= kb && !halo_row && active) {
 			const long long oh = (long long)k * p.plane + row;
 			float4 c0 = hk0, c1 = hk1, c2 = hk2;
-			if (k < he && j < p.ny - 1 && !shk) { // H of shell cells: copied through here, updated by k_shell_H
+			if (k < he && j < p.ny - 1 && !shk && !xsk) { // H of shell / x-slab cells: not updated here
 				const float4 v0jp = xV0[k % 3][ty + 1][lane], v2jp = xV2[k % 3][ty + 1][lane];
 				const float4 v1xp = make_float4(ek1.y, ek1.z, ek1.w, r1);
 				const float4 v2xp = make_float4(ek2.y, ek2.z, ek2.w, r2);
@@ -399,31 +293,29 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 					}
 				}
 			}
-			if (XS && mm) {
-#pragma unroll
-				for (int c = 0; c < 4; ++c)
-					if (mm >> c & 1u) { setcomp(c0, c, comp(m0, c)); setcomp(c1, c, comp(m1, c)); setcomp(c2, c, comp(m2, c)); }
-			}
 			if (k < p.kHc1) {
-				st4(p.Id + oh, c0);
-				st4(p.Id + p.comp + oh, c1);
-				st4(p.Id + 2 * p.comp + oh, c2);
+				if (!xsk) {
+					st4(p.Id + oh, c0);
+					st4(p.Id + p.comp + oh, c1);
+					st4(p.Id + 2 * p.comp + oh, c2);
+				}
 			}
 		}
-		if (xs_tile) { hs0 = h0n; hs1 = h1n; hs2 = h2n; es_idx = eidx; xs_k = xs_kk; }
 		// rotate: plane kk becomes "k"
 		ek0 = v0; ek1 = v1; ek2 = v2;
 		hk0 = i0c; hk1 = i1c; hk2 = i2c;
 #pragma unroll
 		for (int c = 0; c < 4; ++c) ek_idx[c] = e[c];
 		hcV1 = nV1; hcV2 = nV2; hcI0 = nI0;
-		shk = sh;
+		shk = sh; xsk = xsc;
 	}
 	const int k = e_last;
 	if (k == ke - 1 && k >= kb && !halo_row && active && k < p.kHc1) {
 		const long long oh = (long long)k * p.plane + row;
-		st4(p.Id + oh, hk0);
-		st4(p.Id + p.comp + oh, hk1);
-		st4(p.Id + 2 * p.comp + oh, hk2);
+		if (!xsk) {
+			st4(p.Id + oh, hk0);
+			st4(p.Id + p.comp + oh, hk1);
+			st4(p.Id + 2 * p.comp + oh, hk2);
+		}
 	}
 }

@@ -139,7 +139,7 @@ def test_graded_mesh_wide_operator_index():
     assert_fields_equal(eng, s, "graded mesh, register-staged one-pass kernel")
 
 
-@pytest.mark.parametrize("n,pml", [((23, 26, 21), 4), ((150, 20, 18), 8), ((300, 12, 40), 8), ((9, 7, 60), 1)])
+@pytest.mark.parametrize("n,pml", [((23, 26, 21), 4), ((150, 20, 18), 8), ((300, 12, 40), 8), ((12, 7, 60), 1)])
 def test_x_slab_boxes_inside_the_one_pass_kernel(n, pml):
     """option "xslab": the UPML boxes at the x ends are updated by lanes of the TMA one-pass kernel
     (one cell per lane, flux of the voltages ping-ponged) instead of the shell launches; one, two
