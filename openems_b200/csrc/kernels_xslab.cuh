@@ -20,6 +20,9 @@
 #include "kernels_fused.cuh"
 
 #define XSLAB_ROWS 15 // rows a block owns (+1 halo row = 16 threads in y)
+#ifndef XSLAB_PF
+#define XSLAB_PF 3     // planes ahead that are pulled into L2
+#endif
 
 struct XSlabBox {
 	int w0;              // first line of the 16-line window
@@ -108,6 +111,19 @@ __global__ void __launch_bounds__(256) k_xslab_EH(const __grid_constant__ XSlabP
 
 	for (int kk = kb; kk <= e_last; ++kk) {
 		const long long o = (long long)kk * p.plane + row;
+		// pull the lines of plane kk+XSLAB_PF into L2 (one lane per row: a row of the window is one 64-byte piece,
+		// HBM delivers its 128-byte line): the block has too few loads in flight to cover HBM latency otherwise
+		if (tx == 0 && kk + XSLAB_PF <= e_last) {
+			const long long of = o + (long long)XSLAB_PF * p.plane;
+			prefetch_l2(p.Is + of); prefetch_l2(p.Is + p.comp + of); prefetch_l2(p.Is + 2 * p.comp + of);
+			prefetch_l2(p.Vs + of); prefetch_l2(p.Vs + p.comp + of); prefetch_l2(p.Vs + 2 * p.comp + of);
+			prefetch_l2(reinterpret_cast<const IdxT*>(p.idx) + of);
+			if (row_in && (unsigned)(kk + XSLAB_PF - B.s2) < (unsigned)B.n2) {
+				const long long ff = (long long)(kk + XSLAB_PF - B.s2) * fplane + ((long long)(j - B.s1)) * B.bn0;
+				prefetch_l2(B.fVs + ff); prefetch_l2(B.fVs + ff + B.cs); prefetch_l2(B.fVs + ff + 2 * B.cs);
+				prefetch_l2(B.fI + ff); prefetch_l2(B.fI + ff + B.cs); prefetch_l2(B.fI + ff + 2 * B.cs);
+			}
+		}
 		const unsigned e = n_e;
 		const float h0 = n_h0, h1 = n_h1, h2 = n_h2, j0m = n_j0m, j2m = n_j2m;
 		float v0 = n_v0, v1 = n_v1, v2 = n_v2;
