@@ -15,6 +15,8 @@ so.set_excite_gauss(7.5e9, 7.5e9)
 so.add_excitation((n[0] // 2, n[1] // 2, n[2] // 2 + 0.5), (n[0] // 2, n[1] // 2, n[2] // 2 + 0.5), EXC_E_SOFT, (0, 0, 1))
 so.build()
 eng = so.CreateEngine()
+if os.environ.get("XSLAB") is not None:
+    eng.SetOption("xslab", int(os.environ["XSLAB"]))
 eng.SetTuning(0, 0, 0)   # no graph: ncu sees plain launches
 eng.IterateTS(6)
 eng.Synchronize()
