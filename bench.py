@@ -214,10 +214,6 @@ def run_gpu(args):
         slab = slab_range(nz, world, rank, pml_lo=PML, pml_hi=PML, pml_weight=3.2)
 
     so, t_build = build_c5(n)
-    # the e2e leg copies the operator from PINNED host memory (bench contract): page-lock the builder's index
-    t0 = time.time()
-    pinned = so.pin()
-    t_pin = time.time() - t0
     op = so.operator()
 
     # ---------------- e2e leg: engine creation from HOST buffers + K timesteps with probe readback
@@ -309,10 +305,10 @@ def run_gpu(args):
     eng = make_engine()
     link(eng)
     t_upload = time.perf_counter() - t0
-    # bytes copied host->device while creating the engine: coefficient tuples + the per-cell index of
-    # the planes this rank holds (+ a few KB of signal / excitation / probe lists, ignored)
-    held = n[2] if slab is None else (slab[1] - slab[0] + (1 if slab[0] > 0 else 0) + (1 if slab[1] < n[2] else 0))
-    h2d = (so.n_unique * 128 + n[0] * n[1] * held * index_bytes) * world
+    # bytes copied host->device while creating the engine: coefficient tuples + the operator index as the host
+    # builder holds it -- unique xy planes and one plane id per z, expanded on the device
+    # (oems_cuda_set_operator_planes) -- per rank (+ a few KB of signal / excitation / probe lists, ignored)
+    h2d = (so.n_unique * 128 + so.unique_planes * n[0] * n[1] * index_bytes + n[2] * 4) * world
     done, d2h = 0, 0
     while done < args.steps:
         m = min(burst, args.steps - done)
@@ -341,7 +337,7 @@ def run_gpu(args):
                              % ((24 + index_bytes) * local_cells / 1e9),
                        "n_unique_coeff_tuples": so.n_unique, "index_bytes": index_bytes, "pml_cells": pml_cells,
                        "host_operator_build_s": round(t_build, 2), "burst_ts": burst,
-                       "operator_index_host_memory": "pinned (%.2f s to page-lock)" % t_pin if pinned else "pageable"},
+                       "operator_index": "%d unique xy planes + plane ids (%.1f MB), expanded on the device" % (so.unique_planes, so.unique_planes * n[0] * n[1] * index_bytes / 1e6)},
             "roofline": roofline,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                     "includes": "engine creation from host buffers (operator H2D %.2f s) + %d timesteps in bursts of %d with "

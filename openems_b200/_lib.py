@@ -45,6 +45,7 @@ SIGNATURES = {
     "oems_cuda_set_slab": (C.c_int, [_vp, C.c_uint, C.c_uint]),
     "oems_cuda_set_operator_dense": (C.c_int, [_vp, _fp, _fp, _fp, _fp]),
     "oems_cuda_set_operator_compressed": (C.c_int, [_vp, C.c_uint, _vp, _vp, C.c_int]),
+    "oems_cuda_set_operator_planes": (C.c_int, [_vp, C.c_uint, _vp, C.c_uint, _vp, _up, C.c_int]),
     "oems_cuda_set_signal": (C.c_int, [_vp, _fp, _fp, C.c_uint, C.c_uint]),
     "oems_cuda_add_excitation": (C.c_int, [_vp, C.c_int, C.c_uint, _up, _up, _fp, _up]),
     "oems_cuda_add_upml": (C.c_int, [_vp, _u3, _u3] + [_fp] * 6),

@@ -105,6 +105,56 @@ int Engine::set_operator_dense(const float* vv, const float* vi, const float* ii
 	return 0;
 }
 
+// development aid: OEMS_TIMING=1 prints how long the stages of the operator upload take
+struct StageTimer {
+	bool on; cudaStream_t st; double t0; const char* what;
+	static double now() { return omp_get_wtime(); }
+	StageTimer(const char* w, cudaStream_t s) : on(getenv("OEMS_TIMING") != nullptr), st(s), t0(0), what(w) { if (on) t0 = now(); }
+	void lap(const char* name) { if (!on) return; cudaStreamSynchronize(st); const double t = now(); fprintf(stderr, "[oems timing] %s: %s %.1f ms\n", what, name, (t - t0) * 1e3); t0 = t; }
+};
+
+// operator index as unique xy planes + a plane id per z, expanded on the device
+int Engine::set_operator_planes(unsigned nu, const oems_coeff_entry* table, unsigned n_uplanes, const void* uplanes,
+                                const unsigned* plane_of_z, int ib)
+{
+	if (finalized) return fail("engine already finalized");
+	if (!table || !uplanes || !plane_of_z || nu == 0 || n_uplanes == 0) return fail("set_operator_planes: null/empty input");
+	if (ib != 2 && ib != 4) return fail("set_operator_planes: index_bytes must be 2 or 4");
+	if (ib == 2 && nu > 65535) return fail("set_operator_planes: more than 65535 entries need a 32-bit index");
+	for (unsigned k = 0; k < gn[2]; ++k)
+		if (plane_of_z[k] >= n_uplanes) return fail("set_operator_planes: plane id out of range");
+	CK(cudaSetDevice(device));
+	if (!stream) CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+	if (d_idx) return fail("operator already uploaded");
+	h_table.assign(table, table + nu);
+	index_bytes = ib;
+	n_unique = nu;
+	const size_t cells = (size_t)plane * nzl, np = (size_t)gn[0] * gn[1];
+	void* p = nullptr;
+	CK(cudaMalloc(&p, cells * ib));
+	allocs.push_back(p);
+	hbm_bytes += cells * ib;
+	d_idx = p;
+	void* d_up = nullptr;
+	unsigned* d_pz = nullptr;
+	CK(cudaMalloc(&d_up, np * n_uplanes * ib));
+	CK(cudaMalloc((void**)&d_pz, gn[2] * sizeof(unsigned)));
+	CK(cudaMemcpyAsync(d_up, uplanes, np * n_uplanes * ib, cudaMemcpyHostToDevice, stream));
+	CK(cudaMemcpyAsync(d_pz, plane_of_z, gn[2] * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
+	const long long rows = (long long)gn[1] * nzl, n = rows * pitch;
+	const unsigned blocks = (unsigned)((n + 255) / 256);
+	if (ib == 2) k_expand_planes<uint16_t><<<blocks, 256, 0, stream>>>((uint16_t*)p, (const uint16_t*)d_up, d_pz, z0, rows, (int)gn[0], (int)gn[1], pitch, (uint16_t)nu);
+	else k_expand_planes<uint32_t><<<blocks, 256, 0, stream>>>((uint32_t*)p, (const uint32_t*)d_up, d_pz, z0, rows, (int)gn[0], (int)gn[1], pitch, (uint32_t)nu);
+	CK(cudaStreamSynchronize(stream)); // the caller's buffers are free again
+	CK(cudaGetLastError());
+	cudaFree(d_up);
+	cudaFree(d_pz);
+	h2d_index_bytes = np * n_uplanes * ib + gn[2] * sizeof(unsigned);
+	have_compressed = true;
+	have_dense = false;
+	return 0;
+}
+
 int Engine::set_operator_compressed(unsigned nu, const oems_coeff_entry* table, const void* index, int ib)
 {
 	if (finalized) return fail("engine already finalized");
@@ -113,6 +163,7 @@ int Engine::set_operator_compressed(unsigned nu, const oems_coeff_entry* table, 
 	if (ib == 2 && nu > 65535) return fail("set_operator_compressed: more than 65535 entries need a 32-bit index");
 	CK(cudaSetDevice(device));
 	if (!stream) CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+	StageTimer tmu("set_operator_compressed", nullptr);
 	h_table.assign(table, table + nu);
 	index_bytes = ib;
 	n_unique = nu;
@@ -175,6 +226,7 @@ int Engine::set_operator_compressed(unsigned nu, const oems_coeff_entry* table, 
 	}
 	have_compressed = true;
 	have_dense = false;
+	tmu.lap("index allocation + copy issued");
 	return 0;
 }
 
@@ -336,14 +388,6 @@ int Engine::steadystate_check(double* last_diff, unsigned* n_checks)
 	if (last_diff) *last_diff = diff;
 	return 0;
 }
-
-// development aid: OEMS_TIMING=1 prints how long the stages of the operator upload take
-struct StageTimer {
-	bool on; cudaStream_t st; double t0; const char* what;
-	static double now() { return omp_get_wtime(); }
-	StageTimer(const char* w, cudaStream_t s) : on(getenv("OEMS_TIMING") != nullptr), st(s), t0(0), what(w) { if (on) t0 = now(); }
-	void lap(const char* name) { if (!on) return; cudaStreamSynchronize(st); const double t = now(); fprintf(stderr, "[oems timing] %s: %s %.1f ms\n", what, name, (t - t0) * 1e3); t0 = t; }
-};
 
 // ------------------------------------------------------------------------------ compression
 // Re-keys the operator per cell: the 12 stencil coefficients plus, inside UPML

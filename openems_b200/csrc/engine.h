@@ -92,6 +92,7 @@ public:
 
 	int set_slab(unsigned zb, unsigned ze);
 	int set_operator_dense(const float* vv, const float* vi, const float* ii, const float* iv);
+	int set_operator_planes(unsigned nu, const oems_coeff_entry* table, unsigned n_uplanes, const void* uplanes, const unsigned* plane_of_z, int ib);
 	int set_operator_compressed(unsigned n_unique, const oems_coeff_entry* table, const void* index, int index_bytes);
 	int set_signal(const float* sv, const float* si, unsigned len, unsigned period);
 	int add_excitation(int is_curr, unsigned count, const unsigned* idx3, const unsigned* dir, const float* amp, const unsigned* delay);
@@ -248,6 +249,7 @@ private:
 	FusedTmaParams pFT[2]; // the same with the TMA descriptors of the source set (kernels_fused_tma.cuh)
 	int tma_req = 1;       // option "tma": stage the inputs of the one-pass kernel through TMA
 	bool tma_active = false;
+	size_t h2d_index_bytes = 0;  // bytes of operator index copied host -> device
 	// UPML boxes updated inside the one-pass kernel ("x slabs", kernels_fused_tma.cuh): index into pE.box, -1 none
 	int xs_box[2] = {-1, -1};
 	int xslab_req = 0;           // option "xslab": thin UPML boxes at the x ends get their own one-pass kernel (off: not faster yet, experiments_r01.md #15)

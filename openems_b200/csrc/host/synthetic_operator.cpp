@@ -84,6 +84,10 @@ struct oems_synth {
 	EntrySet table;
 	std::vector<uint16_t> idx16;
 	std::vector<uint32_t> idx32;
+	// the same index as unique xy planes + one plane id per z (what oems_synth_upload sends)
+	std::vector<unsigned> plane_of_z;
+	std::vector<uint16_t> uplanes16;
+	std::vector<uint32_t> uplanes32;
 	int index_bytes = 0;
 	unsigned unique_planes = 0;
 	std::vector<unsigned> exc_idx[2][3], exc_dir[2], exc_delay[2];
@@ -669,17 +673,22 @@ int oems_synth_build(oems_synth* s, unsigned max_ts)
 	}
 	const unsigned U = (unsigned)s->table.items.size();
 	s->index_bytes = (U + 1 <= 65536) ? 2 : 4;
+	s->plane_of_z.assign(plane_id.begin(), plane_id.end());
 	if (s->index_bytes == 2) {
 		s->idx16.resize(np * Nz);
 		std::vector<std::vector<uint16_t>> p16(rep.size());
+		s->uplanes16.resize(np * rep.size());
 		for (size_t r = 0; r < rep.size(); ++r) {
 			p16[r].resize(np);
 			for (size_t p = 0; p < np; ++p) p16[r][p] = (uint16_t)plane_index[r][p];
+			memcpy(s->uplanes16.data() + r * np, p16[r].data(), np * 2);
 		}
 #pragma omp parallel for schedule(static)
 		for (long long k = 0; k < (long long)Nz; ++k) memcpy(s->idx16.data() + (size_t)k * np, p16[plane_id[k]].data(), np * 2);
 	} else {
 		s->idx32.resize(np * Nz);
+		s->uplanes32.resize(np * rep.size());
+		for (size_t r = 0; r < rep.size(); ++r) memcpy(s->uplanes32.data() + r * np, plane_index[r].data(), np * 4);
 #pragma omp parallel for schedule(static)
 		for (long long k = 0; k < (long long)Nz; ++k) memcpy(s->idx32.data() + (size_t)k * np, plane_index[plane_id[k]].data(), np * 4);
 	}
@@ -923,7 +932,11 @@ int oems_synth_pin(oems_synth* s)
 int oems_synth_upload(const oems_synth* s, oems_cuda_engine* eng)
 {
 	if (!s || !s->built || !eng) return 1;
-	int rc = oems_cuda_set_operator_compressed(eng, oems_synth_n_unique(s), oems_synth_table(s), oems_synth_index(s), s->index_bytes);
+	// unique xy planes + a plane id per z: for meshes that repeat along z this is a small fraction of the
+	// full per-cell index (C5 1024^3: 20 planes of 1024), the engine expands it on the device
+	int rc = oems_cuda_set_operator_planes(eng, oems_synth_n_unique(s), oems_synth_table(s), s->unique_planes,
+	                                       s->index_bytes == 2 ? (const void*)s->uplanes16.data() : (const void*)s->uplanes32.data(),
+	                                       s->plane_of_z.data(), s->index_bytes);
 	if (rc) return rc;
 	rc = oems_cuda_set_signal(eng, s->sig[0].data(), s->sig[1].data(), s->sig_len,
 	                          s->exc_period > 0 ? (unsigned)(int)(s->exc_period / s->dT) : 0);

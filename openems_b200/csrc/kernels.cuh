@@ -650,6 +650,19 @@ __global__ void k_sheet_apply_I(const __grid_constant__ SheetParams p)
 
 __global__ void k_tick(unsigned* numTS) { *numTS += 1; }
 
+// upload helper: expands an operator index given as unique xy planes + one plane id per z into the per-cell
+// index idx[z][y][pitch] (padding cells point at the all-zero entry `pad`)
+template <typename IdxT>
+__global__ void k_expand_planes(IdxT* idx, const IdxT* uplanes, const unsigned* plane_of_z, int z0, long long rows, int nx, int ny, int pitch, IdxT pad)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; // one thread per (row, x)
+	if (t >= rows * pitch) return;
+	const long long r = t / pitch;
+	const int x = (int)(t % pitch);
+	const int zl = (int)(r / ny), y = (int)(r % ny);
+	idx[t] = x < nx ? uplanes[((size_t)plane_of_z[z0 + zl] * ny + y) * nx + x] : pad;
+}
+
 // upload helper: operator index of the padding cells (i >= nx) points at the all-zero entry
 template <typename IdxT>
 __global__ void k_fill_index_padding(IdxT* idx, long long rows, int nx, int pitch, IdxT value)
