@@ -125,6 +125,8 @@ SIGNATURES = {
     "oems_synth_lorentz_count": (C.c_uint, [_vp, C.c_int]),
     "oems_synth_upload": (C.c_int, [_vp, _vp]),
     "oems_synth_pin": (C.c_int, [_vp]),
+    "oems_synth_plane_of_z": (_up, [_vp]),
+    "oems_synth_plane_data": (_vp, [_vp]),
 }
 
 _lib = None

@@ -883,6 +883,8 @@ int oems_synth_index_bytes(const oems_synth* s) { return s->index_bytes; }
 const oems_coeff_entry* oems_synth_table(const oems_synth* s) { return s->table.items.data(); }
 const void* oems_synth_index(const oems_synth* s) { return s->index_bytes == 2 ? (const void*)s->idx16.data() : (const void*)s->idx32.data(); }
 unsigned oems_synth_unique_planes(const oems_synth* s) { return s->unique_planes; }
+const unsigned* oems_synth_plane_of_z(const oems_synth* s) { return s->plane_of_z.data(); }
+const void* oems_synth_plane_data(const oems_synth* s) { return s->index_bytes == 2 ? (const void*)s->uplanes16.data() : (const void*)s->uplanes32.data(); }
 unsigned oems_synth_signal_length(const oems_synth* s) { return s->sig_len; }
 const float* oems_synth_signal(const oems_synth* s, int is_curr) { return s->sig[is_curr ? 1 : 0].data(); }
 unsigned oems_synth_exc_count(const oems_synth* s, int w) { return (unsigned)s->exc_dir[w ? 1 : 0].size(); }

@@ -47,6 +47,9 @@ unsigned oems_synth_n_unique(const oems_synth* s);
 int      oems_synth_index_bytes(const oems_synth* s);
 const oems_coeff_entry* oems_synth_table(const oems_synth* s);
 const void* oems_synth_index(const oems_synth* s); /* [nz][ny][nx] */
+/* the same index as unique xy planes [unique_planes][ny][nx] + one plane id per z (what oems_synth_upload sends) */
+const unsigned* oems_synth_plane_of_z(const oems_synth* s);
+const void* oems_synth_plane_data(const oems_synth* s);
 unsigned oems_synth_unique_planes(const oems_synth* s);
 unsigned oems_synth_signal_length(const oems_synth* s);
 const float* oems_synth_signal(const oems_synth* s, int is_curr);

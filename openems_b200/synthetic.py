@@ -107,6 +107,15 @@ class SyntheticOperator:
         ptr = C.cast(self._L.oems_synth_index(self._h), C.POINTER(C.c_uint16 if dt == np.uint16 else C.c_uint32))
         return np.ctypeslib.as_array(ptr, shape=(cnt,)).reshape(self.N[2], self.N[1], self.N[0])
 
+    def planes(self):
+        """the index as the engine receives it: (unique xy planes [P][ny][nx], plane id per z [nz])"""
+        dt = np.uint16 if self.index_bytes == 2 else np.uint32
+        P = self.unique_planes
+        ptr = C.cast(self._L.oems_synth_plane_data(self._h), C.POINTER(C.c_uint16 if dt == np.uint16 else C.c_uint32))
+        up = np.ctypeslib.as_array(ptr, shape=(P * self.N[1] * self.N[0],)).reshape(P, self.N[1], self.N[0])
+        ids = np.ctypeslib.as_array(self._L.oems_synth_plane_of_z(self._h), shape=(self.N[2],))
+        return up, ids
+
     def dense(self, which):
         """expands table[index] to an ArrayNIJK coefficient array (tests only; O(N) memory)"""
         col = {"vv": 0, "vi": 3, "ii": 6, "iv": 9, "pml": 12, "pml_vv": 13, "pml_vvfn": 16, "pml_vvfo": 19,

@@ -64,6 +64,10 @@ def test_vacuum_all_pml():
     compare(o, p)
     assert p.n_unique < 6000 and p.index_bytes == 2  # ~17^3 depth classes
     assert p.unique_planes < 40  # interior planes away from the source share one computation
+    # the plane representation the engine receives (oems_cuda_set_operator_planes) is the same index
+    up, ids = p.planes()
+    assert up.shape == (p.unique_planes, 28, 30) and ids.shape == (40,) and ids.max() < p.unique_planes
+    assert np.array_equal(up[ids], p.index())
 
 
 def test_mixed_bc_materials_metal_nonuniform_mesh():
