@@ -207,11 +207,13 @@ def run_gpu(args):
     nz = n[2]
     slab = None
     if world > 1:
-        # strong scaling: z-slabs of the same mesh.  In the one-pass schedule a full z-UPML plane costs
-        # 26.7 us (shell E + H) on top of the 8.45 us every plane costs (1-GPU kernel times),
-        # so the two end slabs get fewer planes
+        # strong scaling: z-slabs of the same mesh.  In the one-pass schedule a full z-UPML plane costs about
+        # 3.4x a plain plane (shell E + H on top of the pass through the big kernel), so the two end slabs get
+        # fewer planes.  Weight 3.2 (from 1-GPU kernel times) left rank 0 waiting 0.08 ms per step for its
+        # neighbour at 4 and at 8 GPUs (halo_wait_E in profiles/bench_r01_{4,8}gpu_tma_balanced.json), i.e. 5-7
+        # planes too few: 2.4 evens that out
         from openems_b200.slabs import slab_range
-        slab = slab_range(nz, world, rank, pml_lo=PML, pml_hi=PML, pml_weight=3.2)
+        slab = slab_range(nz, world, rank, pml_lo=PML, pml_hi=PML, pml_weight=2.4)
 
     so, t_build = build_c5(n)
     op = so.operator()
