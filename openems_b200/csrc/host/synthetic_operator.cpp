@@ -248,11 +248,14 @@ struct oems_synth {
 				for (int n = 0; n < 3; ++n) {
 					const int nP = (n + 1) % 3, nPP = (n + 2) % 3;
 					const int pos[3] = {i, j, (int)k};
-					auto at = [&](int comp, bool isL, int d0, int d1, int d2) -> double {
+					// EC_L / EC_C are FDTD_FLOAT arrays (operator.h:346-349): each product L*C, each 1/(L*C) and each
+					// two-term sum on the right-hand sides of operator.cpp:1984-1990 is a FLOAT expression in the
+					// reference and only its result is widened to double -- keep `at` float and the casts below
+					auto at = [&](int comp, bool isL, int d0, int d1, int d2) -> float {
 						const int q[2] = {refl(pos[0] + d0, Nx), refl(pos[1] + d1, Ny)};
 						const PlaneEC& P = *E[d2 + 1];
 						const size_t p = (size_t)q[1] * Nx + q[0];
-						return isL ? (double)P.L[comp][p] : (double)P.C[comp][p];
+						return isL ? P.L[comp][p] : P.C[comp][p];
 					};
 					auto sh = [&](int a, int sa, int b, int sb, int out[3]) {
 						out[0] = out[1] = out[2] = 0;
@@ -261,30 +264,30 @@ struct oems_synth {
 					int d[3], d1[3], d2[3], dp[3];
 					// wqp
 					sh(n, 0, n, 0, d);
-					const double LPP0 = at(nPP, true, 0, 0, 0), LP0 = at(nP, true, 0, 0, 0), Cn0 = at(n, false, 0, 0, 0);
+					const float LPP0 = at(nPP, true, 0, 0, 0), LP0 = at(nP, true, 0, 0, 0), Cn0 = at(n, false, 0, 0, 0);
 					sh(nP, 1, n, 0, d);
-					double wqp = 1 / (LPP0 * at(n, false, d[0], d[1], d[2])) + 1 / (LPP0 * Cn0);
+					double wqp = (float)(1 / (LPP0 * at(n, false, d[0], d[1], d[2])) + 1 / (LPP0 * Cn0));
 					sh(nPP, 1, n, 0, d);
-					wqp += 1 / (LP0 * at(n, false, d[0], d[1], d[2])) + 1 / (LP0 * Cn0);
+					wqp += (float)(1 / (LP0 * at(n, false, d[0], d[1], d[2])) + 1 / (LP0 * Cn0));
 					sh(nP, -1, n, 0, d1);
-					const double LPP1 = at(nPP, true, d1[0], d1[1], d1[2]), Cn1 = at(n, false, d1[0], d1[1], d1[2]);
-					wqp += 1 / (LPP1 * Cn0) + 1 / (LPP1 * Cn1);
+					const float LPP1 = at(nPP, true, d1[0], d1[1], d1[2]), Cn1 = at(n, false, d1[0], d1[1], d1[2]);
+					wqp += (float)(1 / (LPP1 * Cn0) + 1 / (LPP1 * Cn1));
 					sh(nP, -1, nPP, -1, d2);
-					const double LP2 = at(nP, true, d2[0], d2[1], d2[2]), Cn2 = at(n, false, d2[0], d2[1], d2[2]);
-					wqp += 1 / (LP2 * Cn1) + 1 / (LP2 * Cn2);
+					const float LP2 = at(nP, true, d2[0], d2[1], d2[2]), Cn2 = at(n, false, d2[0], d2[1], d2[2]);
+					wqp += (float)(1 / (LP2 * Cn1) + 1 / (LP2 * Cn2));
 					// wt1
-					const double CP0 = at(nP, false, 0, 0, 0), CPP0 = at(nPP, false, 0, 0, 0);
+					const float CP0 = at(nP, false, 0, 0, 0), CPP0 = at(nPP, false, 0, 0, 0);
 					sh(nPP, -1, n, 0, dp);
-					const double LPPm = LPP1; // L[nPP] at pos - nP
-					const double LPm = at(nP, true, dp[0], dp[1], dp[2]); // L[nP] at pos - nPP
-					double w4[4] = {1 / (LPP0 * CP0), 1 / (LPPm * CP0), 1 / (LP0 * CPP0), 1 / (LPm * CPP0)};
+					const float LPPm = LPP1; // L[nPP] at pos - nP
+					const float LPm = at(nP, true, dp[0], dp[1], dp[2]); // L[nP] at pos - nPP
+					double w4[4] = {(float)(1 / (LPP0 * CP0)), (float)(1 / (LPPm * CP0)), (float)(1 / (LP0 * CPP0)), (float)(1 / (LPm * CPP0))};
 					double mn = w4[0]; // min() of operator.cpp:1942-1952: plain '<' scan
 					for (int q = 1; q < 4; ++q) if (w4[q] < mn) mn = w4[q];
 					const double wt1 = w4[0] + w4[1] + w4[2] + w4[3] - 2 * mn;
 					// wt2
 					sh(n, 1, n, 0, d);
-					const double CPn = at(nP, false, d[0], d[1], d[2]), CPPn = at(nPP, false, d[0], d[1], d[2]);
-					double v4[4] = {1 / (LPP0 * CPn), 1 / (LPPm * CPn), 1 / (LP0 * CPPn), 1 / (LPm * CPPn)};
+					const float CPn = at(nP, false, d[0], d[1], d[2]), CPPn = at(nPP, false, d[0], d[1], d[2]);
+					double v4[4] = {(float)(1 / (LPP0 * CPn)), (float)(1 / (LPPm * CPn)), (float)(1 / (LP0 * CPPn)), (float)(1 / (LPm * CPPn))};
 					mn = v4[0];
 					for (int q = 1; q < 4; ++q) if (v4[q] < mn) mn = v4[q];
 					const double wt2 = v4[0] + v4[1] + v4[2] + v4[3] - 2 * mn;
@@ -383,13 +386,13 @@ struct oems_synth {
 			for (int n = 0; n < 3; ++n) {
 				if (!yee_coords(n, pos, c, false)) continue;
 				const Prop* q = prop_at(c, MASK_EXC);
-				if (q && q->exc_vec[n] != 0 && q->exc_type == 1) e.vv[n] = e.vi[n] = 0;
+				if (q && q->exc_type == 1) e.vv[n] = e.vi[n] = 0;   // ActiveDir is true for all components (CSPropExcitation default)
 			}
 			for (int n = 0; n < 3; ++n) {
 				if (pos[0] >= N[0] - 1 || pos[1] >= N[1] - 1 || pos[2] >= N[2] - 1) continue;
 				if (!yee_coords(n, pos, c, true)) continue;
 				const Prop* q = prop_at(c, MASK_EXC);
-				if (q && q->exc_vec[n] != 0 && q->exc_type == 3) e.ii[n] = e.iv[n] = 0;
+				if (q && q->exc_type == 3) e.ii[n] = e.iv[n] = 0;
 			}
 		}
 		if (!upml.empty() && in_upml(pos)) {
@@ -715,7 +718,7 @@ int oems_synth_build(oems_synth* s, unsigned max_ts)
 						if (!s->yee_coords(n, pos, c, false)) continue;
 						const Prop* e = s->prop_at(c, MASK_EXC);
 						if (!e) continue;
-						if (e->exc_vec[n] != 0 && (e->exc_type == 0 || e->exc_type == 1)) {
+						if (e->exc_type == 0 || e->exc_type == 1) {
 							const double amp = e->exc_vec[n] * s->edge_length(n, pos, false);
 							if (amp != 0) {
 								for (int a = 0; a < 3; ++a) s->exc_idx[0][a].push_back(pos[a]);
@@ -729,7 +732,7 @@ int oems_synth_build(oems_synth* s, unsigned max_ts)
 						if (!s->yee_coords(n, pos, c, true)) continue;
 						const Prop* e = s->prop_at(c, MASK_EXC);
 						if (!e) continue;
-						if (e->exc_vec[n] != 0 && (e->exc_type == 2 || e->exc_type == 3)) {
+						if (e->exc_type == 2 || e->exc_type == 3) {
 							const double amp = e->exc_vec[n] * s->edge_length(n, pos, true);
 							if (amp != 0) {
 								for (int a = 0; a < 3; ++a) s->exc_idx[1][a].push_back(pos[a]);

@@ -493,25 +493,28 @@ static double calc_timestep(const orc_sim* s)
 					e[nP][nP] = 1; e[nPP][nPP] = 1; e[n][n] = 1;
 #define SH(a, sa, b, sb) refl_pos(s, pos, e[a][0] * (sa) + e[b][0] * (sb), e[a][1] * (sa) + e[b][1] * (sb), e[a][2] * (sa) + e[b][2] * (sb))
 					size_t ip = SH(n, 0, n, 0);
+					/* EC_L and EC_C are FDTD_FLOAT arrays (operator.h:346-349): every product L*C, every 1/(L*C) and
+					   every two-term sum on the right-hand sides of operator.cpp:1984-1990 is evaluated in float
+					   and only then widened; the 4-term sums of wt_4[] (double array) are double */
 					double wqp, wt1, wt2, w4[4];
-					wqp = 1 / ((double)LPP[ip] * Cn[SH(nP, 1, n, 0)]) + 1 / ((double)LPP[ip] * Cn[ip]);
-					wqp += 1 / ((double)LP[ip] * Cn[SH(nPP, 1, n, 0)]) + 1 / ((double)LP[ip] * Cn[ip]);
+					wqp = (float)(1 / (LPP[ip] * Cn[SH(nP, 1, n, 0)]) + 1 / (LPP[ip] * Cn[ip]));
+					wqp += (float)(1 / (LP[ip] * Cn[SH(nPP, 1, n, 0)]) + 1 / (LP[ip] * Cn[ip]));
 					size_t i1 = SH(nP, -1, n, 0); /* Shift(nP,-1) */
-					wqp += 1 / ((double)LPP[i1] * Cn[ip]) + 1 / ((double)LPP[i1] * Cn[i1]);
+					wqp += (float)(1 / (LPP[i1] * Cn[ip]) + 1 / (LPP[i1] * Cn[i1]));
 					size_t i2 = SH(nP, -1, nPP, -1); /* Shift(nPP,-1) keeps the nP shift */
-					wqp += 1 / ((double)LP[i2] * Cn[i1]) + 1 / ((double)LP[i2] * Cn[i2]);
+					wqp += (float)(1 / (LP[i2] * Cn[i1]) + 1 / (LP[i2] * Cn[i2]));
 
-					w4[0] = 1 / ((double)LPP[ip] * CP[ip]);
-					w4[1] = 1 / ((double)LPP[SH(nP, -1, n, 0)] * CP[ip]);
-					w4[2] = 1 / ((double)LP[ip] * CPP[ip]);
-					w4[3] = 1 / ((double)LP[SH(nPP, -1, n, 0)] * CPP[ip]);
+					w4[0] = (float)(1 / (LPP[ip] * CP[ip]));
+					w4[1] = (float)(1 / (LPP[SH(nP, -1, n, 0)] * CP[ip]));
+					w4[2] = (float)(1 / (LP[ip] * CPP[ip]));
+					w4[3] = (float)(1 / (LP[SH(nPP, -1, n, 0)] * CPP[ip]));
 					wt1 = w4[0] + w4[1] + w4[2] + w4[3] - 2 * min4(w4);
 
 					size_t in1 = SH(n, 1, n, 0);
-					w4[0] = 1 / ((double)LPP[ip] * CP[in1]);
-					w4[1] = 1 / ((double)LPP[SH(nP, -1, n, 0)] * CP[in1]);
-					w4[2] = 1 / ((double)LP[ip] * CPP[in1]);
-					w4[3] = 1 / ((double)LP[SH(nPP, -1, n, 0)] * CPP[in1]);
+					w4[0] = (float)(1 / (LPP[ip] * CP[in1]));
+					w4[1] = (float)(1 / (LPP[SH(nP, -1, n, 0)] * CP[in1]));
+					w4[2] = (float)(1 / (LP[ip] * CPP[in1]));
+					w4[3] = (float)(1 / (LP[SH(nPP, -1, n, 0)] * CPP[in1]));
 					wt2 = w4[0] + w4[1] + w4[2] + w4[3] - 2 * min4(w4);
 #undef SH
 					double w_total = wqp + wt1 + wt2;
@@ -735,7 +738,9 @@ static void build_excitation(orc_sim* s)
 					if (!yee_coords(s, n, pos, c, 0)) continue;
 					const prop_t* e = prop_at(s, c, MASK_EXC);
 					if (!e) continue;
-					if (e->exc_vec[n] != 0 && (e->exc_type == 0 || e->exc_type == 1)) {
+					/* CSPropExcitation::ActiveDir is true for every component unless set otherwise: a hard source
+					   zeroes vv/vi of all three components in its box, whatever the excitation vector */
+					if (e->exc_type == 0 || e->exc_type == 1) {
 						double amp = e->exc_vec[n] * orc_edge_length(s, n, pos, 0);
 						if (amp != 0) exc_push(&V, pos, n, (float)amp, (unsigned)(e->delay / dT));
 						if (e->exc_type == 1) {
@@ -749,7 +754,7 @@ static void build_excitation(orc_sim* s)
 					if (!yee_coords(s, n, pos, c, 1)) continue;
 					const prop_t* e = prop_at(s, c, MASK_EXC);
 					if (!e) continue;
-					if (e->exc_vec[n] != 0 && (e->exc_type == 2 || e->exc_type == 3)) {
+					if (e->exc_type == 2 || e->exc_type == 3) {
 						double amp = e->exc_vec[n] * orc_edge_length(s, n, pos, 1);
 						if (amp != 0) exc_push(&Cu, pos, n, (float)amp, (unsigned)(e->delay / dT));
 						if (e->exc_type == 3) {

@@ -1,8 +1,11 @@
-"""Generates the fixtures of this directory FROM THE ORACLE (oracle/fdtd_oracle.c), not from openEMS:
-the reference cannot be built or imported in this container, and its test tree holds no
-golden vectors for the time loop.  The fixtures therefore do not pin the oracle against the reference
-(tests/test_oracle_pinning.py does what can be done there); they freeze its output so that an accidental
-change of the oracle, of a test case builder or of the CUDA engine shows up as a bit difference.
+"""Generates the fixtures of this directory FROM THE REFERENCE ITSELF: oracle/_ref/libopenems_ref.so, i.e. the
+unmodified translation units of /root/reference (operator, multithreaded sse-compressed engine -- the
+reference's default engine --, extensions, Engine_Interface_FDTD) compiled by oracle/Makefile.ref and driven
+by oracle/ref_driver.cpp.  Needs /root/reference (or the prebuilt library).  Each fixture holds the timestep,
+voltage-probe series of every timestep and bit digests of E and H at three timesteps.
+
+The CPU suite checks the oracle restatement against them (tests/test_oracle_pinning.py), the GPU suite the
+CUDA engine, both schedules (tests/test_gpu_parity.py).
 
 usage: python tests/golden/make_golden.py      (rewrites tests/golden/*.npz)"""
 import os
@@ -12,7 +15,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from tests import cases  # noqa: E402
+from tests import cases, configs  # noqa: E402
 from oracle.pyoracle import BC_PML, BC_MUR, BC_PEC, BC_PMC  # noqa: E402
 
 PROBES = [((5, 4, 5), (6, 4, 5)), ((10, 2, 20), (10, 8, 20)), ((20, 5, 12), (20, 5, 28))]
@@ -33,6 +36,27 @@ def allpml_case():
     return cases.uniform_box(n=(40, 36, 44), bc=(BC_PML,) * 6, pml=8)
 
 
+def ppw_sinus_case():
+    return configs.c1_parallel_plate_waveguide("sinus")[0]
+
+
+def drude_case():
+    return configs.c4_drude_block(n=(30, 30, 30), block=(10, 20))
+
+
+def patch_case():
+    return configs.c3_patch_antenna(n=(40, 40, 30))[0]
+
+
+CASES = {
+    "cavity_mur_pml_pmc": (cavity_case, 240, PROBES),
+    "uniform_allpml_40x36x44": (allpml_case, 120, [((20, 18, 10), (20, 18, 30)), ((8, 8, 8), (30, 8, 8))]),
+    "ppw_sinus_mur_pmc": (ppw_sinus_case, 150, [((10, 0, 25), (10, 20, 25)), ((10, 0, 35), (10, 20, 35))]),
+    "drude_block_30": (drude_case, 100, [((5, 15, 15), (25, 15, 15)), ((15, 12, 8), (15, 18, 8))]),
+    "patch_lumped_rc_pml": (patch_case, 80, [((17, 20, 12), (17, 20, 14)), ((10, 10, 16), (30, 10, 16))]),
+}
+
+
 def record(s, steps, probes):
     series = np.zeros((steps, len(probes)), np.float64)
     digests = []
@@ -46,12 +70,15 @@ def record(s, steps, probes):
 
 
 def main():
-    for name, make, steps, probes in (("cavity_mur_pml_pmc", cavity_case, 240, PROBES),
-                                      ("uniform_allpml_40x36x44", allpml_case, 120, [((20, 18, 10), (20, 18, 30)), ((8, 8, 8), (30, 8, 8))])):
-        s = make()
+    from oracle import pyref
+    from tests.ref_util import backend, ref_class
+    for name, (make, steps, probes) in CASES.items():
+        with backend(ref_class(pyref.ENGINE_MULTITHREADED, 3)):
+            s = make()
         series, digests = record(s, steps, probes)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), series=series, digests=digests, dT=np.float64(s.dT),
-                            probes=np.array(probes, np.int64), steps=np.int64(steps))
+                            probes=np.array(probes, np.int64), steps=np.int64(steps),
+                            source=np.bytes_(b"oracle/_ref/libopenems_ref.so (" + pyref.lib().ref_version() + b"), Engine_Multithread"))
         print(name, "dT", s.dT, "max|U|", np.abs(series).max(), "digests", digests.tolist())
 
 

@@ -215,15 +215,20 @@ def test_tfsf_restatement_injects_a_plane_wave():
     assert 0.9e-3 < peak_in < 1.1e-3 and peak_out < 0.01 * peak_in
 
 
-@pytest.mark.parametrize("name", ["cavity_mur_pml_pmc", "uniform_allpml_40x36x44"])
+from tests.golden.make_golden import CASES as GOLDEN_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
 def test_oracle_reproduces_committed_golden_vectors(name):
-    """tests/golden/*.npz were written by tests/golden/make_golden.py FROM THE ORACLE (the reference cannot
-    run here): they freeze probe series and field digests so that a change of the oracle or of a case
-    builder is noticed; the GPU suite checks the CUDA engine against the same files"""
+    """tests/golden/*.npz were written by tests/golden/make_golden.py FROM THE REFERENCE (oracle/_ref: the
+    unmodified reference TUs, multithreaded engine): timestep, voltage series of every timestep and E/H bit
+    digests.  The restatement must reproduce them bit for bit; the GPU suite checks the CUDA engine against the
+    same files."""
     import os
     from tests.golden import make_golden as G
     g = np.load(os.path.join(os.path.dirname(G.__file__), name + ".npz"))
-    s = G.cavity_case() if name.startswith("cavity") else G.allpml_case()
+    assert b"libopenems_ref" in bytes(g["source"])
+    s = GOLDEN_CASES[name][0]()
     assert s.dT == float(g["dT"])
     probes = [tuple(map(tuple, p)) for p in g["probes"].tolist()]
     series, digests = G.record(s, int(g["steps"]), probes)

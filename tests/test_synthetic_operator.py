@@ -1,16 +1,25 @@
 """The product's host-side operator builder (csrc/host/synthetic_operator.cpp)
-against the oracle's dense restatement of Operator::CalcECOperator: timestep, every
-coefficient, UPML aux coefficients, excitation lists and Mur coefficients, bit for bit.
+against (a) the REFERENCE'S OWN Operator::CalcECOperator + extension builders (oracle/_ref, the unmodified
+reference translation units) and (b) the oracle's dense restatement: timestep, every coefficient, UPML aux
+coefficients, excitation lists and Mur coefficients, bit for bit.
 CPU only (host code of libopenems_b200.so; no kernel is launched)."""
 import numpy as np
 import pytest
 
 from oracle.pyoracle import OracleSim, BC_PEC, BC_PMC, BC_MUR, BC_PML, EXC_E_SOFT, EXC_E_HARD, EXC_H_SOFT
+from oracle import pyref
 from openems_b200 import SyntheticOperator
 
+AGAINST = [pytest.param("reference", marks=pytest.mark.skipif(not pyref.available(), reason="oracle/_ref not available")), "oracle"]
 
-def both(lines, setup, unit=1.0):
-    o = OracleSim(*lines, unit)
+
+@pytest.fixture(params=AGAINST)
+def against(request):
+    return request.param
+
+
+def both(lines, setup, unit=1.0, against="oracle"):
+    o = pyref.RefSim(*lines, unit) if against == "reference" else OracleSim(*lines, unit)
     p = SyntheticOperator(*lines, unit)
     setup(o)
     setup(p)
@@ -52,7 +61,7 @@ def compare(o, p):
     assert np.array_equal(pml != 0, inbox)
 
 
-def test_vacuum_all_pml():
+def test_vacuum_all_pml(against):
     # mesh in drawing units (mm) with unit 1e-3, like the tutorials: exact, equal spacings
     lines = tuple(np.arange(n, dtype=np.float64) for n in (30, 28, 40))
 
@@ -60,7 +69,7 @@ def test_vacuum_all_pml():
         s.set_bc([BC_PML] * 6, (8,) * 6)
         s.set_excite_gauss(0.0, 15e9)
         s.add_excitation((14.5, 14, 16), (14.5, 14, 16), EXC_E_SOFT, (1, 0, 0))
-    o, p = both(lines, setup, unit=1e-3)
+    o, p = both(lines, setup, unit=1e-3, against=against)
     compare(o, p)
     assert p.n_unique < 6000 and p.index_bytes == 2  # ~17^3 depth classes
     assert p.unique_planes < 40  # interior planes away from the source share one computation
@@ -70,7 +79,7 @@ def test_vacuum_all_pml():
     assert np.array_equal(up[ids], p.index())
 
 
-def test_mixed_bc_materials_metal_nonuniform_mesh():
+def test_mixed_bc_materials_metal_nonuniform_mesh(against):
     x = np.cumsum(np.r_[0, np.full(10, 1.0), np.linspace(1.0, 0.5, 6), np.full(12, 0.5)]) * 1e-3
     y = np.arange(26) * 0.8e-3
     z = np.cumsum(np.r_[0, np.full(30, 0.7)]) * 1e-3
@@ -84,23 +93,23 @@ def test_mixed_bc_materials_metal_nonuniform_mesh():
         s.add_metal((x[6], y[5], z[18]), (x[18], y[15], z[18]))
         s.add_excitation((x[12], y[10], z[3]), (x[12], y[16], z[3]), EXC_E_HARD, (0, 1, 0), delay=2e-11)
         s.add_excitation((x[3], y[3], z[8]), (x[5], y[5], z[8]), EXC_H_SOFT, (1, 1, 0))
-    o, p = both(lines := (x, y, z), setup)
+    o, p = both((x, y, z), setup, against=against)
     compare(o, p)
 
 
-def test_excitation_on_mur_plane_delays_start():
+def test_excitation_on_mur_plane_delays_start(against):
     lines = tuple(np.arange(n) * 1e-3 for n in (14, 15, 20))
 
     def setup(s):
         s.set_bc([BC_PEC, BC_PEC, BC_PEC, BC_PEC, BC_MUR, BC_MUR])
         s.set_excite_gauss(10e9, 8e9)
         s.add_excitation((0, 0, 0), (0.013, 0.0135, 0), EXC_E_SOFT, (0, 1, 0))
-    o, p = both(lines, setup)
+    o, p = both(lines, setup, against=against)
     compare(o, p)
     assert p.mur_planes()[0]["start_ts"] > 0
 
 
-def test_lorentz_lists_match():
+def test_lorentz_lists_match(against):
     lines = tuple(np.arange(n) * 1e-3 for n in (20, 22, 24))
 
     def setup(s):
@@ -109,7 +118,7 @@ def test_lorentz_lists_match():
         s.add_lorentz((0.006, 0.007, 0.008), (0.013, 0.014, 0.015), epsR=1.0, eps_fp=(5e9, 2e9), eps_tau=(5e-9, 0.0),
                       eps_flor=(0.0, 7e9), mue_fp=(5e9,), mue_tau=(5e-9,))
         s.add_excitation((0.003, 0.003, 0.0035), (0.003, 0.003, 0.0035), EXC_E_SOFT, (0, 0, 1))
-    o, p = both(lines, setup)
+    o, p = both(lines, setup, against=against)
     compare(o, p)
     ol = o.lorentz()
     assert p.lorentz_counts() == [L["count"] for L in ol]
