@@ -196,6 +196,16 @@ int oems_cuda_add_dump(oems_cuda_engine* h, int is_H, int interp, unsigned nx, u
 /* computes the dump on the device at the current numTS and copies it to `out`
    (asynchronously into pinned staging, then to the caller's buffer) */
 int oems_cuda_read_dump(oems_cuda_engine* h, int dump_id, float* out);
+/* the same without stalling the time loop (ProcessFieldsTD::Process, Common/processfields_td.cpp:50-91, is the
+   consumer): the dump is evaluated on the device at the current numTS, the copy into `pinned_out` (page-locked,
+   e.g. from oems_cuda_host_alloc; 3*nx*ny*nz floats) runs on a second stream while oems_cuda_iterate goes on.
+   oems_cuda_wait(ticket) returns when that copy has landed.  One copy per dump box may be outstanding; issuing
+   the next one for the same box orders itself after the previous copy on the device (no host wait). */
+int oems_cuda_read_dump_async(oems_cuda_engine* h, int dump_id, float* pinned_out, long long* ticket);
+int oems_cuda_wait(oems_cuda_engine* h, long long ticket);
+/* page-locked host memory for asynchronous read-outs */
+int oems_cuda_host_alloc(size_t bytes, void** out);
+int oems_cuda_host_free(void* p);
 
 /* ProcessFieldsFD (Common/processfields_fd.cpp:40-107): running DFT of a field dump, kept on the
    device.  oems_cuda_add_fd_dump attaches n_freq complex<float> accumulators (zero) to a dump

@@ -18,13 +18,15 @@
 class Engine_Interface_CUDA_FDTD : public Engine_Interface_FDTD
 {
 public:
-	Engine_Interface_CUDA_FDTD(Operator* op) : Engine_Interface_FDTD(op), m_Eng_CUDA(NULL), m_cache_ts((unsigned int)-1) {}
+	//! Engine_Interface_FDTD's constructor takes the engine from op->GetEngine() (engine_interface_fdtd.cpp:31):
+	//! interfaces are created after Operator::CreateEngine (openems.cpp:1316-1330)
+	Engine_Interface_CUDA_FDTD(Operator* op) : Engine_Interface_FDTD(op), m_Eng_CUDA(dynamic_cast<Engine_CUDA*>(m_Eng)),
+		m_slots(0), m_cache_ts((unsigned int)-1) {}
 	virtual ~Engine_Interface_CUDA_FDTD() {}
 
 	virtual std::string GetInterfaceString() const {return std::string("B200 CUDA FDTD engine interface");}
 
-	//! openEMS::SetupProcessing calls SetFDTDEngine() after construction (openems.cpp:447-476)
-	void SetFDTDEngine(Engine* eng) {Engine_Interface_FDTD::SetFDTDEngine(eng); m_Eng_CUDA = dynamic_cast<Engine_CUDA*>(eng);}
+	virtual void SetFDTDEngine(Engine* eng) {Engine_Interface_FDTD::SetFDTDEngine(eng); m_Eng_CUDA = dynamic_cast<Engine_CUDA*>(eng);}
 
 	virtual double CalcVoltageIntegral(const unsigned int* start, const unsigned int* stop) const;
 	virtual double CalcFastEnergy() const;

@@ -2,6 +2,9 @@
 #include "operator_cuda.h"
 #include "engine_cuda.h"
 
+using std::cout;
+using std::endl;
+
 Operator_CUDA* Operator_CUDA::New(unsigned int numThreads, int device)
 {
 	cout << "Create FDTD operator (B200 CUDA engine, host build multi-threaded)" << endl;
@@ -10,15 +13,6 @@ Operator_CUDA* Operator_CUDA::New(unsigned int numThreads, int device)
 	op->m_device = device;
 	op->Init();
 	return op;
-}
-
-int Operator_CUDA::CalcECOperator( DebugFlags debugFlags )
-{
-	// Operator_SSE_Compressed::CalcECOperator would compress after the build
-	// (operator_sse_compressed.cpp:56-63); switch that off and run the threaded build.
-	m_Use_Compression = false;
-	m_max_fifo = 0;
-	return Operator_Multithread::CalcECOperator( debugFlags );
 }
 
 Engine* Operator_CUDA::CreateEngine()

@@ -1,10 +1,14 @@
 /*
  * operator_cuda.h -- Operator_CUDA: the operator half of --engine=cuda.
- * Goes to openEMS/FDTD/operator_cuda.h.  Compiled inside openEMS (needs its headers and
- * CSXCAD); it is NOT built in this repository, see INTEGRATION.md.
+ * Goes to openEMS/FDTD/operator_cuda.h.  Compiled inside openEMS; in this repository it is compiled
+ * against the reference's unmodified headers and run by the oracle/_ref harness
+ * (oracle/Makefile.ref, target libopenems_ref_cuda.so; tests/test_gpu_reference_integration.py).
  *
  * Derives from Operator_Multithread so the host build (Calc_EC, CalcPEC, extensions'
  * BuildExtension) stays the reference's own, threaded code; only CreateEngine differs.
+ * (The sse compression of Operator_SSE_Compressed::CalcECOperator still runs -- it cannot be
+ * skipped without editing the reference -- and is simply not used: Engine_CUDA reads the
+ * coefficients through GetVV/GetVI/GetII/GetIV and the library re-keys them per cell.)
  */
 #ifndef OPERATOR_CUDA_H
 #define OPERATOR_CUDA_H
@@ -25,9 +29,6 @@ public:
 
 protected:
 	Operator_CUDA() : Operator_Multithread(), m_device(-1) {}
-	//! keep the dense f4 arrays: Engine_CUDA re-keys them per cell (library side), so the
-	//! SSE compression (per 4 interleaved z cells, operator_sse_compressed.cpp:114-175) is skipped
-	virtual int CalcECOperator( DebugFlags debugFlags = None );
 	int m_device;
 };
 

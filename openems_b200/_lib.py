@@ -73,6 +73,10 @@ SIGNATURES = {
     "oems_cuda_add_dump": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, _up, _up, _up,
                                      C.POINTER(_dp), C.POINTER(_dp), _ip]),
     "oems_cuda_read_dump": (C.c_int, [_vp, C.c_int, _fp]),
+    "oems_cuda_read_dump_async": (C.c_int, [_vp, C.c_int, C.c_void_p, C.POINTER(C.c_longlong)]),
+    "oems_cuda_wait": (C.c_int, [_vp, C.c_longlong]),
+    "oems_cuda_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "oems_cuda_host_free": (C.c_int, [C.c_void_p]),
     "oems_cuda_get_field": (C.c_int, [_vp, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, _fp]),
     "oems_cuda_set_field": (C.c_int, [_vp, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_float]),
     "oems_cuda_get_fields": (C.c_int, [_vp, C.c_int, _fp]),

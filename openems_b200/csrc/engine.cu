@@ -62,6 +62,13 @@ Engine::~Engine()
 	}
 	for (auto& d : dumps) {
 		if (d.h_pinned) cudaFreeHost(d.h_pinned);
+		if (d.ev_computed) cudaEventDestroy(d.ev_computed);
+		if (d.ev_copied) cudaEventDestroy(d.ev_copied);
+	}
+	if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+	for (auto& f : fds) {
+		if (f.h_w) cudaFreeHost(f.h_w);
+		for (int r = 0; r < FdHost::RING; ++r) if (f.ev[r]) cudaEventDestroy(f.ev[r]);
 	}
 	for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
 	for (void* p : allocs) cudaFree(p);
@@ -401,14 +408,16 @@ int Engine::compress_dense(std::vector<uint32_t>& index32)
 	index32.assign((size_t)nx * ny * nzl, 0);
 	const int nthreads = std::max(1, std::min(omp_get_max_threads(), nzl));
 	std::vector<EntrySet> sets(nthreads);
+	std::vector<int> owner(nzl, 0); // the thread (= thread-local set) that keyed plane kl: the remap below must not rely on the runtime handing out the same planes again
 	for (auto& B : h_upml)
 		if (B.c[0].empty()) return fail("dense operator needs dense UPML coefficient arrays");
 #pragma omp parallel num_threads(nthreads)
 	{
-		const int t = omp_get_thread_num();
+		const int t = omp_get_thread_num() % nthreads;
 		EntrySet& S = sets[t];
 #pragma omp for schedule(static)
 		for (int kl = 0; kl < nzl; ++kl) {
+			owner[kl] = t;
 			const unsigned gz = (unsigned)(z0 + kl);
 			for (unsigned j = 0; j < ny; ++j)
 				for (unsigned i = 0; i < nx; ++i) {
@@ -443,14 +452,11 @@ int Engine::compress_dense(std::vector<uint32_t>& index32)
 		remap[t].resize(sets[t].items.size());
 		for (size_t u = 0; u < sets[t].items.size(); ++u) remap[t][u] = G.insert(sets[t].items[u]);
 	}
-#pragma omp parallel num_threads(nthreads)
-	{
-		const int t = omp_get_thread_num();
-#pragma omp for schedule(static)
-		for (int kl = 0; kl < nzl; ++kl) {
-			uint32_t* row = index32.data() + (size_t)kl * ny * nx;
-			for (size_t q = 0; q < (size_t)ny * nx; ++q) row[q] = remap[t][row[q]];
-		}
+#pragma omp parallel for schedule(static)
+	for (int kl = 0; kl < nzl; ++kl) {
+		uint32_t* row = index32.data() + (size_t)kl * ny * nx;
+		const std::vector<uint32_t>& R = remap[owner[kl]];
+		for (size_t q = 0; q < (size_t)ny * nx; ++q) row[q] = R[row[q]];
 	}
 	h_table.swap(G.items);
 	n_unique = (unsigned)h_table.size();
@@ -770,39 +776,37 @@ int Engine::build_mur()
 		cPP.insert(cPP.end(), M.cPP.begin(), M.cPP.end());
 	}
 	// write conflicts on shared edges: Apply2Voltages runs the planes in reverse insertion order
-	// (engine.cpp:87-91,239-244), so the plane inserted FIRST writes last and wins.  A component
-	// c of a cell is written by at most two planes (normals != c).
-	std::vector<unsigned char> winner((size_t)total, 3);
+	// (engine.cpp:87-91,239-244), so the plane inserted FIRST writes last and wins -- once it is active
+	// (IsActive(), engine_ext_mur_abc.h:56).  A component c of a cell is written by at most two planes
+	// (normals != c).  Per entry and component: the start timestep of the earlier-inserted plane that
+	// overrides this write (0xffffffff: nobody does); resolved at run time against numTS, so planes with
+	// different start delays (a source on one Mur face) follow the reference step by step.
+	std::vector<unsigned> ovr((size_t)2 * total, 0xffffffffu);
 	for (size_t m = 0; m < h_mur.size(); ++m) {
 		const MurPlane& P = pMur.pl[m];
 		for (int a = 0; a < P.n0; ++a)
 			for (int b = 0; b < P.n1; ++b) {
 				int pos[3];
 				pos[P.ny] = P.line; pos[P.nyP] = a; pos[P.nyPP] = b;
-				unsigned char w = 3;
 				const int comps[2] = {P.nyP, P.nyPP};
 				for (int q = 0; q < 2; ++q) {
 					const int other = 3 - P.ny - comps[q]; // normal of the other plane that writes comps[q]
 					for (size_t m2 = 0; m2 < m; ++m2)
-						if (pMur.pl[m2].ny == other && pos[other] == pMur.pl[m2].line) {
-							// the earlier plane overrides this write; exact only if both are active at the
-							// same time, which holds unless their start delays differ
-							if (pMur.pl[m2].start_ts <= P.start_ts) w &= (unsigned char)~(1u << q);
-						}
+						if (pMur.pl[m2].ny == other && pos[other] == pMur.pl[m2].line)
+							ovr[(size_t)q * total + (size_t)P.eoff + (size_t)a * P.n1 + b] = pMur.pl[m2].start_ts;
 				}
-				winner[(size_t)P.eoff + (size_t)a * P.n1 + b] = w;
 			}
 	}
 	pMur.V = d_V;
 	pMur.cP = upload(cP); pMur.cPP = upload(cPP);
 	pMur.vP = dalloc<float>((size_t)total); pMur.vPP = dalloc<float>((size_t)total);
-	pMur.winner = upload(winner);
+	pMur.ovr_start = upload(ovr);
 	pMur.numTS = d_numTS;
 	pMur.nplanes = (int)h_mur.size();
 	pMur.total = total;
 	pMur.pitch = pitch; pMur.plane = plane; pMur.comp = comp;
 	pMur.z0 = z0; pMur.zown0 = (int)zb; pMur.zown1 = (int)ze;
-	if (!pMur.cP || !pMur.cPP || !pMur.vP || !pMur.vPP || !pMur.winner) return fail("out of device memory (Mur)");
+	if (!pMur.cP || !pMur.cPP || !pMur.vP || !pMur.vPP || !pMur.ovr_start) return fail("out of device memory (Mur)");
 	return 0;
 }
 
@@ -1068,7 +1072,7 @@ void Engine::build_schedule()
 	// ---- multi-GPU: the ghost H plane of this step must have arrived
 	if (multi && peer_lo)
 		(labels.push_back("halo_wait_H"), step.push_back([this](cudaStream_t s) {
-			WaitParams w{d_flagH, d_numTS, 0u, d_halo_err, 4000000000ll};
+			WaitParams w{d_flagH, d_numTS, 0u, d_halo_err, halo_timeout_cycles()};
 			k_halo_wait<<<1, 1, 0, s>>>(w);
 		}));
 	// ---- E half-step with fused UPML
@@ -1112,7 +1116,7 @@ void Engine::build_schedule()
 		if (sheet_dev[a].i.count) (labels.push_back("sheet_pre_I"), step.push_back([this, a](cudaStream_t s) { launch1d(k_sheet_pre, sheet_dev[a].i, sheet_dev[a].i.count, s); }));
 	if (multi && peer_hi)
 		(labels.push_back("halo_wait_E"), step.push_back([this](cudaStream_t s) {
-			WaitParams w{d_flagE, d_numTS, 1u, d_halo_err, 4000000000ll};
+			WaitParams w{d_flagE, d_numTS, 1u, d_halo_err, halo_timeout_cycles()};
 			k_halo_wait<<<1, 1, 0, s>>>(w);
 		}));
 	// ---- H half-step with fused UPML, then the UPML cells the stencil never visits
@@ -1258,15 +1262,20 @@ int Engine::make_tma_maps(int par)
 			return 1;
 		}
 		encode = (EncodeFn)fn;
-		static bool attr_done = false;
-		if (!attr_done) {
-			attr_done = true;
+	}
+	{
+		// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: set it on every
+		// device an engine of this process lives on (two engines on two GPUs: link_engines_in_process)
+		static std::vector<int> attr_devices;
+		if (std::find(attr_devices.begin(), attr_devices.end(), device) == attr_devices.end()) {
+			CK(cudaSetDevice(device));
 			const int s16 = ft_smem_bytes<uint16_t, FT_STAGES>(), s32 = ft_smem_bytes<uint32_t, FT_STAGES>();
 			cudaFuncSetAttribute(k_fused_tma<uint16_t, true, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
 			cudaFuncSetAttribute(k_fused_tma<uint16_t, false, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
 			cudaFuncSetAttribute(k_fused_tma<uint32_t, true, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
 			cudaFuncSetAttribute(k_fused_tma<uint32_t, false, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
-			if (cudaGetLastError() != cudaSuccess) { encode = nullptr; return 1; }
+			if (cudaGetLastError() != cudaSuccess) return 1;
+			attr_devices.push_back(device);
 		}
 	}
 	const int S = par;
@@ -1471,7 +1480,7 @@ void Engine::build_schedule_fused()
 		if (multi && peer_lo) {
 			lab("halo_wait_H");
 			L.push_back([this](cudaStream_t s) {
-				WaitParams w{d_flagH, d_numTS, 0u, d_halo_err, 4000000000ll};
+				WaitParams w{d_flagH, d_numTS, 0u, d_halo_err, halo_timeout_cycles()};
 				k_halo_wait<<<1, 1, 0, s>>>(w);
 			});
 		}
@@ -1570,7 +1579,7 @@ void Engine::build_schedule_fused()
 		if (multi && peer_hi) {
 			lab("halo_wait_E");
 			L.push_back([this](cudaStream_t s) {
-				WaitParams w{d_flagE, d_numTS, 1u, d_halo_err, 4000000000ll};
+				WaitParams w{d_flagE, d_numTS, 1u, d_halo_err, halo_timeout_cycles()};
 				k_halo_wait<<<1, 1, 0, s>>>(w);
 			});
 			lab("update_H_top");
@@ -1625,8 +1634,19 @@ void Engine::flux_sets_sync(bool to_set0)
 }
 
 // schedule rebuild that keeps the state: the set of x-slab boxes may change with the options
+// option "halo_timeout_s" (default 600 s): how long a slab waits for its neighbour's halo before giving up.
+// Host-side skew between ranks (per-rank dump processing between bursts, uneven engine creation, a rank's launch
+// queue filling before the other rank is enqueued) must stay below it.
+long long Engine::halo_timeout_cycles() const
+{
+	int khz = 0;
+	if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device) != cudaSuccess || khz <= 0) khz = 2000000;
+	return (long long)halo_timeout_s * (long long)khz * 1000ll;
+}
+
 int Engine::rebuild_schedule()
 {
+	CK(cudaSetDevice(device));
 	CK(cudaStreamSynchronize(stream));
 	if (fused_active) flux_sets_sync(true);
 	build_schedule();
@@ -1644,6 +1664,7 @@ bool Engine::fused_auto_choice() const
 int Engine::set_fused_active(int req)
 {
 	const bool on = fused_possible && !edge_dirty && (req == 1 || (req < 0 && fused_auto_choice()));
+	CK(cudaSetDevice(device));
 	CK(cudaStreamSynchronize(stream));
 	if (fused_active) flux_sets_sync(true);
 	if (fused_active && !on && (numTS_host & 1u)) {
@@ -1707,11 +1728,17 @@ int Engine::iterate(unsigned n)
 int Engine::set_option(const char* key, long long value)
 {
 	const std::string k = key ? key : "";
+	if (finalized) CK(cudaSetDevice(device));
 	if (k == "fused") {
 		// 0: two-pass, 1: one-pass (if the hook set allows it), -1: automatic
 		if (!finalized) { fused_req = value < 0 ? -1 : (value != 0); return 0; }
 		if (value > 0 && edge_dirty) return 0;
 		return set_fused_active(value < 0 ? -1 : (value != 0));
+	}
+	if (k == "halo_timeout_s") {
+		halo_timeout_s = (int)std::max<long long>(1, std::min<long long>(86400, value));
+		if (finalized) return rebuild_schedule();
+		return 0;
 	}
 	if (k == "shell_zchunk") { // planes a UPML shell block marches (tuning aid)
 		shell_zchunk = (int)std::max<long long>(1, std::min<long long>(64, value));
@@ -1772,7 +1799,13 @@ int Engine::iterate_timed(unsigned n, double* ms)
 int Engine::sync()
 {
 	CK(cudaSetDevice(device));
-	if (stream) CK(cudaStreamSynchronize(stream));
+	if (stream) {
+		cudaError_t e = cudaStreamSynchronize(stream);
+		if (e != cudaSuccess && peers_linked)
+			return fail(std::string("device fault while stepping a z-slab (") + cudaGetErrorString(e) +
+			            "): a halo wait gave up after option halo_timeout_s seconds without the neighbour's plane, or a kernel faulted");
+		CK(e);
+	}
 	if (d_halo_err) {
 		unsigned e = 0;
 		CK(cudaMemcpy(&e, d_halo_err, sizeof(e), cudaMemcpyDeviceToHost));
@@ -2044,14 +2077,54 @@ int Engine::add_dump(int is_H, int interp, unsigned nx, unsigned ny, unsigned nz
 int Engine::read_dump(int id, float* out)
 {
 	if (id < 0 || id >= (int)dumps.size()) return fail("read_dump: bad id");
+	long long t = 0;
+	DumpHost& D = dumps[id];
+	if (read_dump_async(id, D.h_pinned, &t)) return 1;
+	if (wait_ticket(t)) return 1;
+	memcpy(out, D.h_pinned, 3 * D.count * sizeof(float));
+	return 0;
+}
+
+// ProcessFieldsTD::Process without stalling the time loop (north_star (4), Common/processfields_td.cpp:50-91):
+// k_dump gathers/interpolates at the CURRENT timestep on the engine stream; the D2H copy into the caller's
+// page-locked buffer runs on a second stream.  Stepping may continue immediately (the kernel has captured the
+// fields of this timestep in d_out); the ticket is waited for only when the host needs the data.
+int Engine::read_dump_async(int id, float* pinned_out, long long* ticket)
+{
+	if (id < 0 || id >= (int)dumps.size()) return fail("read_dump_async: bad id");
+	if (!pinned_out || !ticket) return fail("read_dump_async: null pointer");
 	CK(cudaSetDevice(device));
 	DumpHost& D = dumps[id];
+	if (!copy_stream) CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+	if (!D.ev_computed) {
+		CK(cudaEventCreateWithFlags(&D.ev_computed, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&D.ev_copied, cudaEventDisableTiming));
+	}
+	if (D.copy_pending) CK(cudaStreamWaitEvent(stream, D.ev_copied, 0)); // d_out still being read by the last copy
 	D.p.V = sV[cur()]; D.p.I = sI[cur()];
 	launch1d(k_dump, D.p, (long long)D.count, stream);
 	++kernels_launched;
-	CK(cudaMemcpyAsync(D.h_pinned, D.d_out, 3 * D.count * sizeof(float), cudaMemcpyDeviceToHost, stream));
-	CK(cudaStreamSynchronize(stream));
-	memcpy(out, D.h_pinned, 3 * D.count * sizeof(float));
+	CK(cudaEventRecord(D.ev_computed, stream));
+	CK(cudaStreamWaitEvent(copy_stream, D.ev_computed, 0));
+	CK(cudaMemcpyAsync(pinned_out, D.d_out, 3 * D.count * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
+	CK(cudaEventRecord(D.ev_copied, copy_stream));
+	D.copy_pending = true;
+	++D.seq;
+	*ticket = ((long long)id << 32) | (long long)(D.seq & 0xffffffffull);
+	return 0;
+}
+
+int Engine::wait_ticket(long long ticket)
+{
+	const int id = (int)(ticket >> 32);
+	if (id < 0 || id >= (int)dumps.size()) return fail("wait: bad ticket");
+	DumpHost& D = dumps[id];
+	// an older ticket of the same box is covered too: copies of one box are ordered on the copy stream
+	CK(cudaSetDevice(device));
+	if (D.copy_pending) {
+		CK(cudaEventSynchronize(D.ev_copied));
+		D.copy_pending = false;
+	}
 	return 0;
 }
 
@@ -2067,14 +2140,19 @@ int Engine::add_fd_dump(int dump_id, unsigned nfreq, int* id)
 	F.dump = dump_id; F.nfreq = nfreq; F.samples = 0;
 	const size_t n = 3 * dumps[dump_id].count;
 	F.d_acc = dalloc<float2>(n * nfreq);
-	F.d_w = dalloc<float2>(nfreq);
+	F.d_w = dalloc<float2>((size_t)FdHost::RING * nfreq);
 	if (!F.d_acc || !F.d_w) return fail("out of device memory (FD dump)");
+	F.h_w = nullptr;
+	CK(cudaMallocHost((void**)&F.h_w, (size_t)FdHost::RING * nfreq * sizeof(float2)));
+	for (int r = 0; r < FdHost::RING; ++r) CK(cudaEventCreateWithFlags(&F.ev[r], cudaEventDisableTiming));
 	CK(cudaMemsetAsync(F.d_acc, 0, n * nfreq * sizeof(float2), stream));
 	if (id) *id = (int)fds.size();
 	fds.push_back(F);
 	return 0;
 }
 
+// one sample of ProcessFieldsFD::Process; only enqueues (the weights travel through a small page-locked ring,
+// so the caller's buffer is free on return and the time loop is not stalled)
 int Engine::fd_accumulate(int fd_id, const float* w)
 {
 	if (fd_id < 0 || fd_id >= (int)fds.size()) return fail("fd_accumulate: bad id");
@@ -2082,15 +2160,21 @@ int Engine::fd_accumulate(int fd_id, const float* w)
 	CK(cudaSetDevice(device));
 	FdHost& F = fds[fd_id];
 	DumpHost& D = dumps[F.dump];
+	const int slot = (int)(F.samples % FdHost::RING);
+	if (F.samples >= (unsigned)FdHost::RING) CK(cudaEventSynchronize(F.ev[slot])); // the copy of RING samples ago has left this slot
+	float2* hw = F.h_w + (size_t)slot * F.nfreq;
+	float2* dw = F.d_w + (size_t)slot * F.nfreq;
+	memcpy(hw, w, F.nfreq * sizeof(float2));
+	if (D.copy_pending) CK(cudaStreamWaitEvent(stream, D.ev_copied, 0));
 	D.p.V = sV[cur()]; D.p.I = sI[cur()];
 	launch1d(k_dump, D.p, (long long)D.count, stream);
-	CK(cudaMemcpyAsync(F.d_w, w, F.nfreq * sizeof(float2), cudaMemcpyHostToDevice, stream));
+	CK(cudaMemcpyAsync(dw, hw, F.nfreq * sizeof(float2), cudaMemcpyHostToDevice, stream));
+	CK(cudaEventRecord(F.ev[slot], stream));
 	FdParams q;
-	q.td = D.d_out; q.acc = F.d_acc; q.w = F.d_w; q.n = (long long)(3 * D.count); q.nfreq = F.nfreq;
+	q.td = D.d_out; q.acc = F.d_acc; q.w = dw; q.n = (long long)(3 * D.count); q.nfreq = F.nfreq;
 	launch1d(k_fd_accumulate, q, q.n, stream);
 	kernels_launched += 2;
 	++F.samples;
-	CK(cudaStreamSynchronize(stream)); // w is the caller's buffer
 	return 0;
 }
 

@@ -52,6 +52,12 @@ struct DumpHost {
 	float* d_out;
 	float* h_pinned;
 	std::vector<void*> dev_allocs;
+	// asynchronous read-out (oems_cuda_read_dump_async): k_dump runs on the engine stream, the D2H copy on the
+	// copy stream; ev_computed orders the copy after the kernel, ev_copied is the ticket and also keeps the
+	// next k_dump of this box from overwriting d_out before the copy has left
+	cudaEvent_t ev_computed = nullptr, ev_copied = nullptr;
+	unsigned long long seq = 0;
+	bool copy_pending = false;
 };
 
 struct TfsfHost {     // Operator_Ext_TFSF tables, index (n*2+l)*2+c
@@ -70,10 +76,13 @@ struct SheetHost {    // one local absorbing sheet (Operator_Ext_Absorbing_BC)
 struct SheetDev { SheetParams v, i; };
 
 struct FdHost {
+	static const int RING = 4;
 	int dump;          // time-domain dump this spectrum is taken from
 	unsigned nfreq;
 	float2* d_acc;     // [nfreq][3*count]
-	float2* d_w;       // [nfreq]
+	float2* d_w;       // [RING][nfreq]: weights of the last RING samples
+	float2* h_w;       // the same in page-locked host memory (source of the asynchronous H2D copies)
+	cudaEvent_t ev[RING]; // slot s may be rewritten once ev[s] has passed
 	unsigned samples;
 };
 
@@ -121,6 +130,8 @@ public:
 	int add_dump(int is_H, int interp, unsigned nx, unsigned ny, unsigned nz, const unsigned* px, const unsigned* py,
 	             const unsigned* pz, const double* const el[3], const double* const del[3], int* id);
 	int read_dump(int id, float* out);
+	int read_dump_async(int id, float* pinned_out, long long* ticket);
+	int wait_ticket(long long ticket);
 	int add_fd_dump(int dump_id, unsigned nfreq, int* id);
 	int fd_accumulate(int fd_id, const float* w);
 	int read_fd(int fd_id, float* out, unsigned* samples);
@@ -169,6 +180,7 @@ private:
 	long long plane, comp;
 	bool finalized = false, slab_set = false;
 	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream = nullptr; // D2H of dumps, overlapping the time loop
 
 	// host staging
 	std::vector<float> h_dense[4];    // local slab, NIJK over local planes
@@ -280,6 +292,8 @@ private:
 	unsigned *d_flagE = nullptr, *d_flagH = nullptr, *d_halo_cnt = nullptr, *d_halo_err = nullptr;
 	long long peer_lo_comp = 0, peer_hi_comp = 0, peer_lo_ghostE_off = 0, peer_hi_ghostH_off = 0;
 	bool peers_linked = false;
+	int halo_timeout_s = 600;
+	long long halo_timeout_cycles() const;
 	std::vector<void*> ipc_opened;
 
 	template <typename T> T* dalloc(size_t n, bool zero = true);

@@ -375,7 +375,7 @@ struct MurParams {
 	float* V;
 	const float* cP; const float* cPP;
 	float* vP; float* vPP;
-	const unsigned char* winner; // bit0: this entry's nyP write survives, bit1: nyPP
+	const unsigned* ovr_start; // [2][total]: start timestep of the earlier-inserted plane whose write to the same edge wins (0xffffffff: none)
 	const unsigned* numTS;
 	int nplanes;
 	long long total;
@@ -427,9 +427,9 @@ __global__ void k_mur_apply(const __grid_constant__ MurParams p)
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	int m; long long o[2], os[2];
 	if (!mur_locate(p, t, m, o, os)) return;
-	const unsigned char w = p.winner[t];
-	if (w & 1) p.V[o[0]] = p.vP[t];
-	if (w & 2) p.V[o[1]] = p.vPP[t];
+	const unsigned ts = *p.numTS;
+	if (ts < p.ovr_start[t]) p.V[o[0]] = p.vP[t];
+	if (ts < p.ovr_start[p.total + t]) p.V[o[1]] = p.vPP[t];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1056,7 +1056,13 @@ __global__ void k_halo_wait(const __grid_constant__ WaitParams p)
 	const unsigned want = *p.numTS + p.flag_add;
 	const long long t0 = clock64();
 	while ((int)(*p.flag - want) < 0) {
-		if (clock64() - t0 > p.timeout_cycles) { *p.error = 1; break; }
+		if (clock64() - t0 > p.timeout_cycles) {
+			// the neighbour never published this step: stop here instead of stepping on with a stale ghost plane.
+			// The trap makes every later call on this device fail (reported by iterate / sync), nothing is consumed.
+			*p.error = 1;
+			__threadfence_system();
+			__trap();
+		}
 		__nanosleep(200);
 	}
 	__threadfence_system();

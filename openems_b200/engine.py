@@ -402,6 +402,28 @@ class Engine_CUDA:
         self._ck(self._L.oems_cuda_read_dump(self._h, dump_id, _ptr(out, _fp)))
         return out
 
+    def ReadDumpAsync(self, dump_id):
+        """ProcessFieldsTD::Process without stalling the time loop: evaluates the dump at the current timestep and starts
+        its copy into page-locked host memory on a second stream; returns a ticket.  WaitDump(ticket) -> ndarray"""
+        shape = self._dump_shapes[dump_id]
+        if not hasattr(self, "_dump_pinned"):
+            self._dump_pinned = {}
+        if dump_id not in self._dump_pinned:
+            p = C.c_void_p()
+            if self._L.oems_cuda_host_alloc(int(np.prod(shape)) * 4, C.byref(p)):
+                raise EngineError("oems_cuda_host_alloc failed")
+            self._dump_pinned[dump_id] = p
+        t = C.c_longlong()
+        self._ck(self._L.oems_cuda_read_dump_async(self._h, dump_id, self._dump_pinned[dump_id], C.byref(t)))
+        return (dump_id, t.value)
+
+    def WaitDump(self, ticket):
+        dump_id, t = ticket
+        self._ck(self._L.oems_cuda_wait(self._h, t))
+        shape = self._dump_shapes[dump_id]
+        buf = (C.c_float * int(np.prod(shape))).from_address(self._dump_pinned[dump_id].value)
+        return np.frombuffer(buf, np.float32).reshape(shape).copy()
+
     def AddFDDump(self, dump_id, n_freq):
         """ProcessFieldsFD::InitProcess: complex accumulators for n_freq frequencies on the device"""
         i = C.c_int()

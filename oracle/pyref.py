@@ -21,6 +21,7 @@ from .pyoracle import OracleSim, _Namespace, _u3, _d3, _dp, _fp, _up
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_ref", "libopenems_ref.so")
+_LIB_CUDA = os.path.join(_HERE, "_ref", "libopenems_ref_cuda.so")
 REFERENCE_TREE = os.environ.get("OPENEMS_REFERENCE", "/root/reference")
 
 ENGINE_BASIC, ENGINE_SSE, ENGINE_SSE_COMPRESSED, ENGINE_MULTITHREADED, ENGINE_CUDA = 0, 1, 2, 3, 4
@@ -48,14 +49,38 @@ def build(force=False):
 
 
 _lib = None
+_lib_cuda = None
+
+
+def cuda_available():
+    """the harness variant that also contains integration/*.cpp (Operator_CUDA, Engine_CUDA, ...) linked with
+    libopenems_b200.so"""
+    if have_reference_tree():
+        build()
+    return os.path.exists(_LIB_CUDA)
+
+
+def lib_cuda():
+    global _lib_cuda
+    if _lib_cuda is None:
+        build()
+        if not os.path.exists(_LIB_CUDA):
+            raise FileNotFoundError("oracle/_ref/libopenems_ref_cuda.so missing")
+        _lib_cuda = _bind(C.CDLL(_LIB_CUDA))
+        _lib_cuda.ref_set_fast_processing.restype = None
+        _lib_cuda.ref_set_fast_processing.argtypes = [C.c_void_p, C.c_int]
+    return _lib_cuda
 
 
 def lib():
     global _lib
-    if _lib is not None:
-        return _lib
+    if _lib is None:
+        _lib = _bind(C.CDLL(build()))
+    return _lib
+
+
+def _bind(L):
     pyoracle.lib()   # fills pyoracle.SIGNATURES
-    L = C.CDLL(build())
     vp = C.c_void_p
     for name, (res, args) in pyoracle.SIGNATURES.items():
         rname = "ref_" + name[4:]
@@ -77,6 +102,8 @@ def lib():
         "ref_add_probe": (C.c_int, [vp, C.c_int, C.c_char_p, _d3, _d3, C.c_double, C.c_int]),
         "ref_add_dump": (C.c_int, [vp, C.c_char_p, _d3, _d3, C.c_int, C.c_int, C.c_int, C.c_uint]),
         "ref_add_fd_dump": (C.c_int, [vp, C.c_char_p, _d3, _d3, C.c_int, C.c_int, C.c_uint, _dp]),
+        "ref_add_mode_match": (C.c_int, [vp, C.c_char_p, _d3, _d3, C.c_int, C.c_char_p, C.c_char_p, C.c_int]),
+        "ref_has_cuda": (C.c_int, []),
         "ref_run": (None, [vp, C.c_uint]),
         "ref_recorded_count": (C.c_int, []),
         "ref_recorded_key": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
@@ -90,7 +117,6 @@ def lib():
     for name, (res, args) in extra.items():
         f = getattr(L, name)
         f.restype, f.argtypes = res, args
-    _lib = L
     return L
 
 
@@ -100,13 +126,19 @@ class RefSim(OracleSim):
     engine: ENGINE_BASIC (Engine, FDTD/engine.cpp), ENGINE_SSE, ENGINE_SSE_COMPRESSED,
     ENGINE_MULTITHREADED (Engine_Multithread, the reference's default)."""
 
-    def __init__(self, x, y, z, grid_delta=1.0, engine=ENGINE_BASIC, threads=1):
+    def __init__(self, x, y, z, grid_delta=1.0, engine=ENGINE_BASIC, threads=1, fast_processing=True):
+        self.engine = engine
         super().__init__(x, y, z, grid_delta)
         self._f.set_engine(self._h, engine, threads)
-        self.engine = engine
+        if engine == ENGINE_CUDA:
+            self._f.set_fast_processing(self._h, int(fast_processing))
 
     def _functions(self):
-        return _Namespace(lib(), "ref_")
+        # ENGINE_CUDA: the reference's operator and Processing classes around integration/Engine_CUDA + libopenems_b200.so
+        return _Namespace(lib_cuda() if self.engine == ENGINE_CUDA else lib(), "ref_")
+
+    def add_mode_match(self, name, start, stop, field_type, func_P, func_PP, ny):
+        return self._f.add_mode_match(self._h, name.encode(), _d3(*start), _d3(*stop), field_type, func_P.encode(), func_PP.encode(), ny)
 
     # fields are snapshots here (the reference engines keep their own layouts)
     def set_field(self, is_curr, n, x, y, z, value):
@@ -169,9 +201,9 @@ class RefSim(OracleSim):
         self._f.run(self._h, nr_ts)
 
 
-def recorded():
+def recorded(cuda=False):
     """datasets the reference's HDF5/VTK writers were asked to write: {key: ndarray}"""
-    L = lib()
+    L = lib_cuda() if cuda else lib()
     out = {}
     buf = C.create_string_buffer(1024)
     for i in range(L.ref_recorded_count()):
@@ -185,8 +217,8 @@ def recorded():
     return out
 
 
-def recorded_clear():
-    lib().ref_recorded_clear()
+def recorded_clear(cuda=False):
+    (lib_cuda() if cuda else lib()).ref_recorded_clear()
 
 
 def read_probe_file(path):

@@ -52,6 +52,7 @@
 #include "operator_cuda.h"
 #include "engine_cuda.h"
 #include "engine_interface_cuda_fdtd.h"
+#include "processing_cuda.h"
 #endif
 
 struct ref_rlc_raw {
@@ -70,6 +71,7 @@ struct ref_sim {
 	Engine_Interface_FDTD* eif;
 	ProcessingArray* PA;
 	int engine_kind, threads;
+	int fast_processing;   // with the CUDA engine: use the Process*_CUDA classes (integration/processing_cuda.h) instead of the stock ones
 	unsigned N[3];
 	std::vector<double> lines[3];
 	int bc[6];
@@ -141,7 +143,7 @@ ref_sim* ref_create(const unsigned nlines[3], const double* x, const double* y, 
 	s->csx->GetGrid()->SetDeltaUnit(grid_delta);
 	s->exc = new Excitation();
 	s->op = NULL; s->eng = NULL; s->eif = NULL; s->PA = NULL;
-	s->engine_kind = 0; s->threads = 1;
+	s->engine_kind = 0; s->threads = 1; s->fast_processing = 1;
 	for (int n = 0; n < 6; ++n) { s->bc[n] = 0; s->pml[n] = 8; s->mur_v[n] = -1; }
 	s->forced_dT = 0; s->ts_factor = 1; s->cell_constant_material = 0;
 	s->built = false;
@@ -167,6 +169,15 @@ void ref_destroy(ref_sim* s)
 
 /* 0 basic (Engine), 1 sse (Engine_sse), 2 sse-compressed, 3 multithreaded (openems.cpp:224-251,738-753), 4 cuda */
 void ref_set_engine(ref_sim* s, int kind, int threads) { s->engine_kind = kind; s->threads = threads; }
+void ref_set_fast_processing(ref_sim* s, int on) { s->fast_processing = on; }
+int ref_has_cuda(void)
+{
+#ifdef REF_WITH_CUDA
+	return 1;
+#else
+	return 0;
+#endif
+}
 
 void ref_set_bc(ref_sim* s, const int bc[6], const unsigned pml_size[6])
 {
@@ -584,6 +595,11 @@ static float* snapshot(ref_sim* s, bool curr)
 {
 	std::vector<float>& b = curr ? s->buf_curr : s->buf_volt;
 	b.resize(3 * ncell(s));
+#ifdef REF_WITH_CUDA
+	if (Engine_CUDA* ec = dynamic_cast<Engine_CUDA*>(s->eng)) {   // one bulk copy instead of 3N per-cell GetVolt round trips
+		if (oems_cuda_get_fields(ec->GetHandle(), curr ? 1 : 0, b.data()) == 0) return b.data();
+	}
+#endif
 	size_t p = 0;
 	for (unsigned n = 0; n < 3; ++n)
 		for (unsigned i = 0; i < s->N[0]; ++i)
@@ -733,7 +749,13 @@ int ref_add_probe(ref_sim* s, int kind, const char* name, const double start[3],
 	ProcessIntegral* p = NULL;
 	switch (kind) {
 	case 0: p = new ProcessVoltage(new_eif(s)); break;
-	case 1: { ProcessCurrent* c = new ProcessCurrent(new_eif(s)); c->SetDualMesh(true); p = c; break; }
+	case 1: {
+		ProcessCurrent* c = NULL;
+#ifdef REF_WITH_CUDA
+		if (s->engine_kind == 4 && s->fast_processing) c = new ProcessCurrent_CUDA(new_eif(s));
+#endif
+		if (!c) c = new ProcessCurrent(new_eif(s));
+		c->SetDualMesh(true); p = c; break; }
 	case 2: p = new ProcessFieldProbe(new_eif(s), 0); break;
 	case 3: { ProcessFieldProbe* f = new ProcessFieldProbe(new_eif(s), 1); f->SetDualMesh(true); p = f; break; }
 	default: return -1;
@@ -752,8 +774,13 @@ int ref_add_probe(ref_sim* s, int kind, const char* name, const double start[3],
 /* field dump box, dump_type 0 E 1 H, file_type 0 vtk 1 hdf5 (recorded in memory, see ref_glue.cpp), interp 0/1/2 */
 int ref_add_dump(ref_sim* s, const char* name, const double start[3], const double stop[3], int dump_type, int file_type, int interp, unsigned interval)
 {
-	ProcessFieldsTD* p = new ProcessFieldsTD(new_eif(s));
+	ProcessFieldsTD* p = NULL;
+#ifdef REF_WITH_CUDA
+	if (s->engine_kind == 4 && s->fast_processing) p = new ProcessFieldsTD_CUDA(new_eif(s));
+#endif
+	if (!p) p = new ProcessFieldsTD(new_eif(s));
 	p->SetProcessInterval(interval ? interval : s->exc->GetNyquistNum() / 4);
+	if (dump_type == 1) { p->SetDualTime(true); p->SetDualMesh(true); }   // openems.cpp:631-636
 	p->SetDumpType((ProcessFields::DumpType)dump_type);
 	p->SetDumpMode((Engine_Interface_Base::InterpolationType)interp);
 	p->SetFileType(file_type ? ProcessFields::HDF5_FILETYPE : ProcessFields::VTK_FILETYPE);
@@ -766,8 +793,13 @@ int ref_add_dump(ref_sim* s, const char* name, const double start[3], const doub
 }
 int ref_add_fd_dump(ref_sim* s, const char* name, const double start[3], const double stop[3], int dump_type, int interp, unsigned nfreq, const double* freqs)
 {
-	ProcessFieldsFD* p = new ProcessFieldsFD(new_eif(s));
+	ProcessFieldsFD* p = NULL;
+#ifdef REF_WITH_CUDA
+	if (s->engine_kind == 4 && s->fast_processing) p = new ProcessFieldsFD_CUDA(new_eif(s));
+#endif
+	if (!p) p = new ProcessFieldsFD(new_eif(s));
 	p->SetProcessInterval(s->exc->GetNyquistNum() / 4);
+	if (dump_type == 1) { p->SetDualTime(true); p->SetDualMesh(true); }
 	p->SetDumpType((ProcessFields::DumpType)dump_type);
 	p->SetDumpMode((Engine_Interface_Base::InterpolationType)interp);
 	p->SetFileType(ProcessFields::HDF5_FILETYPE);
@@ -779,6 +811,27 @@ int ref_add_fd_dump(ref_sim* s, const char* name, const double start[3], const d
 	s->PA->AddProcessing(p);
 	return (int)s->PA->GetNumberOfProcessings() - 1;
 }
+/* waveguide-port mode matching (openems.cpp:548-556): field_type 0 E / 1 H, mode functions of the two tangential
+   directions in fparser syntax over x,y,z,rho,a,r,t */
+int ref_add_mode_match(ref_sim* s, const char* name, const double start[3], const double stop[3], int field_type, const char* func_P, const char* func_PP, int ny)
+{
+	ProcessModeMatch* p = NULL;
+#ifdef REF_WITH_CUDA
+	if (s->engine_kind == 4 && s->fast_processing) p = new ProcessModeMatch_CUDA(new_eif(s));
+#endif
+	if (!p) p = new ProcessModeMatch(new_eif(s));
+	p->SetFieldType(field_type);
+	p->SetModeFunction((ny + 1) % 3, func_P);
+	p->SetModeFunction((ny + 2) % 3, func_PP);
+	if (field_type == 1) { p->SetDualTime(true); }
+	p->SetProcessInterval(s->exc->GetNyquistNum() / 4);
+	p->SetName(name);
+	double a[3] = { start[0], start[1], start[2] }, b[3] = { stop[0], stop[1], stop[2] };
+	p->DefineStartStopCoord(a, b);
+	s->PA->AddProcessing(p);
+	return (int)s->PA->GetNumberOfProcessings() - 1;
+}
+
 /* openEMS::RunFDTD main loop without the energy end criterion: IterateTS in steps of PA->Process() */
 void ref_run(ref_sim* s, unsigned nr_ts)
 {

@@ -63,9 +63,14 @@ def test_slabs_one_pass_and_two_pass(fused):
     run_slabs(s, [0, 15, 30], [0, 0], steps=(1, 3, 50), fused=fused)
 
 
-def test_two_gpus():
+@pytest.mark.parametrize("fused", [0, 1])
+def test_two_gpus(fused):
+    """two engines on two real GPUs in one process (peer access, no IPC): both schedules, the one-pass one with
+    its ping-pong ghost-plane targets and the per-device shared-memory opt-in of the TMA kernel"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     s = cases.uniform_box(n=(40, 36, 44), bc=(BC_PML,) * 6, pml=8)
-    run_slabs(s, [0, 22, 44], [0, 1], steps=(1, 5, 80))
+    engines = run_slabs(s, [0, 22, 44], [0, 1], steps=(1, 5, 80), fused=fused)
+    if fused:
+        assert all(e.GetOption("tma") == 1 for e in engines)
