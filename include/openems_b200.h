@@ -28,6 +28,12 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+/* The library is built with -fvisibility=hidden: only the C entry points declared here are exported.  Its internal
+   C++ classes (one of them is called Engine, like FDTD/engine.h's) must never be visible to, or be interposed by,
+   the host application's symbols. */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 typedef struct oems_cuda_engine oems_cuda_engine;
 
@@ -289,6 +295,9 @@ int oems_cuda_open_peers(oems_cuda_engine* h, const unsigned char* lower /*OEMS_
 /* same-process variant (tests, or one process driving several GPUs) */
 int oems_cuda_link_peers(oems_cuda_engine* h, oems_cuda_engine* lower, oems_cuda_engine* upper);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -14,8 +14,10 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     # parity contract: no FMA contraction, flush denormals, IEEE div/sqrt
     "-fmad=false", "-ftz=true", "-prec-div=true", "-prec-sqrt=true",
-    "-Xcompiler", "-fPIC,-fopenmp,-O2,-ffp-contract=off",
-    "-shared", "-lgomp",
+    # hidden visibility + -Bsymbolic: only the extern "C" API is exported and the library's own C++ symbols (class
+    # Engine ...) can neither clash with nor be interposed by the host application's (openEMS has an Engine too)
+    "-Xcompiler", "-fPIC,-fopenmp,-O2,-ffp-contract=off,-fvisibility=hidden",
+    "-shared", "-lgomp", "-Xlinker", "-Bsymbolic",
 ]
 
 

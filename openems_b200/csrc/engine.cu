@@ -1888,6 +1888,7 @@ int Engine::add_probe_voltage(const unsigned start[3], const unsigned stop[3], i
 		}
 	}
 	if (id) *id = (int)h_probes.size();
+	n_values += P.kind >= 2 ? 3 : 1; // num_probe_values() is the slot of the next probe even before the device lists are rebuilt
 	h_probes.push_back(std::move(P));
 	return 0;
 }
@@ -1926,6 +1927,7 @@ int Engine::add_probe_current(const unsigned start[3], const unsigned stop[3], i
 		break;
 	}
 	if (id) *id = (int)h_probes.size();
+	n_values += P.kind >= 2 ? 3 : 1; // num_probe_values() is the slot of the next probe even before the device lists are rebuilt
 	h_probes.push_back(std::move(P));
 	return 0;
 }
@@ -1941,6 +1943,7 @@ int Engine::add_probe_field(int is_H, const unsigned pos[3], int* id)
 	if (owned(pos[2]))
 		for (int n = 0; n < 3; ++n) { P.off.push_back(n * comp + cell_off(pos[0], pos[1], pos[2])); P.sign.push_back(1); }
 	if (id) *id = (int)h_probes.size();
+	n_values += P.kind >= 2 ? 3 : 1; // num_probe_values() is the slot of the next probe even before the device lists are rebuilt
 	h_probes.push_back(std::move(P));
 	return 0;
 }

@@ -15,6 +15,12 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+/* The library is built with -fvisibility=hidden: only the C entry points declared here are exported.  Its internal
+   C++ classes (one of them is called Engine, like FDTD/engine.h's) must never be visible to, or be interposed by,
+   the host application's symbols. */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 typedef struct oems_synth oems_synth;
 
@@ -68,6 +74,9 @@ int oems_synth_upload(const oems_synth* s, oems_cuda_engine* eng);
 /* page-lock the index buffer (needs a CUDA device); engine uploads then run at the PCIe rate */
 int oems_synth_pin(oems_synth* s);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -126,8 +126,9 @@ class RefSim(OracleSim):
     engine: ENGINE_BASIC (Engine, FDTD/engine.cpp), ENGINE_SSE, ENGINE_SSE_COMPRESSED,
     ENGINE_MULTITHREADED (Engine_Multithread, the reference's default)."""
 
-    def __init__(self, x, y, z, grid_delta=1.0, engine=ENGINE_BASIC, threads=1, fast_processing=True):
+    def __init__(self, x, y, z, grid_delta=1.0, engine=ENGINE_BASIC, threads=1, fast_processing=True, cuda_lib=False):
         self.engine = engine
+        self.cuda_lib = bool(cuda_lib) or engine == ENGINE_CUDA   # which of the two harness libraries serves this sim
         super().__init__(x, y, z, grid_delta)
         self._f.set_engine(self._h, engine, threads)
         if engine == ENGINE_CUDA:
@@ -135,7 +136,7 @@ class RefSim(OracleSim):
 
     def _functions(self):
         # ENGINE_CUDA: the reference's operator and Processing classes around integration/Engine_CUDA + libopenems_b200.so
-        return _Namespace(lib_cuda() if self.engine == ENGINE_CUDA else lib(), "ref_")
+        return _Namespace(lib_cuda() if self.cuda_lib else lib(), "ref_")
 
     def add_mode_match(self, name, start, stop, field_type, func_P, func_PP, ny):
         return self._f.add_mode_match(self._h, name.encode(), _d3(*start), _d3(*stop), field_type, func_P.encode(), func_PP.encode(), ny)

@@ -46,6 +46,11 @@
 #include "CSPrimBox.h"
 
 #include <cstring>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+#include <cstdio>
+#include <cstdlib>
 #include <complex>
 
 #ifdef REF_WITH_CUDA
@@ -127,11 +132,21 @@ static EngExt* find_eng_ext(const ref_sim* s, const Operator_Extension* op_ext)
 	return NULL;
 }
 
+static void segv_backtrace(int sig)
+{
+	void* frames[64];
+	int n = backtrace(frames, 64);
+	backtrace_symbols_fd(frames, n, 2);
+	signal(sig, SIG_DFL);
+	raise(sig);
+}
+
 extern "C" {
 
 ref_sim* ref_create(const unsigned nlines[3], const double* x, const double* y, const double* z, double grid_delta)
 {
 	if (nlines[0] < 3 || nlines[1] < 3 || nlines[2] < 3) return NULL;
+	if (getenv("REF_DEBUG")) signal(SIGSEGV, segv_backtrace);
 	ref_sim* s = new ref_sim();
 	s->csx = new ContinuousStructure();
 	const double* l[3] = { x, y, z };
@@ -156,15 +171,25 @@ ref_sim* ref_create(const unsigned nlines[3], const double* x, const double* y, 
 void ref_destroy(ref_sim* s)
 {
 	if (!s) return;
-	for (size_t i = 0; i < s->procs.size(); ++i) delete s->procs[i];
+	const bool dbg = getenv("REF_DEBUG") != NULL;
+#define DBG(msg) do { if (dbg) { fprintf(stderr, "ref_destroy: %s\n", msg); fflush(stderr); } } while (0)
+	DBG("processings");
+	if (s->PA) s->PA->DeleteAll();
 	delete s->PA;
+	DBG("engine interface");
 	delete s->eif;
 	// openEMS deletes the engine before the operator (openems.cpp:99-113)
+	DBG("engine");
 	delete s->eng;
+	DBG("operator");
 	delete s->op;
+	DBG("excitation");
 	delete s->exc;
+	DBG("csx");
 	delete s->csx;
+	DBG("done");
 	delete s;
+#undef DBG
 }
 
 /* 0 basic (Engine), 1 sse (Engine_sse), 2 sse-compressed, 3 multithreaded (openems.cpp:224-251,738-753), 4 cuda */

@@ -115,6 +115,36 @@ def test_field_dump(is_H, interp):
     assert np.array_equal(sub, ref[:, pz][:, :, py][:, :, :, px])
 
 
+def test_async_dump_does_not_stall_and_matches():
+    """oems_cuda_read_dump_async / oems_cuda_wait: the dump captures the fields of the timestep it was issued at; the
+    engine steps on while the copy is in flight, a second dump of the same box queues behind the first"""
+    s = cases.uniform_box(n=(30, 26, 28), bc=(BC_PML, BC_PML, BC_MUR, BC_MUR, BC_PEC, BC_PML), pml=5)
+    eng = operator_from_oracle(s).CreateEngine()
+    start, stop = (3, 2, 1), (26, 23, 25)
+    el = [[s.edge_length(n, [p if a == n else 0 for a in range(3)], False) for p in range(s.N[n])] for n in range(3)]
+    dl = [[s.edge_length(n, [p if a == n else 0 for a in range(3)], True) for p in range(s.N[n])] for n in range(3)]
+    d = eng.AddDump(0, 2, np.arange(start[0], stop[0] + 1), np.arange(start[1], stop[1] + 1), np.arange(start[2], stop[2] + 1), el, dl)
+    s.iterate(40)
+    eng.IterateTS(40)
+    ref40 = s.dump_field(0, 2, start, stop)
+    t = eng.ReadDumpAsync(d)
+    eng.IterateTS(25)             # enqueued behind the dump kernel, overlapping its copy
+    got40 = eng.WaitDump(t)
+    assert np.abs(ref40).max() > 0 and np.array_equal(got40.view(np.uint32), ref40.view(np.uint32))
+    s.iterate(25)
+    t1 = eng.ReadDumpAsync(d)
+    eng.IterateTS(10)
+    s.iterate(10)
+    ref65 = s.dump_field(0, 2, start, stop)  # oracle is now at 75; recompute the 65 reference from a fresh run below
+    got65 = eng.WaitDump(t1)
+    s2 = cases.uniform_box(n=(30, 26, 28), bc=(BC_PML, BC_PML, BC_MUR, BC_MUR, BC_PEC, BC_PML), pml=5)
+    s2.iterate(65)
+    assert np.array_equal(got65.view(np.uint32), s2.dump_field(0, 2, start, stop).view(np.uint32))
+    assert not np.array_equal(got65, ref65)
+    assert np.array_equal(eng.ReadDump(d).view(np.uint32), ref65.view(np.uint32))
+    assert_fields_equal(eng, s, "after async dumps")
+
+
 def test_lorentz_drude_block():
     """config C4 in small: Drude eps+mue block (f_p 5 GHz, tau 5 ns) and a 2-pole Lorentz block"""
     n = (34, 30, 38)
