@@ -83,8 +83,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_c5(n, with_probes=True, slab=None, device=-1):
-    """host side: build the compressed operator of the C5 mesh and create the engine"""
+def build_c5(n, slab=None, reduce_min=None):
+    """host side: build the compressed operator of the C5 mesh.  With a slab (one process per GPU) only the planes
+    the rank holds are built; the ranks agree on the timestep through `reduce_min` (a MIN all-reduce of a float)"""
     from openems_b200 import SyntheticOperator
     from openems_b200.synthetic import BC_PML, EXC_E_SOFT
     C0 = 299792458.0
@@ -97,6 +98,9 @@ def build_c5(n, with_probes=True, slab=None, device=-1):
     c = (nx // 2, ny // 2, nz // 2)
     so.add_excitation((c[0], c[1], c[2] + 0.5), (c[0], c[1], c[2] + 0.5), EXC_E_SOFT, (0, 0, 1))
     t0 = time.time()
+    if slab is not None:
+        so.set_slab(*slab)
+        so.set_timestep(reduce_min(so.local_timestep()))
     so.build()
     t_build = time.time() - t0
     return so, t_build
@@ -135,26 +139,62 @@ def algorithmic_bytes(n, pml_cells, index_bytes, one_pass=False):
     return per_half, 2 * per_half
 
 
-def cpu_baseline(sample_n, steps, threads):
-    """the reference algorithm restated (oracle/fdtd_oracle_sse.c: sse-compressed layout, x-slab
-    threads, one barrier per phase) on a bounded sample of the same workload"""
+class quiet_stdout:
+    """the reference prints banners to stdout (\"Create FDTD operator\" ...): route fd 1 to stderr meanwhile, the bench
+    line must be the only thing on stdout"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def cpu_baseline(sample_n, steps, threads, warm=3):
+    with quiet_stdout():
+        return _cpu_baseline(sample_n, steps, threads, warm)
+
+
+def _cpu_baseline(sample_n, steps, threads, warm=3):
+    """the reference's CPU engine on a bounded sample of the same workload (same BC, source, timestep rule).
+    kind "reference": oracle/_ref/libopenems_ref.so = the UNMODIFIED reference translation units (operator build,
+    Engine_Multithread -- the reference's default engine --, UPML extension) compiled by oracle/Makefile.ref, run with
+    `threads` threads.  Fallback kind "port": the sse-compressed multithreaded restatement (oracle/fdtd_oracle_sse.c).
+    -> (MCells/s, seconds, kind, description)"""
     from oracle.pyoracle import OracleSim, OracleSSE, BC_PML, EXC_E_SOFT
     C0 = 299792458.0
     lines = tuple(np.arange(m, dtype=np.float64) for m in sample_n)
-    s = OracleSim(*lines, 1e-3)
+    kind, s = "port", None
+    try:
+        from oracle import pyref
+        if pyref.available():
+            s = pyref.RefSim(*lines, 1e-3, engine=pyref.ENGINE_MULTITHREADED, threads=threads)
+            kind = "reference"
+    except Exception:
+        s = None
+    if s is None:
+        s = OracleSim(*lines, 1e-3)
     s.set_bc([BC_PML] * 6, (PML,) * 6)
     fc = C0 / (20 * 1e-3)
     s.set_excite_gauss(fc / 2, fc / 2)
     c = tuple(m // 2 for m in sample_n)
     s.add_excitation((c[0], c[1], c[2] + 0.5), (c[0], c[1], c[2] + 0.5), EXC_E_SOFT, (0, 0, 1))
+    t0 = time.time()
     s.build()
-    eng = OracleSSE(s, threads=threads)
-    eng.iterate(3)
+    t_build = time.time() - t0
+    eng = s if kind == "reference" else OracleSSE(s, threads=threads)
+    eng.iterate(warm)
     t0 = time.time()
     eng.iterate(steps)
     dt = time.time() - t0
     cells = sample_n[0] * sample_n[1] * sample_n[2]
-    return cells * steps / dt / 1e6, dt
+    what = ("unmodified reference (oracle/_ref: Operator_Multithread + Engine_Multithread, %d threads)" % threads) if kind == "reference" \
+        else ("sse-compressed multithreaded restatement (oracle/fdtd_oracle_sse.c, %d threads)" % threads)
+    return cells * steps / dt / 1e6, dt, kind, what + ", operator build %.1f s" % t_build
 
 
 def run_reference(args):
@@ -165,21 +205,69 @@ def run_reference(args):
     sample = tuple(args.cpu_sample)
     # each "step" of this arm = one timestep on the bounded sample mesh
     steps = max(1, min(args.steps, 400))
-    cpu_baseline(sample, max(1, args.warmup), threads)
-    val, dt = cpu_baseline(sample, steps, threads)
+    val, dt, kind, what = cpu_baseline(sample, steps, threads, warm=max(1, args.warmup))
     n = tuple(args.n)
+    try:
+        import psutil
+        ram_gb = round(psutil.virtual_memory().total / 2 ** 30, 1)
+    except Exception:
+        ram_gb = None
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C5 uniform vacuum %dx%dx%d PML_8x6 centre Ez Gauss source, 12 probes" % n,
-                   "timed_on": "bounded sample %dx%dx%d of the same workload (same BC, source, dT), all host cores" % sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%dx%dx%d PML_8 mesh, %d timesteps, sse-compressed multithreaded restatement "
-                                   "(oracle/fdtd_oracle_sse.c)" % (sample + (steps,))},
+                   "timed_on": "bounded sample %dx%dx%d of the same workload (same BC, source, timestep rule), all host cores; "
+                               "the reference's own operator build of the full 1024^3 mesh needs ~150 B/cell of host memory and "
+                               "tens of minutes (single-threaded parts), so the headline size is not run on the CPU: "
+                               "same_config is false by construction, MCells/s is per cell" % sample,
+                   "host_ram_gb": ram_gb},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": "%dx%dx%d PML_8 mesh, %d timesteps; %s" % (sample + (steps, what))},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
+
+
+def parity_check(world, rank, local_rank, dist, reduce_min, reduce_sum_u64):
+    """the timed path on a small mesh, in this very run: N>1: z-slab engines in N processes (CUDA-IPC halos) against ONE
+    single-GPU engine of the same mesh on rank 0; N=1: the one-pass schedule against the two-pass schedule.  Both
+    sides start from the same deterministic pre-fill and must end with identical E/H digests.  (That the single-GPU
+    engine equals the reference bit for bit is what tests/ establish.)"""
+    from openems_b200.slabs import slab_range
+    n = (192, 160, max(64, 48 * world))
+    steps = 24
+    slab = slab_range(n[2], world, rank, pml_lo=PML, pml_hi=PML, pml_weight=2.4) if world > 1 else None
+    so, _ = build_c5(n, slab=slab, reduce_min=reduce_min)
+    eng = so.operator().CreateEngine(device=local_rank, slab=slab)
+    eng.SetOption("fused", 1)
+    if world > 1:
+        blobs = [None] * world
+        dist.all_gather_object(blobs, eng.ExportIPC())
+        eng.OpenPeers(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
+        dist.barrier()
+    one_pass = bool(eng.GetOption("fused"))
+    eng.FillFields(7)
+    eng.IterateTS(steps)
+    eng.Synchronize()
+    got = reduce_sum_u64(eng.FieldDigest())
+    eng.close()
+    if world > 1:
+        dist.barrier()
+    want = None
+    if rank == 0:
+        so1, _ = build_c5(n)
+        ref = so1.operator().CreateEngine(device=local_rank)
+        ref.SetOption("fused", 1 if world > 1 else 0)
+        ref.FillFields(7)
+        ref.IterateTS(steps)
+        want = list(ref.FieldDigest())
+        ref.close()
+    return {"mesh": "%dx%dx%d PML_8" % n, "timesteps": steps,
+            "compared": ("%d z-slab processes (CUDA-IPC halos, %s schedule) vs one single-GPU engine" % (world, "one-pass" if one_pass else "two-pass"))
+            if world > 1 else "one-pass schedule vs two-pass schedule, single GPU",
+            "digest_E": "%016x" % got[0], "digest_H": "%016x" % got[1],
+            "equal": None if want is None else bool(want == list(got))}
 
 
 def run_gpu(args):
@@ -215,7 +303,21 @@ def run_gpu(args):
         from openems_b200.slabs import slab_range
         slab = slab_range(nz, world, rank, pml_lo=PML, pml_hi=PML, pml_weight=2.4)
 
-    so, t_build = build_c5(n)
+    def reduce_min(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
+    def reduce_sum_u64(vals):
+        """sum mod 2^64 over the ranks (digests of slab engines add up to the single-GPU digest)"""
+        if world == 1:
+            return list(vals)
+        parts = [None] * world
+        dist.all_gather_object(parts, list(vals))
+        return [sum(p[i] for p in parts) % (1 << 64) for i in range(len(vals))]
+
+    # every rank builds only the planes it holds (the ranks agree on the timestep by a MIN reduction)
+    so, t_build = build_c5(n, slab=slab, reduce_min=reduce_min if world > 1 else None)
     op = so.operator()
 
     # ---------------- e2e leg: engine creation from HOST buffers + K timesteps with probe readback
@@ -241,13 +343,18 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # ---------------- parity gate of this run: the path that is timed below, on a small mesh
+    parity = parity_check(world, rank, local_rank, dist, reduce_min if world > 1 else None, reduce_sum_u64)
+
     eng = make_engine()
     link(eng)
     stats0 = eng.GetStats()
     pml_cells = stats0["pml_cells"]
     index_bytes = stats0["index_bytes"]
 
-    # ---------------- device-resident leg
+    # ---------------- device-resident leg: the timed window starts from a FILLED domain (deterministic pre-fill,
+    # a function of the global cell index: the same state at every N), not from the zeros a point source leaves
+    eng.FillFields(0)
     eng.IterateTS(args.warmup)
     eng.Synchronize()
     barrier()
@@ -260,6 +367,9 @@ def run_gpu(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.GetStats()["kernels_launched"] - k0
+    # digest of E and H after warmup + K timesteps: identical for every N (z-slab digests add up)
+    dig = reduce_sum_u64(eng.FieldDigest())
+    energy_after = eng.CalcFastEnergy() if world == 1 else None
     if world > 1:
         t = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -310,7 +420,12 @@ def run_gpu(args):
     # bytes copied host->device while creating the engine: coefficient tuples + the operator index as the host
     # builder holds it -- unique xy planes and one plane id per z, expanded on the device
     # (oems_cuda_set_operator_planes) -- per rank (+ a few KB of signal / excitation / probe lists, ignored)
-    h2d = (so.n_unique * 128 + so.unique_planes * n[0] * n[1] * index_bytes + n[2] * 4) * world
+    # counted by the engine at its copy calls (option "h2d_bytes"), summed over the ranks
+    h2d = eng.GetOption("h2d_bytes")
+    if world > 1:
+        t = torch.tensor([h2d], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        h2d = int(t.item())
     done, d2h = 0, 0
     while done < args.steps:
         m = min(burst, args.steps - done)
@@ -346,15 +461,18 @@ def run_gpu(args):
                                 "probe read-back" % (t_upload, args.steps, burst), "probe_sample": probe_sample},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "parity_check": dict(parity, full_size_digest={"timesteps": args.warmup + args.steps, "prefill_seed": 0,
+                                                           "E": "%016x" % dig[0], "H": "%016x" % dig[1],
+                                                           "note": "same value at every N for the same --warmup/--steps (bit-exact slabs)"}),
         }
+        if energy_after is not None:
+            out["parity_check"]["full_size_digest"]["energy_estimate_J"] = energy_after
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             sample = tuple(args.cpu_sample)
-            v, dt = cpu_baseline(sample, args.cpu_steps, threads)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                   "sample": "%dx%dx%d PML_8 mesh, %d timesteps in %.1f s, sse-compressed multithreaded "
-                                             "restatement of the reference engine (oracle/fdtd_oracle_sse.c)"
-                                             % (sample + (args.cpu_steps, dt))}
+            v, dt, kind, what = cpu_baseline(sample, args.cpu_steps, threads)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                                   "sample": "%dx%dx%d PML_8 mesh, %d timesteps in %.1f s; %s" % (sample + (args.cpu_steps, dt, what))}
         print(json.dumps(out))
     eng.close()
     if world > 1:
@@ -369,12 +487,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, nargs=3, default=[1024, 1024, 1024], help="mesh lines (default: the 1024^3 headline config)")
-    ap.add_argument("--cpu-sample", type=int, nargs=3, default=[256, 256, 256])
-    ap.add_argument("--cpu-steps", type=int, default=300)
+    ap.add_argument("--cpu-sample", type=int, nargs=3, default=None,
+                    help="bounded sample mesh of the CPU arm (default 192^3 inside the GPU line, 256^3 for --impl reference)")
+    ap.add_argument("--cpu-steps", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.cpu_sample is None:
+        args.cpu_sample = [256, 256, 256] if args.impl == "reference" else [192, 192, 192]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -190,6 +190,14 @@ int oems_cuda_read_probe_series(oems_cuda_engine* h, double* out, unsigned* ts_o
 /* Engine_Interface_FDTD::CalcFastEnergy (engine_interface_fdtd.cpp:302-347) */
 int oems_cuda_energy(oems_cuda_engine* h, double* energy);
 
+/* Measurement aids (bench.py).  oems_cuda_fill_fields: deterministic pre-fill of E and H of the held
+   planes, a function of the global cell index and the seed only ((hash mod 2^16 - 2^15) * 1e-6; H scaled by 1/Z0,
+   zero on the last line of each direction), so that a timed window does not run on an all-zero domain.
+   oems_cuda_field_digest: order-independent 64-bit digest (sum mod 2^64 over the OWNED cells of a hash of global
+   index and bit pattern): the digests of z-slab engines add up to the single-GPU digest of the same state. */
+int oems_cuda_fill_fields(oems_cuda_engine* h, unsigned long long seed);
+int oems_cuda_field_digest(oems_cuda_engine* h, int is_curr, unsigned long long* out);
+
 /* ProcessFields::CalcField box dump (Common/processfields.cpp:283-409) with the
    NO/NODE/CELL interpolation of engine_interface_fdtd.cpp:63-124,150-204, gathered and
    interpolated on the device.  px/py/pz are the posLines index lists; edge_len[n] /

@@ -73,6 +73,8 @@ SIGNATURES = {
     "oems_cuda_add_dump": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, _up, _up, _up,
                                      C.POINTER(_dp), C.POINTER(_dp), _ip]),
     "oems_cuda_read_dump": (C.c_int, [_vp, C.c_int, _fp]),
+    "oems_cuda_fill_fields": (C.c_int, [_vp, C.c_ulonglong]),
+    "oems_cuda_field_digest": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_ulonglong)]),
     "oems_cuda_read_dump_async": (C.c_int, [_vp, C.c_int, C.c_void_p, C.POINTER(C.c_longlong)]),
     "oems_cuda_wait": (C.c_int, [_vp, C.c_longlong]),
     "oems_cuda_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -109,6 +111,8 @@ SIGNATURES = {
     "oems_synth_set_excite_gauss": (None, [_vp, C.c_double, C.c_double]),
     "oems_synth_set_excite_sinus": (None, [_vp, C.c_double]),
     "oems_synth_build": (C.c_int, [_vp, C.c_uint]),
+    "oems_synth_set_slab": (C.c_int, [_vp, C.c_uint, C.c_uint]),
+    "oems_synth_local_timestep": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "oems_synth_last_error": (C.c_char_p, [_vp]),
     "oems_synth_dT": (C.c_double, [_vp]),
     "oems_synth_nyquist": (C.c_uint, [_vp]),

@@ -36,7 +36,10 @@ template <typename T> T* Engine::dalloc(size_t n, bool zero)
 template <typename T> T* Engine::upload(const std::vector<T>& v)
 {
 	T* p = dalloc<T>(v.size(), v.empty());
-	if (p && !v.empty()) cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream);
+	if (p && !v.empty()) {
+		cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream);
+		h2d_bytes += v.size() * sizeof(T);
+	}
 	return p;
 }
 
@@ -148,6 +151,7 @@ int Engine::set_operator_planes(unsigned nu, const oems_coeff_entry* table, unsi
 	CK(cudaMalloc((void**)&d_pz, gn[2] * sizeof(unsigned)));
 	CK(cudaMemcpyAsync(d_up, uplanes, np * n_uplanes * ib, cudaMemcpyHostToDevice, stream));
 	CK(cudaMemcpyAsync(d_pz, plane_of_z, gn[2] * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
+	h2d_bytes += np * n_uplanes * ib + gn[2] * sizeof(unsigned);
 	const long long rows = (long long)gn[1] * nzl, n = rows * pitch;
 	const unsigned blocks = (unsigned)((n + 255) / 256);
 	if (ib == 2) k_expand_planes<uint16_t><<<blocks, 256, 0, stream>>>((uint16_t*)p, (const uint16_t*)d_up, d_pz, z0, rows, (int)gn[0], (int)gn[1], pitch, (uint16_t)nu);
@@ -194,6 +198,7 @@ int Engine::set_operator_compressed(unsigned nu, const oems_coeff_entry* table, 
 	const char* src = (const char*)index + (size_t)z0 * gn[1] * gn[0] * ib;
 	cudaPointerAttributes attr;
 	const bool src_pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	h2d_bytes += (size_t)gn[0] * ib * gn[1] * nzl;
 	cudaGetLastError();
 	if (src_pinned) {
 		// page-locked source (oems_synth_pin, cudaHostRegister / cudaMallocHost by the caller): one DMA
@@ -1771,6 +1776,7 @@ int Engine::get_option(const char* key, long long* value)
 	if (k == "fused") { *value = fused_active ? 1 : 0; return 0; }
 	if (k == "tma") { *value = (fused_active && tma_active) ? 1 : 0; return 0; }
 	if (k == "xslab") { *value = fused_active ? (xs_box[0] >= 0) + (xs_box[1] >= 0) : 0; return 0; }
+	if (k == "h2d_bytes") { *value = (long long)h2d_bytes; return 0; } // bytes copied host -> device since oems_cuda_create (counted at the copy calls)
 	return fail("get_option: unknown key " + k);
 }
 
@@ -2039,6 +2045,47 @@ int Engine::energy(double* e)
 	CK(cudaMemcpyAsync(acc, d_energy, sizeof(acc), cudaMemcpyDeviceToHost, stream));
 	CK(cudaStreamSynchronize(stream));
 	*e = 8.85418781762e-12 * acc[0] + 1.256637062e-6 * acc[1];
+	return 0;
+}
+
+// ------------------------------------------------------------------------------ measurement aids
+int Engine::fill_fields(unsigned long long seed)
+{
+	if (!finalized) return fail("fill_fields: engine not finalized");
+	CK(cudaSetDevice(device));
+	FillParams p;
+	p.V = sV[cur()]; p.I = sI[cur()];
+	p.nx = (int)gn[0]; p.ny = (int)gn[1]; p.nzg = (int)gn[2];
+	p.z0 = z0; p.nzl = nzl;
+	p.pitch = pitch; p.plane = plane; p.comp = comp;
+	p.seed = seed;
+	const long long rows = (long long)nzl * gn[1];
+	const unsigned blocks = (unsigned)std::min<long long>((rows + 7) / 8, 148 * 16);
+	k_fill<<<blocks, dim3(32, 8), 0, stream>>>(p);
+	++kernels_launched;
+	CK(cudaStreamSynchronize(stream));
+	return 0;
+}
+
+int Engine::field_digest(int is_curr, unsigned long long* out)
+{
+	if (!finalized) return fail("field_digest: engine not finalized");
+	if (!out) return fail("field_digest: null pointer");
+	CK(cudaSetDevice(device));
+	unsigned long long* d_acc = (unsigned long long*)d_energy; // 16 bytes of scratch
+	DigestParams p;
+	p.X = is_curr ? sI[cur()] : sV[cur()];
+	p.nx = (int)gn[0]; p.ny = (int)gn[1];
+	p.z0 = z0; p.k0 = (int)zb - z0; p.k1 = (int)ze - z0;
+	p.pitch = pitch; p.plane = plane; p.comp = comp;
+	p.acc = d_acc;
+	CK(cudaMemsetAsync(d_acc, 0, sizeof(unsigned long long), stream));
+	const long long rows = (long long)(p.k1 - p.k0) * gn[1];
+	const unsigned blocks = (unsigned)std::min<long long>((rows + 7) / 8, 148 * 16);
+	k_digest<<<blocks, dim3(32, 8), 0, stream>>>(p);
+	++kernels_launched;
+	CK(cudaMemcpyAsync(out, d_acc, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
 	return 0;
 }
 

@@ -127,6 +127,8 @@ public:
 	int record_probes(unsigned interval, unsigned max_samples);
 	int read_probe_series(double* out, unsigned* ts_out, unsigned cap, unsigned* n);
 	int energy(double* e);
+	int fill_fields(unsigned long long seed);
+	int field_digest(int is_curr, unsigned long long* out);
 	int add_dump(int is_H, int interp, unsigned nx, unsigned ny, unsigned nz, const unsigned* px, const unsigned* py,
 	             const unsigned* pz, const double* const el[3], const double* const del[3], int* id);
 	int read_dump(int id, float* out);
@@ -261,6 +263,7 @@ private:
 	FusedTmaParams pFT[2]; // the same with the TMA descriptors of the source set (kernels_fused_tma.cuh)
 	int tma_req = 1;       // option "tma": stage the inputs of the one-pass kernel through TMA
 	bool tma_active = false;
+	size_t h2d_bytes = 0;        // every byte copied host -> device by this engine (uploads), counted where the copy is issued
 	size_t h2d_index_bytes = 0;  // bytes of operator index copied host -> device
 	// UPML boxes updated inside the one-pass kernel ("x slabs", kernels_fused_tma.cuh): index into pE.box, -1 none
 	int xs_box[2] = {-1, -1};

@@ -90,6 +90,29 @@ struct oems_synth {
 	std::vector<uint32_t> uplanes32;
 	int index_bytes = 0;
 	unsigned unique_planes = 0;
+	// z-slab restricted build (one process per GPU): only the planes [slab_lo, slab_hi) this rank holds are built
+	bool slab_set = false;
+	unsigned slab_lo = 0, slab_hi = 0;
+	bool held(unsigned k) const { return !slab_set || (k >= slab_lo && k < slab_hi); }
+	uint32_t cell_id(unsigned k, size_t p2) const
+	{
+		const size_t np = (size_t)N[0] * N[1];
+		return index_bytes == 2 ? uplanes16[(size_t)plane_of_z[k] * np + p2] : uplanes32[(size_t)plane_of_z[k] * np + p2];
+	}
+	void ensure_full_index()
+	{ // the per-cell index [nz][ny][nx]; only materialised for callers that ask for it (oems_synth_index / pin)
+		const size_t np = (size_t)N[0] * N[1];
+		const long long Nz = N[2];
+		if (index_bytes == 2 && idx16.empty()) {
+			idx16.resize(np * Nz);
+#pragma omp parallel for schedule(static)
+			for (long long k = 0; k < Nz; ++k) memcpy(idx16.data() + (size_t)k * np, uplanes16.data() + (size_t)plane_of_z[k] * np, np * 2);
+		} else if (index_bytes == 4 && idx32.empty()) {
+			idx32.resize(np * Nz);
+#pragma omp parallel for schedule(static)
+			for (long long k = 0; k < Nz; ++k) memcpy(idx32.data() + (size_t)k * np, uplanes32.data() + (size_t)plane_of_z[k] * np, np * 4);
+		}
+	}
 	std::vector<unsigned> exc_idx[2][3], exc_dir[2], exc_delay[2];
 	std::vector<float> exc_amp[2];
 	std::vector<MurPlaneH> mur;
@@ -551,6 +574,40 @@ static unsigned calc_nyquist(double fmax, double dT)
 	return (unsigned)std::floor(1 / fmax / 2 / dT);
 }
 
+int oems_synth_set_slab(oems_synth* s, unsigned z_begin, unsigned z_end)
+{
+	if (!s || s->built) return 1;
+	if (z_begin >= z_end || z_end > s->N[2]) { s->err = "set_slab: bad range"; return 1; }
+	s->slab_set = true;
+	s->slab_lo = z_begin > 0 ? z_begin - 1 : 0;            // plus the ghost planes the slab engine holds
+	s->slab_hi = z_end < s->N[2] ? z_end + 1 : s->N[2];
+	return 0;
+}
+
+// Operator::CalcTimestep over the planes of this rank's slab only (all planes without a slab): the ranks take the
+// minimum of these values (one MPI/NCCL/gloo MIN-reduction of a double) and pass it to oems_synth_set_timestep
+int oems_synth_local_timestep(oems_synth* s, double* dT_out)
+{
+	if (!s || !dT_out) return 1;
+	const unsigned Nz = s->N[2];
+	std::map<std::vector<uint64_t>, unsigned> seen;
+	double dT = 1e200;
+	std::map<unsigned, PlaneEC> cache;
+	for (unsigned k = 0; k < Nz; ++k) {
+		if (!s->held(k)) continue;
+		if (!seen.emplace(s->zsig(k), k).second) continue;
+		const int km = oems_synth::refl((int)k - 1, (int)Nz), kp = oems_synth::refl((int)k + 1, (int)Nz);
+		for (int q : {km, (int)k, kp})
+			if (!cache.count((unsigned)q)) s->ec_plane((unsigned)q, cache[(unsigned)q]);
+		const PlaneEC* E[3] = {&cache[(unsigned)km], &cache[k], &cache[(unsigned)kp]};
+		dT = std::min(dT, s->timestep_plane(k, E));
+		for (auto it = cache.begin(); it != cache.end();)
+			it = (it->first + 1 < k) ? cache.erase(it) : std::next(it);
+	}
+	*dT_out = dT;
+	return 0;
+}
+
 int oems_synth_build(oems_synth* s, unsigned max_ts)
 {
 	if (s->built) { s->err = "already built"; return 1; }
@@ -586,17 +643,20 @@ int oems_synth_build(oems_synth* s, unsigned max_ts)
 		if (BC[5] == 3) { start[2] = Nz - 1 - size[5]; stop[2] = Nz - 1; add(); }
 	}
 
-	// ---- group planes by z-signature
+	// ---- group planes by z-signature (with a slab set: only the planes this rank holds; the others map to class 0
+	// and are never looked at by the slab engine)
 	std::map<std::vector<uint64_t>, unsigned> sig2id;
-	std::vector<unsigned> plane_id(Nz), rep; // representative plane of every class
+	std::vector<unsigned> plane_id(Nz, 0), rep; // representative plane of every class
 	for (unsigned k = 0; k < Nz; ++k) {
+		if (!s->held(k)) continue;
 		auto it = sig2id.find(s->zsig(k));
 		if (it == sig2id.end()) { it = sig2id.emplace(s->zsig(k), (unsigned)rep.size()).first; rep.push_back(k); }
 		plane_id[k] = it->second;
 	}
 	s->unique_planes = (unsigned)rep.size();
 
-	// ---- timestep (operator.cpp:994-1025): minimum over the representative planes
+	// ---- timestep (operator.cpp:994-1025): minimum over the representative planes (of this rank's slab: ranks agree
+	// on the global minimum through oems_synth_local_timestep + set_timestep before they build)
 	if (s->forced_dT > 0) s->dT = s->forced_dT;
 	else {
 		double dT = 1e200;
@@ -678,22 +738,14 @@ int oems_synth_build(oems_synth* s, unsigned max_ts)
 	s->index_bytes = (U + 1 <= 65536) ? 2 : 4;
 	s->plane_of_z.assign(plane_id.begin(), plane_id.end());
 	if (s->index_bytes == 2) {
-		s->idx16.resize(np * Nz);
-		std::vector<std::vector<uint16_t>> p16(rep.size());
 		s->uplanes16.resize(np * rep.size());
 		for (size_t r = 0; r < rep.size(); ++r) {
-			p16[r].resize(np);
-			for (size_t p = 0; p < np; ++p) p16[r][p] = (uint16_t)plane_index[r][p];
-			memcpy(s->uplanes16.data() + r * np, p16[r].data(), np * 2);
+			uint16_t* dst = s->uplanes16.data() + r * np;
+			for (size_t p = 0; p < np; ++p) dst[p] = (uint16_t)plane_index[r][p];
 		}
-#pragma omp parallel for schedule(static)
-		for (long long k = 0; k < (long long)Nz; ++k) memcpy(s->idx16.data() + (size_t)k * np, p16[plane_id[k]].data(), np * 2);
 	} else {
-		s->idx32.resize(np * Nz);
 		s->uplanes32.resize(np * rep.size());
 		for (size_t r = 0; r < rep.size(); ++r) memcpy(s->uplanes32.data() + r * np, plane_index[r].data(), np * 4);
-#pragma omp parallel for schedule(static)
-		for (long long k = 0; k < (long long)Nz; ++k) memcpy(s->idx32.data() + (size_t)k * np, plane_index[plane_id[k]].data(), np * 4);
 	}
 
 	// ---- excitation lists: operator_ext_excitation.cpp:143-232, loop order z, y, x
@@ -815,7 +867,7 @@ int oems_synth_build(oems_synth* s, unsigned max_ts)
 						const unsigned pos[3] = {i, j, k};
 						const size_t p2 = (size_t)j * Nx + i;
 						const PlaneEC& E = ecs[k - lo[2]];
-						const uint32_t id = s->index_bytes == 2 ? s->idx16[(size_t)k * np + p2] : s->idx32[(size_t)k * np + p2];
+						const uint32_t id = s->cell_id(k, p2);
 						const oems_coeff_entry& ce = tab[id];
 						bool on = false;
 						double L_D[3], R_D[3], C_L[3], C_D[3], G_D[3], L_L[3], coord[3];
@@ -884,7 +936,12 @@ unsigned oems_synth_nyquist(const oems_synth* s) { return s->nyquist; }
 unsigned oems_synth_n_unique(const oems_synth* s) { return (unsigned)s->table.items.size(); }
 int oems_synth_index_bytes(const oems_synth* s) { return s->index_bytes; }
 const oems_coeff_entry* oems_synth_table(const oems_synth* s) { return s->table.items.data(); }
-const void* oems_synth_index(const oems_synth* s) { return s->index_bytes == 2 ? (const void*)s->idx16.data() : (const void*)s->idx32.data(); }
+const void* oems_synth_index(const oems_synth* cs)
+{
+	oems_synth* s = const_cast<oems_synth*>(cs);
+	s->ensure_full_index();
+	return s->index_bytes == 2 ? (const void*)s->idx16.data() : (const void*)s->idx32.data();
+}
 unsigned oems_synth_unique_planes(const oems_synth* s) { return s->unique_planes; }
 const unsigned* oems_synth_plane_of_z(const oems_synth* s) { return s->plane_of_z.data(); }
 const void* oems_synth_plane_data(const oems_synth* s) { return s->index_bytes == 2 ? (const void*)s->uplanes16.data() : (const void*)s->uplanes32.data(); }
@@ -925,6 +982,7 @@ int oems_synth_pin(oems_synth* s)
 {
 	if (!s || !s->built) return 1;
 	if (s->pinned) return 0;
+	s->ensure_full_index();
 	const size_t bytes = (size_t)s->index_bytes * (s->index_bytes == 2 ? s->idx16.size() : s->idx32.size());
 	if (cudaHostRegister(const_cast<void*>(oems_synth_index(s)), bytes, cudaHostRegisterPortable) != cudaSuccess) {
 		cudaGetLastError();

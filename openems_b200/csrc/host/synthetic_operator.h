@@ -44,6 +44,11 @@ int  oems_synth_add_excitation(oems_synth* s, int prio, const double start[3], c
 void oems_synth_set_excite_gauss(oems_synth* s, double f0, double fc);
 void oems_synth_set_excite_sinus(oems_synth* s, double f0);
 /* builds timestep, compressed operator, extension data; 0 on success */
+/* z-slab restricted build for one-process-per-GPU runs: only the xy planes rank-owned [z_begin, z_end) (+ one ghost
+   plane per side) are built.  The ranks first agree on the timestep: each calls oems_synth_local_timestep (minimum of
+   Operator::CalcTimestep over ITS planes), they MIN-reduce the values and hand the result to oems_synth_set_timestep. */
+int  oems_synth_set_slab(oems_synth* s, unsigned z_begin, unsigned z_end);
+int  oems_synth_local_timestep(oems_synth* s, double* dT_out);
 int  oems_synth_build(oems_synth* s, unsigned max_ts);
 const char* oems_synth_last_error(const oems_synth* s);
 

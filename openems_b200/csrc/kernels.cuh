@@ -764,6 +764,75 @@ __global__ void k_energy(const __grid_constant__ EnergyParams p)
 }
 
 // ---------------------------------------------------------------------------------------
+// Deterministic pre-fill and bit digest of the fields (measurement aids): bench.py starts its timed
+// window from a filled domain instead of the all-zero one a point source leaves after a few steps, and prints a
+// digest of E and H afterwards.  Both are functions of the GLOBAL cell index only, so z-slab engines fill the same
+// values (ghost planes included) and the sum of the per-slab digests equals the single-GPU digest.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+	x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+	return x;
+}
+struct FillParams {
+	float* V; float* I;
+	int nx, ny, nzg;      // global mesh
+	int z0, nzl;          // first held global plane, held planes
+	int pitch; long long plane, comp;
+	unsigned long long seed;
+};
+// value = ((hash(i,j,k,n,field) mod 2^16) - 2^15) * 1e-6 (the recipe of SURVEY 8d); the last line of every
+// direction keeps H = 0 as in any reachable state (ii = iv = 0 there, operator.cpp:1176-1183)
+__global__ void k_fill(const __grid_constant__ FillParams p)
+{
+	const long long rows = (long long)p.nzl * p.ny;
+	for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y) {
+		const int kl = (int)(r / p.ny), j = (int)(r % p.ny);
+		const int k = p.z0 + kl;
+		const long long o = (long long)kl * p.plane + (long long)j * p.pitch;
+		for (int i = threadIdx.x; i < p.nx; i += blockDim.x) {
+			const unsigned long long g = ((unsigned long long)k * p.ny + j) * p.nx + i;
+#pragma unroll
+			for (int n = 0; n < 3; ++n) {
+				const unsigned long long hv = mix64(g * 6 + n + p.seed * 0x9E3779B97F4A7C15ull);
+				const unsigned long long hi = mix64(g * 6 + 3 + n + p.seed * 0x9E3779B97F4A7C15ull);
+				p.V[n * p.comp + o + i] = (float)((int)(hv & 0xffff) - 32768) * 1e-6f;
+				const bool last = (i == p.nx - 1) || (j == p.ny - 1) || (k == p.nzg - 1);
+				p.I[n * p.comp + o + i] = last ? 0.f : (float)((int)(hi & 0xffff) - 32768) * 2.6e-9f;
+			}
+		}
+	}
+}
+struct DigestParams {
+	const float* X;
+	int nx, ny;
+	int z0, k0, k1;       // first held global plane; local plane range of the OWNED planes
+	int pitch; long long plane, comp;
+	unsigned long long* acc;
+};
+// order-independent: sum over owned cells and components of mix(global index, bits) mod 2^64
+__global__ void k_digest(const __grid_constant__ DigestParams p)
+{
+	unsigned long long d = 0;
+	const long long rows = (long long)(p.k1 - p.k0) * p.ny;
+	for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y) {
+		const int kl = p.k0 + (int)(r / p.ny), j = (int)(r % p.ny);
+		const long long o = (long long)kl * p.plane + (long long)j * p.pitch;
+		for (int i = threadIdx.x; i < p.nx; i += blockDim.x) {
+			const unsigned long long g = ((unsigned long long)(p.z0 + kl) * p.ny + j) * p.nx + i;
+#pragma unroll
+			for (int n = 0; n < 3; ++n) {
+				unsigned bits = __float_as_uint(p.X[n * p.comp + o + i]);
+				if (bits == 0x80000000u) bits = 0; // -0 and +0 are the same field value
+				d += mix64((g * 3 + n) * 0x100000001b3ull ^ ((unsigned long long)bits << 17) ^ bits);
+			}
+		}
+	}
+	for (int s = 16; s > 0; s >>= 1) d += __shfl_down_sync(0xffffffffu, d, s);
+	if (threadIdx.x == 0) atomicAdd(p.acc, d);
+}
+
+// ---------------------------------------------------------------------------------------
 // Steady-state detection: Engine_Ext_SteadyState::Apply2Voltages engine_ext_steadystate.cpp:50-107.
 // Every timestep the probe voltages go into a 2-period ring; when a period completes
 // (TS % p == 0, TS >= 2p) the energy estimate of that instant (E after the stencil, H before its

@@ -402,6 +402,19 @@ class Engine_CUDA:
         self._ck(self._L.oems_cuda_read_dump(self._h, dump_id, _ptr(out, _fp)))
         return out
 
+    def FillFields(self, seed=0):
+        """deterministic pre-fill of E and H (function of the global cell index), see oems_cuda_fill_fields"""
+        self._ck(self._L.oems_cuda_fill_fields(self._h, int(seed)))
+
+    def FieldDigest(self):
+        """(digest_E, digest_H) of the owned cells; slab digests add up (mod 2^64) to the single-GPU digest"""
+        out = []
+        for w in (0, 1):
+            d = C.c_ulonglong()
+            self._ck(self._L.oems_cuda_field_digest(self._h, w, C.byref(d)))
+            out.append(d.value)
+        return tuple(out)
+
     def ReadDumpAsync(self, dump_id):
         """ProcessFieldsTD::Process without stalling the time loop: evaluates the dump at the current timestep and starts
         its copy into page-locked host memory on a second stream; returns a ticket.  WaitDump(ticket) -> ndarray"""

@@ -78,6 +78,18 @@ class SyntheticOperator:
     def set_excite_sinus(self, f0):
         self._L.oems_synth_set_excite_sinus(self._h, f0)
 
+    def set_slab(self, z_begin, z_end):
+        """one process per GPU: build only the planes of the owned range [z_begin, z_end) (+ ghost planes)"""
+        if self._L.oems_synth_set_slab(self._h, int(z_begin), int(z_end)):
+            raise EngineError((self._L.oems_synth_last_error(self._h) or b"").decode())
+
+    def local_timestep(self):
+        """Operator::CalcTimestep over this rank's planes; MIN-reduce over the ranks, then set_timestep(dT)"""
+        d = C.c_double()
+        if self._L.oems_synth_local_timestep(self._h, C.byref(d)):
+            raise EngineError("oems_synth_local_timestep failed")
+        return d.value
+
     def build(self, max_ts=10 ** 9):
         if self._L.oems_synth_build(self._h, max_ts):
             raise EngineError((self._L.oems_synth_last_error(self._h) or b"").decode())

@@ -138,3 +138,41 @@ def test_large_mesh_builds_fast_without_dense_arrays():
     assert p.unique_planes <= 2 * 12 + 8
     assert p.index().shape == (256, 256, 256)
     assert dt < 60
+
+
+def test_slab_restricted_build_equals_the_full_build():
+    """one process per GPU: each rank builds only the planes it holds; the timestep is agreed on by a MIN-reduction of
+    the per-rank values; tuples, plane contents and ids of the held planes equal the full build"""
+    lines = tuple(np.arange(n, dtype=np.float64) for n in (30, 28, 48))
+
+    def setup(s):
+        s.set_bc([BC_PML] * 6, (8,) * 6)
+        s.set_excite_gauss(0.0, 15e9)
+        s.add_material((5, 5, 30), (20, 20, 40), epsR=2.0)
+        s.add_excitation((14.5, 14, 16), (14.5, 14, 16), EXC_E_SOFT, (1, 0, 0))
+    full = SyntheticOperator(*lines, 1e-3)
+    setup(full)
+    full.build()
+    tab_full = full.table()
+    idx_full = full.index()
+    bounds = [0, 14, 30, 48]
+    parts = []
+    for r in range(3):
+        p = SyntheticOperator(*lines, 1e-3)
+        setup(p)
+        p.set_slab(bounds[r], bounds[r + 1])
+        parts.append(p)
+    dT = min(p.local_timestep() for p in parts)
+    assert dT == full.dT
+    for r, p in enumerate(parts):
+        p.set_timestep(dT)
+        p.build()
+        assert p.dT == full.dT and p.unique_planes <= full.unique_planes
+        up, ids = p.planes()
+        tab = p.table()
+        lo, hi = max(bounds[r] - 1, 0), min(bounds[r + 1] + 1, 48)
+        for k in range(lo, hi):
+            a = tab[up[ids[k]].astype(np.int64)]
+            b = tab_full[idx_full[k].astype(np.int64)]
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (r, k)
+    assert sum(p.unique_planes for p in parts) >= full.unique_planes
