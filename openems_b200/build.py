@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libopenems_b200.so")
 SOURCES = ["engine.cu", "host/synthetic_operator.cpp"]
-DEPS = ["kernels.cuh", "kernels_fused.cuh", "kernels_fused_tma.cuh", "kernels_xslab.cuh", "engine.h", "abi.inc", "entry_set.h", "host/synthetic_operator.h", "../../include/openems_b200.h"]
+DEPS = ["kernels.cuh", "kernels_fused.cuh", "kernels_fused_tma.cuh", "kernels_xslab.cuh", "kernels_xslab_tma.cuh", "engine.h", "abi.inc", "entry_set.h", "host/synthetic_operator.h", "../../include/openems_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

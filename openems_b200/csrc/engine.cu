@@ -1303,6 +1303,49 @@ int Engine::make_tma_maps(int par)
 	return r == CUDA_SUCCESS ? 0 : 1;
 }
 
+// TMA descriptors of k_xslab_tma (kernels_xslab_tma.cuh): same tensors as make_tma_maps, boxes of 24 columns
+int Engine::make_xslab_maps(int par)
+{
+	typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+	                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+	                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	void* fn = nullptr;
+	cudaDriverEntryPointQueryResult qres;
+	if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+		cudaGetLastError();
+		return 1;
+	}
+	EncodeFn encode = (EncodeFn)fn;
+	{
+		static std::vector<int> attr_devices;
+		if (std::find(attr_devices.begin(), attr_devices.end(), device) == attr_devices.end()) {
+			cudaSetDevice(device);
+			cudaFuncSetAttribute(k_xslab_tma<uint16_t, XT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, xt_smem_bytes<uint16_t, XT_STAGES>());
+			cudaFuncSetAttribute(k_xslab_tma<uint32_t, XT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, xt_smem_bytes<uint32_t, XT_STAGES>());
+			if (cudaGetLastError() != cudaSuccess) return 1;
+			attr_devices.push_back(device);
+		}
+	}
+	const int S = par;
+	XTmaParams& T = pXt[par];
+	const cuuint64_t dim4[4] = {(cuuint64_t)pitch, (cuuint64_t)gn[1], (cuuint64_t)nzl, 3};
+	const cuuint64_t str4[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)plane * 4, (cuuint64_t)comp * 4};
+	const cuuint32_t ones[4] = {1, 1, 1, 1};
+	const cuuint32_t boxI[4] = {XT_W, XT_ROWS_I, 1, 3}, boxV[4] = {XT_W, XT_ROWS_V, 1, 3}, boxX[3] = {XT_W, XT_ROWS_V, 1};
+	const cuuint64_t dim3[3] = {(cuuint64_t)pitch, (cuuint64_t)gn[1], (cuuint64_t)nzl};
+	const cuuint64_t str3[2] = {(cuuint64_t)pitch * index_bytes, (cuuint64_t)plane * index_bytes};
+	CUresult r = encode(&T.mI, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sI[S], dim4, str4, boxI, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r == CUDA_SUCCESS)
+		r = encode(&T.mV, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sV[S], dim4, str4, boxV, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r == CUDA_SUCCESS)
+		r = encode(&T.mX, index_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d_idx, dim3, str3, boxX,
+		           ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+		           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return r == CUDA_SUCCESS ? 0 : 1;
+}
+
 void Engine::build_schedule_fused()
 {
 	const bool i16 = index_bytes == 2;
@@ -1317,17 +1360,29 @@ void Engine::build_schedule_fused()
 	// chunk boundary: the big kernel computes the first line of that chunk with the plain formula for its own
 	// last H line
 	xs_box[0] = xs_box[1] = -1;
+	xs_win[0] = xs_win[1] = 0;
+	xslab_tma = tma_active && xslab_req == 2;
 	if (tma_active && xslab_req) {
 		for (int b = 0; b < pE.nboxes; ++b) {
 			const PmlBox& B = pE.box[b];
 			int g = -1;
-			if (B.s[0] == 0 && (B.n[0] + 3) / 4 * 4 + 1 <= 16 && (B.n[0] + 3) / 4 * 4 < (int)gn[0]) g = 0;
-			else if (B.s[0] + B.n[0] == (int)gn[0] && B.s[0] % 4 != 0 && (int)gn[0] - B.s[0] / 4 * 4 <= 16 && B.s[0] / 4 * 4 > 0) g = 1;
+			if (xslab_tma) {
+				// k_xslab_tma: a window of 16 lines starting on a 64-byte boundary must hold the box (+ the first line
+				// right of it on the low side) and end at / beyond the last line on the high side
+				// (whole 32-byte sectors: the window starts on a multiple of 8 lines)
+				const int ws = B.s[0] / 8 * 8;
+				if (B.s[0] == 0 && B.n[0] + 1 <= 16 && (int)gn[0] >= 48) { g = 0; xs_win[0] = 0; }
+				else if (B.s[0] + B.n[0] == (int)gn[0] && ws >= 32 && ws + 16 >= (int)gn[0] && ws + 16 <= pitch) { g = 1; xs_win[1] = ws; }
+			} else {
+				if (B.s[0] == 0 && (B.n[0] + 3) / 4 * 4 + 1 <= 16 && (B.n[0] + 3) / 4 * 4 < (int)gn[0]) g = 0;
+				else if (B.s[0] + B.n[0] == (int)gn[0] && B.s[0] % 4 != 0 && (int)gn[0] - B.s[0] / 4 * 4 <= 16 && B.s[0] / 4 * 4 > 0) g = 1;
+			}
 			if (g < 0 || xs_box[g] >= 0) continue;
 			bool hit = false;
 			for (long long q = 0; q < fix_count && !hit; ++q) {
 				const int* c = &h_fix_cells[3 * (size_t)q];
-				hit = (unsigned)(c[0] - B.s[0]) < (unsigned)B.n[0] && (unsigned)(c[1] - B.s[1]) < (unsigned)B.n[1] && (unsigned)(c[2] - B.s[2]) < (unsigned)B.n[2];
+				const int lo = xslab_tma ? xs_win[g] : B.s[0], n = xslab_tma ? 16 : B.n[0];
+				hit = (unsigned)(c[0] - lo) < (unsigned)n && (unsigned)(c[1] - B.s[1]) < (unsigned)B.n[1] && (unsigned)(c[2] - B.s[2]) < (unsigned)B.n[2];
 			}
 			if (!hit) xs_box[g] = b;
 		}
@@ -1389,7 +1444,7 @@ void Engine::build_schedule_fused()
 		XP.nx = (int)gn[0]; XP.ny = (int)gn[1]; XP.nz = nzl;
 		XP.pitch = pitch; XP.plane = plane; XP.comp = comp;
 		XP.kE0 = F.kE0; XP.kE1 = F.kE1; XP.kH1 = F.kH1; XP.kHc1 = F.kHc1;
-		XP.zchunk = 16;
+		XP.zchunk = xslab_tma ? xt_zchunk : 16;
 		nxs = 0;
 		for (int b = 0; b < pE.nboxes; ++b) {
 			const PmlBox& B = pE.box[b];
@@ -1397,11 +1452,11 @@ void Engine::build_schedule_fused()
 				const int g = b == xs_box[0] ? 0 : 1;
 				const int c0 = B.s[0] / 4, c1 = (B.s[0] + B.n[0] - 1) / 4; // chunks the box touches
 				XSlabFoot& X = FT.xs[g];
-				X.on = 1; X.c0 = c0; X.cn = c1 - c0 + 1;
+				X.on = xslab_tma ? 0 : 1; X.c0 = c0; X.cn = c1 - c0 + 1; // k_xslab_tma overwrites its window after the big kernel: no store masks
 				X.j0 = B.s[1]; X.jn = B.n[1]; X.k0 = B.s[2]; X.kn = B.n[2];
 				X.x0 = B.s[0]; X.x1 = B.s[0] + B.n[0];
 				XSlabBox& Q = XP.box[nxs++];
-				Q.w0 = c0 * 4; Q.own0 = c0 * 4; Q.own1 = std::min((c1 + 1) * 4, (int)gn[0]);
+				Q.w0 = xslab_tma ? xs_win[g] : c0 * 4; Q.own0 = c0 * 4; Q.own1 = std::min((c1 + 1) * 4, (int)gn[0]);
 				Q.bs0 = B.s[0]; Q.bn0 = B.n[0];
 				Q.s1 = B.s[1]; Q.n1 = B.n[1]; Q.s2 = B.s[2]; Q.n2 = B.n[2];
 				Q.cs = (long long)B.n[0] * B.n[1] * B.n[2];
@@ -1451,6 +1506,10 @@ void Engine::build_schedule_fused()
 			w->nblocks = nb;
 		}
 		FT.f = F;
+		if (xslab_tma && nxs) {
+			pXt[par].x = XP;
+			if (make_xslab_maps(par)) { xslab_tma = false; }
+		}
 		FixParams& X = pFix[par];
 		memset(&X, 0, sizeof(X));
 		X.Is = sI[S]; X.Id = sI[D]; X.Vd = sV[D];
@@ -1498,7 +1557,7 @@ void Engine::build_schedule_fused()
 				if (i16) k_shell_E<uint16_t><<<q.nblocks, dim3(32, 8), 0, s>>>(q); else k_shell_E<uint32_t><<<q.nblocks, dim3(32, 8), 0, s>>>(q);
 			});
 		}
-		if (nxs) {
+		if (nxs && !xslab_tma) {
 			// x slabs: E and H in one pass, source -> destination set (after the shells of the other boxes: it
 			// takes their E_new as neighbour values; before or after the big kernel makes no difference)
 			lab("xslab_EH");
@@ -1526,6 +1585,17 @@ void Engine::build_schedule_fused()
 			if (i16) { if (has_pml) k_fused_EH<uint16_t, true><<<g, block, 0, s>>>(q); else k_fused_EH<uint16_t, false><<<g, block, 0, s>>>(q); }
 			else { if (has_pml) k_fused_EH<uint32_t, true><<<g, block, 0, s>>>(q); else k_fused_EH<uint32_t, false><<<g, block, 0, s>>>(q); }
 		});
+		if (nxs && xslab_tma) {
+			// x slabs, TMA-staged: overwrites its 16-line windows in the destination set AFTER the big kernel (which
+			// treated them as plain cells) and before the hooks / k_shell_H, which read the final E of the window
+			lab("xslab_EH");
+			L.push_back([this, par, i16](cudaStream_t s) {
+				const XTmaParams& q = pXt[par];
+				const dim3 g((unsigned)((q.x.ny + XT_TY - 1) / XT_TY), (unsigned)std::max(1, (q.x.kE1 - q.x.kE0 + q.x.zchunk - 1) / q.x.zchunk), (unsigned)nxs);
+				if (i16) k_xslab_tma<uint16_t, XT_STAGES><<<g, XT_THREADS, xt_smem_bytes<uint16_t, XT_STAGES>(), s>>>(q);
+				else k_xslab_tma<uint32_t, XT_STAGES><<<g, XT_THREADS, xt_smem_bytes<uint32_t, XT_STAGES>(), s>>>(q);
+			});
+		}
 		// ---- post / apply voltage hooks on the destination set
 		pTfsfD[par][0] = pTfsf[0]; pTfsfD[par][0].X = sV[D];
 		pTfsfD[par][1] = pTfsf[1]; pTfsfD[par][1].X = sI[D];
@@ -1745,6 +1815,11 @@ int Engine::set_option(const char* key, long long value)
 		if (finalized) return rebuild_schedule();
 		return 0;
 	}
+	if (k == "xslab_zchunk") {
+		xt_zchunk = (int)std::max<long long>(4, std::min<long long>(63, value)); // one shell bit per plane of a march
+		if (finalized) return rebuild_schedule();
+		return 0;
+	}
 	if (k == "shell_zchunk") { // planes a UPML shell block marches (tuning aid)
 		shell_zchunk = (int)std::max<long long>(1, std::min<long long>(64, value));
 		if (finalized) return rebuild_schedule();
@@ -1759,7 +1834,7 @@ int Engine::set_option(const char* key, long long value)
 	if (k == "xslab") {
 		// 1: thin UPML boxes at the x ends are updated by their own one-pass kernel k_xslab_EH, 0: shell launches
 		// (default: measured faster, profiles/experiments_r01.md #12, #15)
-		xslab_req = value != 0;
+		xslab_req = value <= 0 ? 0 : (value >= 2 ? 2 : 1); // 1: k_xslab_EH (register-staged), 2: k_xslab_tma
 		if (finalized) return rebuild_schedule();
 		return 0;
 	}

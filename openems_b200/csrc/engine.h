@@ -13,6 +13,7 @@
 #include "kernels_fused.cuh"
 #include "kernels_fused_tma.cuh"
 #include "kernels_xslab.cuh"
+#include "kernels_xslab_tma.cuh"
 
 struct UpmlBoxHost {
 	unsigned start[3], n[3];          // global
@@ -269,6 +270,11 @@ private:
 	int xs_box[2] = {-1, -1};
 	int xslab_req = 0;           // option "xslab": thin UPML boxes at the x ends get their own one-pass kernel (off: not faster yet, experiments_r01.md #15)
 	XSlabParams pXs[2];          // per parity
+	XTmaParams pXt[2];           // the same + TMA descriptors (k_xslab_tma)
+	bool xslab_tma = false;
+	int xs_win[2] = {0, 0};      // first line of the 16-line windows of k_xslab_tma
+	int xt_zchunk = 32;
+	int make_xslab_maps(int par);
 	int nxs = 0;                 // x slabs in pXs
 	float* d_flux_v2 = nullptr;  // second voltage-flux set (only the x-slab boxes use it)
 	std::vector<int> h_fix_cells;

@@ -162,6 +162,36 @@ def test_x_slab_boxes_inside_the_one_pass_kernel(n, pml):
                 assert np.array_equal(eng.GetUPMLFlux(b, w, box["n"]).view(np.uint32), s.upml_flux(b, w).view(np.uint32))
 
 
+@pytest.mark.parametrize("n,pml,bc", [((150, 20, 18), 8, None), ((300, 33, 40), 8, None), ((64, 40, 33), 8, None), ((1031, 19, 21), 8, None),
+                                      ((57, 37, 30), 4, None), ((96, 31, 34), 8, (BC_PML, BC_PML, BC_MUR, BC_PML, BC_PEC, BC_PML)),
+                                      ((80, 30, 29), 6, (BC_PML, BC_PEC, BC_PML, BC_PML, BC_PML, BC_PMC))])
+def test_x_slab_windows_tma_staged(n, pml, bc):
+    """option "xslab" = 2: the UPML boxes at the x ends are updated, E and H in one pass, by the TMA-staged window
+    kernel k_xslab_tma (16-line windows = whole 32-byte sectors, launched after the big kernel); window starts that
+    are / are not multiples of 16 lines, partial last row tiles, mixed boundary conditions (Mur / PEC / PMC faces next
+    to the slabs), toggled against the shell path at odd and even timestep counts, flux compared as well"""
+    src = (n[0] - 22 if n[0] > 200 else n[0] // 2, n[1] // 2, n[2] // 2)
+    s = cases.uniform_box(n=n, bc=bc or (BC_PML,) * 6, pml=pml, src_pos=src)
+    eng = operator_from_oracle(s).CreateEngine()
+    eng.SetOption("fused", 1)
+    eng.SetOption("xslab", 2)
+    assert eng.GetOption("tma") == 1
+    nslabs = eng.GetOption("xslab")   # slabs with hook-changed cells inside (Mur faces) stay on the shell path
+    assert nslabs == 2 if bc is None else nslabs in (0, 1, 2), nslabs
+    total = 0
+    for steps, xs in ((1, 2), (6, 2), (3, 0), (4, 2), (45, 2), (2, 1), (9, 2)):
+        eng.SetOption("xslab", xs)
+        s.iterate(steps)
+        eng.IterateTS(steps)
+        total += steps
+        assert_fields_equal(eng, s, "x-slab windows mode %d after %d steps" % (xs, total))
+        for b, box in enumerate(s.upml_boxes()):
+            for w in (0, 1):
+                assert np.array_equal(eng.GetUPMLFlux(b, w, box["n"]).view(np.uint32), s.upml_flux(b, w).view(np.uint32))
+    names = [nm for nm, _ in eng.TimeSchedule(0)]
+    assert ("xslab_EH" in names) == (nslabs > 0)
+
+
 @pytest.mark.parametrize("case", ["line", "box"])
 def test_local_absorbing_sheets(case):
     """Engine_Ext_Absorbing_BC (engine_ext_absorbing_bc.cpp:108-366) -- first order
