@@ -303,6 +303,40 @@ int oems_cuda_open_peers(oems_cuda_engine* h, const unsigned char* lower /*OEMS_
 /* same-process variant (tests, or one process driving several GPUs) */
 int oems_cuda_link_peers(oems_cuda_engine* h, oems_cuda_engine* lower, oems_cuda_engine* upper);
 
+/* ---- readout on z-slab engines (reference template: every MPI rank of Engine_MPI processes the part of a probe /
+   dump box that lies in its sub-domain, FDTD/openems_fdtd_mpi.cpp:201-299, and holds complete neighbour planes,
+   FDTD/engine_mpi.cpp:84-182).
+   The time loop only exchanges the tangential E / H components the stencil needs.  The interpolating readers
+   (field dumps, FD dumps, mode matching: engine_interface_fdtd.cpp:63-124,150-204) also read the normal components
+   and E of the plane below / H of the plane above, so before such a readout every slab completes its neighbours'
+   ghost planes: oems_cuda_exchange_ghosts pushes all components of E and H of its lowest / highest owned plane
+   through the peer mappings and waits (on the device) for the neighbours' planes.  It only enqueues, is a no-op
+   on an engine without neighbours, and is called implicitly by oems_cuda_read_dump(_async), oems_cuda_fd_accumulate
+   and oems_cuda_read_mode_match(_raw); one exchange serves all readouts of the same timestep.  COLLECTIVE: every
+   slab has to reach the same readout at the same timestep.  A single host thread that drives several slabs must call
+   oems_cuda_exchange_ghosts on all of them before the first call that blocks (oems_cuda_read_dump, _wait, ...).
+   The next oems_cuda_iterate (or an explicit oems_cuda_release_ghosts) tells the neighbours that this slab is
+   done reading and waits for theirs before the time loop writes into their ghost planes again. */
+int oems_cuda_exchange_ghosts(oems_cuda_engine* h);
+int oems_cuda_release_ghosts(oems_cuda_engine* h);
+/* a z-slab engine evaluates the z lines of a dump box it owns: entries [first, first + n) of the pz list given to
+   oems_cuda_add_dump (which must ascend); oems_cuda_read_dump / _read_fd return 3*nx*ny*n values, and the host
+   concatenates the slabs along z.  On a single-GPU engine first = 0, n = nz. */
+int oems_cuda_dump_own_range(oems_cuda_engine* h, int dump_id, unsigned* first, unsigned* n);
+/* mode matching over the planes this engine owns: out3 = {value, value^2/purity, purity}.  Slab partial results are
+   put together on the host: value = sum of value, purity = sum of purity, result {value, value^2/purity}. */
+int oems_cuda_read_mode_match_raw(oems_cuda_engine* h, int id, double* out3);
+/* steady-state detection on z-slab engines: every slab records the probes it owns (the order of the list given to
+   oems_cuda_add_steadystate is kept) and the energy of its planes.  oems_cuda_steadystate_raw returns
+   info2 = {checks done, timestep of the last}, energy4 = {scratch, scratch, previous period, current period},
+   snap[2*period][count] and the local probe count; the host adds the energies, concatenates the records (count
+   fastest) and evaluates Engine_Ext_SteadyState::Apply2Voltages (engine_ext_steadystate.cpp:62-106) with
+   oems_cuda_steadystate_eval (host arithmetic, no engine needed). */
+int oems_cuda_steadystate_raw(oems_cuda_engine* h, unsigned* info2, double* energy4, double* snap, unsigned capacity,
+                              unsigned* count);
+int oems_cuda_steadystate_eval(unsigned period_ts, unsigned count, const unsigned* info2, const double* energy4,
+                               const double* snap, double* last_diff);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

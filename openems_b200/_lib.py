@@ -91,6 +91,12 @@ SIGNATURES = {
     "oems_cuda_read_fd": (C.c_int, [_vp, C.c_int, _fp, _up]),
     "oems_cuda_add_mode_match": (C.c_int, [_vp, C.c_int, C.c_int, _up, _up, _dp, _dp, _dp, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(C.c_int)]),
     "oems_cuda_read_mode_match": (C.c_int, [_vp, C.c_int, _dp]),
+    "oems_cuda_read_mode_match_raw": (C.c_int, [_vp, C.c_int, _dp]),
+    "oems_cuda_exchange_ghosts": (C.c_int, [_vp]),
+    "oems_cuda_release_ghosts": (C.c_int, [_vp]),
+    "oems_cuda_dump_own_range": (C.c_int, [_vp, C.c_int, _up, _up]),
+    "oems_cuda_steadystate_raw": (C.c_int, [_vp, _up, _dp, _dp, C.c_uint, _up]),
+    "oems_cuda_steadystate_eval": (C.c_int, [C.c_uint, C.c_uint, _up, _dp, _dp, _dp]),
     "oems_cuda_get_option": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_longlong)]),
     "oems_cuda_set_option": (C.c_int, [_vp, C.c_char_p, C.c_longlong]),
     "oems_cuda_time_schedule": (C.c_int, [_vp, C.c_uint, _dp, C.c_uint, _up]),

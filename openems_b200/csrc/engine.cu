@@ -347,7 +347,6 @@ int Engine::add_rlc(unsigned count, const int* dir, const unsigned* pos3, const 
 int Engine::add_steadystate(unsigned period_ts, unsigned count, const unsigned* pos3, const unsigned* dir)
 {
 	if (finalized) return fail("engine already finalized");
-	if (slab_set) return fail("add_steadystate: not supported on a z-slab engine yet");
 	if (period_ts == 0 || count == 0) return fail("add_steadystate: empty");
 	for (unsigned n = 0; n < count; ++n) {
 		if (dir[n] > 2) return fail("add_steadystate: bad direction");
@@ -355,26 +354,40 @@ int Engine::add_steadystate(unsigned period_ts, unsigned count, const unsigned* 
 			if (pos3[(size_t)a * count + n] >= gn[a]) return fail("add_steadystate: position outside the mesh");
 	}
 	ss_period = period_ts;
-	ss_pos.assign(pos3, pos3 + (size_t)3 * count);
-	ss_dir.assign(dir, dir + count);
+	// a z-slab engine records the probes on the planes it owns (list order kept) and sums the energy of its planes;
+	// the host puts the slabs together (steadystate_raw / steadystate_eval)
+	ss_pos.clear(); ss_dir.clear();
+	std::vector<unsigned> keep;
+	for (unsigned n = 0; n < count; ++n)
+		if (owned(pos3[(size_t)2 * count + n])) keep.push_back(n);
+	for (int a = 0; a < 3; ++a)
+		for (unsigned n : keep) ss_pos.push_back(pos3[(size_t)a * count + n]);
+	for (unsigned n : keep) ss_dir.push_back(dir[n]);
 	return 0;
 }
 
 // Engine_Ext_SteadyState::Apply2Voltages (engine_ext_steadystate.cpp:62-106) evaluated on the host
 // from the device snapshot of the last completed period
-int Engine::steadystate_check(double* last_diff, unsigned* n_checks)
+int Engine::steadystate_raw(unsigned info[2], double en[4], double* snap, unsigned cap, unsigned* count)
 {
-	if (!ss_on) return fail("steadystate_check: no steady-state detection set up");
+	if (!ss_on) return fail("steadystate: no steady-state detection set up");
 	CK(cudaSetDevice(device));
 	const unsigned p = ss_period, cnt = pSs.count;
-	unsigned info[2];
-	double en[4];
-	CK(cudaMemcpyAsync(info, pSs.info, sizeof(info), cudaMemcpyDeviceToHost, stream));
-	CK(cudaMemcpyAsync(en, pSs.energy, sizeof(en), cudaMemcpyDeviceToHost, stream));
-	std::vector<double> snap((size_t)2 * p * cnt);
-	CK(cudaMemcpyAsync(snap.data(), pSs.snap, snap.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+	if (count) *count = cnt;
+	CK(cudaMemcpyAsync(info, pSs.info, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+	CK(cudaMemcpyAsync(en, pSs.energy, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+	if (snap && cnt) {
+		if ((size_t)cap < (size_t)2 * p * cnt) return fail("steadystate_raw: buffer too small");
+		CK(cudaMemcpyAsync(snap, pSs.snap, (size_t)2 * p * cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+	}
 	CK(cudaStreamSynchronize(stream));
-	if (n_checks) *n_checks = info[0];
+	return 0;
+}
+
+// the criterion of Engine_Ext_SteadyState::Apply2Voltages from the raw data; z-slab drivers add up the slabs'
+// energies and concatenate their records ([2*period][count], count fastest) before calling it
+int Engine::steadystate_eval(unsigned p, unsigned cnt, const unsigned info[2], const double en[4], const double* snap, double* last_diff)
+{
 	double diff = 1.0;
 	if (info[0] > 0) {
 		bool no_valid = true;
@@ -399,6 +412,22 @@ int Engine::steadystate_check(double* last_diff, unsigned* n_checks)
 	}
 	if (last_diff) *last_diff = diff;
 	return 0;
+}
+
+// Engine_Ext_SteadyState::Apply2Voltages (engine_ext_steadystate.cpp:62-106) evaluated on the host
+// from the device snapshot of the last completed period
+int Engine::steadystate_check(double* last_diff, unsigned* n_checks)
+{
+	if (!ss_on) return fail("steadystate_check: no steady-state detection set up");
+	if (slab_set && (zb > 0 || ze < gn[2]))
+		return fail("steadystate_check: on z-slab engines gather oems_cuda_steadystate_raw of all slabs and call oems_cuda_steadystate_eval");
+	const unsigned p = ss_period, cnt = pSs.count;
+	unsigned info[2];
+	double en[4];
+	std::vector<double> snap((size_t)2 * p * cnt);
+	if (steadystate_raw(info, en, snap.data(), (unsigned)snap.size(), nullptr)) return 1;
+	if (n_checks) *n_checks = info[0];
+	return steadystate_eval(p, cnt, info, en, snap.data(), last_diff);
 }
 
 // ------------------------------------------------------------------------------ compression
@@ -717,13 +746,24 @@ int Engine::build_sheets()
 {
 	sheet_dev.clear();
 	if (h_sheet.empty()) return 0;
-	if (slab_set) return fail("absorbing sheets on a z-slab engine are not supported yet");
 	for (const SheetHost& S : h_sheet) {
 		const int ny = S.ny, nP = (ny + 1) % 3, nPP = (ny + 2) % 3;
 		const unsigned nl0 = S.x1[nP] - S.x0[nP] + 1, nl1 = S.x1[nPP] - S.x0[nPP] + 1;
 		const unsigned line = S.x0[ny];
 		const unsigned shift_V = line + (S.positive ? 1 : -1);
 		const unsigned pos_I = line + (S.positive ? 0 : -1), shift_I = line + (S.positive ? 1 : -2);
+		// z-slab engines (template: the extension simply lives on the MPI rank that holds the cells): sheets normal to
+		// x or y are cut at the slab's owned planes; a sheet normal to z belongs to the slab that owns its line, and
+		// the lines it reads next to it must be owned by the same slab
+		bool mine = true;
+		if (slab_set && ny == 2) {
+			mine = owned(line);
+			const bool sa = S.type == 2 && nl0 > 1 && nl1 > 1;
+			if (mine && (!owned(shift_V) || (sa && (!owned(pos_I) || !owned(shift_I)))))
+				return fail("absorbing sheet normal to z lies on a z-slab boundary: move the split by a few planes");
+			if (!mine && (owned(shift_V) || (sa && (owned(pos_I) || owned(shift_I)))))
+				return fail("absorbing sheet normal to z lies on a z-slab boundary: move the split by a few planes");
+		}
 		SheetDev D;
 		memset(&D, 0, sizeof(D));
 		auto off = [&](int comp_n, unsigned l, unsigned a, unsigned b) {
@@ -731,11 +771,18 @@ int Engine::build_sheets()
 			pos[ny] = l; pos[nP] = S.x0[nP] + a; pos[nPP] = S.x0[nPP] + b;
 			return (long long)comp_n * comp + cell_off(pos[0], pos[1], pos[2]);
 		};
+		auto here = [&](unsigned a, unsigned b) {
+			if (!slab_set) return true;
+			if (ny == 2) return mine;
+			const unsigned z = nP == 2 ? S.x0[nP] + a : S.x0[nPP] + b;
+			return owned(z);
+		};
 		// voltage list: all sheet points, component nyP then nyPP of a point (order is irrelevant: distinct cells)
 		std::vector<long long> o, os;
 		std::vector<float> k1, k2;
 		for (unsigned a = 0; a < nl0; ++a)
 			for (unsigned b = 0; b < nl1; ++b) {
+				if (!here(a, b)) continue;
 				const size_t q = (size_t)a * nl1 + b;
 				o.push_back(off(nP, line, a, b)); os.push_back(off(nP, shift_V, a, b)); k1.push_back(S.K1P[q]);
 				o.push_back(off(nPP, line, a, b)); os.push_back(off(nPP, shift_V, a, b)); k1.push_back(S.K1PP[q]);
@@ -748,6 +795,7 @@ int Engine::build_sheets()
 			o.clear(); os.clear(); k1.clear();
 			for (unsigned a = 0; a + 1 < nl0; ++a)
 				for (unsigned b = 0; b + 1 < nl1; ++b) {
+					if (!here(a, b)) continue;
 					const size_t q = (size_t)a * nl1 + b;
 					o.push_back(off(nP, pos_I, a, b)); os.push_back(off(nP, shift_I, a, b)); k1.push_back(S.K1P[q]); k2.push_back(S.K2P[q]);
 					o.push_back(off(nPP, pos_I, a, b)); os.push_back(off(nPP, shift_I, a, b)); k1.push_back(S.K1PP[q]); k2.push_back(S.K2PP[q]);
@@ -856,20 +904,51 @@ int Engine::build_exc()
 	return 0;
 }
 
+// Can the one-pass kernel apply the ADE of the Lorentz/Drude cells itself?  It computes E_new = stencil - ADE and
+// H_new = stencil - ADE per cell (engine_ext_lorentzmaterial.cpp:79-168: the pre hooks only read timestep-n values and
+// run as list kernels before it).  That reproduces the reference's hook order as long as no OTHER hook reads or
+// changes a dispersive cell between the stencil and Apply2Voltages / Apply2Current:
+//   * at most two orders (poles); in every row the cells of an order are contiguous in x (one segment per row);
+//   * no dispersive cell inside a UPML box (its post-voltage hook precedes the ADE subtraction);
+//   * none on a Mur plane's boundary or shifted line (k_mur_post reads the stencil value before the subtraction),
+//     no absorbing sheets and no TFSF box together with dispersive material;
+//   * no H cell of the fix-up list is dispersive (checked with the list, build_fix_list).
+// Everything else runs the two-pass schedule.
+bool Engine::lorentz_fusable() const
+{
+	if (h_lor.size() > LOR_FUSED_MAX) return false;
+	if (!h_sheet.empty() || h_tfsf.on) return false;
+	for (const LorHost& L : h_lor) {
+		const unsigned* px = L.pos.data();
+		const unsigned* py = px + L.count;
+		const unsigned* pz = py + L.count;
+		for (unsigned i = 0; i < L.count; ++i) {
+			for (const UpmlBoxHost& B : h_upml)
+				if (px[i] - B.start[0] < B.n[0] && py[i] - B.start[1] < B.n[1] && pz[i] - B.start[2] < B.n[2]) return false;
+			const unsigned pos[3] = {px[i], py[i], pz[i]};
+			for (const MurHost& M : h_mur)
+				if (pos[M.ny] == M.line || pos[M.ny] == M.shift) return false;
+		}
+	}
+	return true;
+}
+
 int Engine::build_lorentz()
 {
 	lor_dev.clear();
 	for (const LorHost& L : h_lor) {
-		// keep only the cells on owned planes
+		// keep only the cells on owned planes, in storage order (z, y, x): the list kernels then read the fields
+		// coalesced, and the one-pass kernel finds a cell's ADE through one {first x, cells, first index} per row
 		std::vector<unsigned> keep;
 		for (unsigned i = 0; i < L.count; ++i)
 			if (owned(L.pos[(size_t)2 * L.count + i])) keep.push_back(i);
+		auto off_of = [&](unsigned i) { return cell_off(L.pos[i], L.pos[(size_t)L.count + i], L.pos[(size_t)2 * L.count + i]); };
+		std::sort(keep.begin(), keep.end(), [&](unsigned a, unsigned b) { return off_of(a) < off_of(b); });
 		const unsigned cnt = (unsigned)keep.size();
 		std::vector<long long> cell(cnt);
-		for (unsigned q = 0; q < cnt; ++q) {
-			const unsigned i = keep[q];
-			cell[q] = cell_off(L.pos[i], L.pos[(size_t)L.count + i], L.pos[(size_t)2 * L.count + i]);
-		}
+		for (unsigned q = 0; q < cnt; ++q) cell[q] = off_of(keep[q]);
+		for (unsigned q = 1; q < cnt; ++q)
+			if (cell[q] == cell[q - 1]) return fail("add_lorentz: a cell is listed twice");
 		auto pick = [&](const std::vector<float>& src) {
 			std::vector<float> d((size_t)3 * cnt);
 			for (int n = 0; n < 3; ++n)
@@ -894,8 +973,31 @@ int Engine::build_lorentz()
 			D.i.ade = dalloc<float>((size_t)3 * cnt);
 			if (!L.c[5].empty()) { D.i.c_lor = upload(pick(L.c[5])); D.i.lor_ade = dalloc<float>((size_t)3 * cnt); }
 		}
+		// entries on the slab's top owned plane (its H is done after the neighbour's E plane has arrived)
+		D.top_first = cnt;
+		{
+			const long long top = (long long)((int)ze - 1 - z0) * plane;
+			D.top_first = (unsigned)(std::lower_bound(cell.begin(), cell.end(), top) - cell.begin());
+		}
+		if (lor_fused) {
+			std::vector<int2> rows((size_t)nzl * gn[1], make_int2(0, 0));
+			for (unsigned q = 0; q < cnt && lor_fused; ++q) {
+				const long long r = cell[q] / pitch;
+				const int x = (int)(cell[q] % pitch);
+				int2& R = rows[(size_t)r];
+				const int n = R.x >> 16, x0 = R.x & 0xffff;
+				if (n == 0) { R.x = x | (1 << 16); R.y = (int)q; }
+				else if (x == x0 + n && n < 32767) R.x = x0 | ((n + 1) << 16);
+				else lor_fused = false; // a second segment in this row
+			}
+			if (gn[0] > 65535) lor_fused = false;
+			if (lor_fused) D.d_rows = upload(rows);
+			if (lor_fused && !D.d_rows) return fail("out of device memory (Lorentz row table)");
+			if (lor_fused) D.h_rows.swap(rows);
+		}
 		lor_dev.push_back(D);
 	}
+	if (!h_lor.empty() && !lor_fused) fused_possible = false;
 	return 0;
 }
 
@@ -956,7 +1058,7 @@ int Engine::finalize()
 	if (!d_V || !d_I) return fail("out of device memory (fields)");
 	d_numTS = dalloc<unsigned>(1);
 	d_energy = dalloc<double>(2);
-	d_flagE = dalloc<unsigned>(8);
+	d_flagE = dalloc<unsigned>(FLAG_WORDS);
 	d_flagH = d_flagE + 1;
 	d_halo_cnt = d_flagE + 2;
 	d_halo_err = d_flagE + 4;
@@ -986,7 +1088,9 @@ int Engine::finalize()
 	sV[0] = d_V; sI[0] = d_I;
 	// the one-pass schedule needs a second field set, no volume hooks between the half-steps and
 	// disjoint UPML boxes (each is updated by its own shell launch)
-	fused_possible = fused_req != 0 && h_lor.empty() && h_rlc.empty() && pml_disjoint;
+	lor_fused = !h_lor.empty() && lorentz_fusable();
+	fused_possible = fused_req != 0 && (h_lor.empty() || lor_fused) && h_rlc.empty() && pml_disjoint;
+	if (!fused_possible) lor_fused = false;
 	if (fused_possible) {
 		sV[1] = dalloc<float>(nfield);
 		sI[1] = dalloc<float>(nfield);
@@ -1004,15 +1108,16 @@ int Engine::finalize()
 	if (build_tfsf()) return 1;
 	ss_on = false;
 	if (ss_period) {
-		const unsigned cnt = (unsigned)ss_dir.size();
+		const unsigned cnt = (unsigned)ss_dir.size(); // may be 0 on a slab that owns none of the probes: energy only
 		std::vector<long long> off(cnt);
 		for (unsigned n = 0; n < cnt; ++n)
 			off[n] = (long long)ss_dir[n] * comp + cell_off(ss_pos[n], ss_pos[(size_t)cnt + n], ss_pos[(size_t)2 * cnt + n]);
 		memset(&pSs, 0, sizeof(pSs));
 		pSs.V = d_V; pSs.I = d_I;
+		if (off.empty()) off.push_back(0);
 		pSs.off = upload(off);
-		pSs.rec = dalloc<double>((size_t)2 * ss_period * cnt);
-		pSs.snap = dalloc<double>((size_t)2 * ss_period * cnt);
+		pSs.rec = dalloc<double>((size_t)2 * ss_period * std::max(1u, cnt));
+		pSs.snap = dalloc<double>((size_t)2 * ss_period * std::max(1u, cnt));
 		pSs.energy = dalloc<double>(4);
 		pSs.info = dalloc<unsigned>(2);
 		pSs.numTS = d_numTS;
@@ -1024,6 +1129,18 @@ int Engine::finalize()
 		ss_on = true;
 	}
 	if (fused_possible && build_fix_list()) return 1;
+	if (fused_possible && lor_fused) {
+		// k_fix_H recomputes plain H cells: a dispersive H cell next to a source / Mur plane keeps the two-pass schedule
+		for (long long q = 0; q < fix_count && lor_fused; ++q) {
+			const int* c = &h_fix_cells[3 * (size_t)q];
+			for (const LorDev& D : lor_dev) {
+				if (!D.i_on) continue;
+				const int2 R = D.h_rows[(size_t)c[2] * gn[1] + c[1]];
+				if ((unsigned)(c[0] - (R.x & 0xffff)) < (unsigned)(R.x >> 16)) lor_fused = false;
+			}
+		}
+		if (!lor_fused) fused_possible = false;
+	}
 	CK(cudaStreamSynchronize(stream));
 	CK(cudaGetLastError());
 	tm.lap("hooks, fix list");
@@ -1053,7 +1170,7 @@ void Engine::build_schedule()
 	// path not in use) and either requested or -- automatic choice -- the mesh is big enough to fill the
 	// GPU with z-marching blocks: below ~160^3 cells the two-pass kernels, which have a thread per cell
 	// column and z chunk, are faster (tools/size_sweep.py, profiles/experiments_r01.md #13)
-	fused_active = fused_possible && !edge_dirty && (fused_req == 1 || (fused_req < 0 && fused_auto_choice()));
+	fused_active = fused_possible && !edge_dirty && (fused_req == 1 || (fused_req < 0 && fused_auto_choice())) && !(lor_fused && !tma_req);
 	const bool i16 = index_bytes == 2;
 	const dim3 block(32, tune_rows);
 	auto stencil_grid = [&](const StencilParams& p, int rows_total) {
@@ -1094,7 +1211,7 @@ void Engine::build_schedule()
 	if (pMur.nplanes) (labels.push_back("mur_post"), step.push_back([this](cudaStream_t s) { launch1d(k_mur_post, pMur, pMur.total, s); }));
 	// ---- apply-voltage hooks in list order: SteadyState, RLC, Lorentz, Mur, Excitation
 	auto ss_launch = [this](const SsParams& q, cudaStream_t s) {
-		k_ss_record<<<(q.count + 63) / 64, 64, 0, s>>>(q);
+		k_ss_record<<<std::max(1u, (q.count + 63) / 64), 64, 0, s>>>(q);
 		k_ss_energy<<<148 * 2, dim3(32, 8), 0, s>>>(q);
 		k_ss_snapshot<<<8, 256, 0, s>>>(q);
 	};
@@ -1279,6 +1396,10 @@ int Engine::make_tma_maps(int par)
 			cudaFuncSetAttribute(k_fused_tma<uint16_t, false, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
 			cudaFuncSetAttribute(k_fused_tma<uint32_t, true, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
 			cudaFuncSetAttribute(k_fused_tma<uint32_t, false, FT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
+			cudaFuncSetAttribute(k_fused_tma<uint16_t, true, FT_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
+			cudaFuncSetAttribute(k_fused_tma<uint16_t, false, FT_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16);
+			cudaFuncSetAttribute(k_fused_tma<uint32_t, true, FT_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
+			cudaFuncSetAttribute(k_fused_tma<uint32_t, false, FT_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32);
 			if (cudaGetLastError() != cudaSuccess) return 1;
 			attr_devices.push_back(device);
 		}
@@ -1351,6 +1472,7 @@ void Engine::build_schedule_fused()
 	const bool i16 = index_bytes == 2;
 	const bool multi = peers_linked;
 	labelsf.clear();
+	sched_error.clear();
 	// TMA descriptors of both source sets; without them the register-staged kernel is used
 	tma_active = tma_req != 0 && make_tma_maps(0) == 0 && make_tma_maps(1) == 0;
 	// UPML boxes updated by their own one-pass kernel k_xslab_EH ("x slabs", kernels_xslab.cuh): thin in x, at
@@ -1506,6 +1628,18 @@ void Engine::build_schedule_fused()
 			w->nblocks = nb;
 		}
 		FT.f = F;
+		memset(&FT.lor, 0, sizeof(FT.lor));
+		if (lor_fused) {
+			if (!tma_active) sched_error = "the one-pass schedule with Lorentz/Drude material needs the TMA-staged kernel (no tensor map could be made)";
+			FT.lor.nord = (int)lor_dev.size();
+			for (size_t o = 0; o < lor_dev.size(); ++o) {
+				const LorDev& Ld = lor_dev[o];
+				FT.lor.o[o].rows = Ld.d_rows;
+				FT.lor.o[o].ade_v = Ld.v_on ? Ld.v.ade : nullptr;
+				FT.lor.o[o].ade_i = Ld.i_on ? Ld.i.ade : nullptr;
+				FT.lor.o[o].count = Ld.v_on ? Ld.v.count : Ld.i.count;
+			}
+		}
 		if (xslab_tma && nxs) {
 			pXt[par].x = XP;
 			if (make_xslab_maps(par)) { xslab_tma = false; }
@@ -1532,6 +1666,19 @@ void Engine::build_schedule_fused()
 
 		// ---- pre-voltage hooks on the source set
 		if (pMur.nplanes) { lab("mur_pre"); L.push_back([this, par](cudaStream_t s) { launch1d(k_mur_pre, pMurS[par], pMurS[par].total, s); }); }
+		// Lorentz / Drude: both pre hooks (engine_ext_lorentzmaterial.cpp:79-127) read timestep-n values of the cell itself
+		// -> list kernels on the source set; the one-pass kernel subtracts the advanced ADE values (LOR instance)
+		if (lor_fused)
+			for (size_t o = 0; o < lor_dev.size(); ++o) {
+				if (lor_dev[o].v_on) {
+					lab("lorentz_pre_V");
+					L.push_back([this, par, o](cudaStream_t s) { LorParams q = lor_dev[o].v; q.X = sV[par]; launch1d(k_lorentz_pre, q, q.count, s); });
+				}
+				if (lor_dev[o].i_on) {
+					lab("lorentz_pre_I");
+					L.push_back([this, par, o](cudaStream_t s) { LorParams q = lor_dev[o].i; q.X = sI[par]; launch1d(k_lorentz_pre, q, q.count, s); });
+				}
+			}
 		// absorbing sheets: both pre hooks read timestep-n values -> the source set, before k_shell_E touches it
 		for (size_t a = 0; a < sheet_dev.size(); ++a) {
 			lab("sheet_pre_V");
@@ -1578,6 +1725,11 @@ void Engine::build_schedule_fused()
 			if (tma_active) {
 				const FusedTmaParams& t = pFT[par];
 				const int sm = i16 ? ft_smem_bytes<uint16_t, FT_STAGES>() : ft_smem_bytes<uint32_t, FT_STAGES>();
+				if (lor_fused) {
+					if (i16) { if (has_pml) k_fused_tma<uint16_t, true, FT_STAGES, true><<<g, block, sm, s>>>(t); else k_fused_tma<uint16_t, false, FT_STAGES, true><<<g, block, sm, s>>>(t); }
+					else { if (has_pml) k_fused_tma<uint32_t, true, FT_STAGES, true><<<g, block, sm, s>>>(t); else k_fused_tma<uint32_t, false, FT_STAGES, true><<<g, block, sm, s>>>(t); }
+					return;
+				}
 				if (i16) { if (has_pml) k_fused_tma<uint16_t, true, FT_STAGES><<<g, block, sm, s>>>(t); else k_fused_tma<uint16_t, false, FT_STAGES><<<g, block, sm, s>>>(t); }
 				else { if (has_pml) k_fused_tma<uint32_t, true, FT_STAGES><<<g, block, sm, s>>>(t); else k_fused_tma<uint32_t, false, FT_STAGES><<<g, block, sm, s>>>(t); }
 				return;
@@ -1612,7 +1764,7 @@ void Engine::build_schedule_fused()
 			lab("steadystate");
 			L.push_back([this, par](cudaStream_t s) {
 				const SsParams& q = pSsF[par];
-				k_ss_record<<<(q.count + 63) / 64, 64, 0, s>>>(q);
+				k_ss_record<<<std::max(1u, (q.count + 63) / 64), 64, 0, s>>>(q);
 				k_ss_energy<<<148 * 2, dim3(32, 8), 0, s>>>(q);
 				k_ss_snapshot<<<8, 256, 0, s>>>(q);
 			});
@@ -1665,6 +1817,17 @@ void Engine::build_schedule_fused()
 				if (i16) { if (has_pml) k_update_H<uint16_t, true><<<g, block, 0, s>>>(q); else k_update_H<uint16_t, false><<<g, block, 0, s>>>(q); }
 				else { if (has_pml) k_update_H<uint32_t, true><<<g, block, 0, s>>>(q); else k_update_H<uint32_t, false><<<g, block, 0, s>>>(q); }
 			});
+			if (lor_fused)
+				for (size_t o = 0; o < lor_dev.size(); ++o) {
+					if (!lor_dev[o].i_on || lor_dev[o].top_first >= lor_dev[o].i.count) continue;
+					lab("lorentz_apply_I_top");
+					L.push_back([this, par, o](cudaStream_t s) {
+						// Apply2Current for the dispersive cells of the top plane: the tail of the (z-sorted) list
+						LorParams q = lor_dev[o].i;
+						q.X = sI[par ^ 1]; q.first = lor_dev[o].top_first;
+						launch1d(k_lorentz_apply, q, q.count - q.first, s);
+					});
+				}
 		}
 		// ---- post-current hook of the TFSF box, then post / apply current hooks of the absorbing sheets: H of the
 		//      destination set is final here
@@ -1738,7 +1901,7 @@ bool Engine::fused_auto_choice() const
 // kernels work in place on set 0
 int Engine::set_fused_active(int req)
 {
-	const bool on = fused_possible && !edge_dirty && (req == 1 || (req < 0 && fused_auto_choice()));
+	const bool on = fused_possible && !edge_dirty && (req == 1 || (req < 0 && fused_auto_choice())) && !(lor_fused && !tma_req);
 	CK(cudaSetDevice(device));
 	CK(cudaStreamSynchronize(stream));
 	if (fused_active) flux_sets_sync(true);
@@ -1778,6 +1941,8 @@ int Engine::iterate(unsigned n)
 	CK(cudaSetDevice(device));
 	if (!probes_built && !h_probes.empty())
 		if (build_probes()) return 1;
+	if (ghost_open && n && release_ghosts()) return 1;
+	if (fused_active && !sched_error.empty()) return fail(sched_error);
 	for (unsigned it = 0; it < n; ++it) {
 		if (fused_active) {
 			const int par = (int)(numTS_host & 1u);
@@ -1828,6 +1993,7 @@ int Engine::set_option(const char* key, long long value)
 	if (k == "tma") {
 		// 1: the one-pass kernel stages its inputs through TMA (default), 0: register-staged loads
 		tma_req = value != 0;
+		if (finalized && lor_fused) return set_fused_active(fused_req); // the register-staged kernel has no ADE instance: two-pass
 		if (finalized) return rebuild_schedule();
 		return 0;
 	}
@@ -1937,7 +2103,8 @@ int Engine::reset()
 		CK(cudaMemsetAsync(pSs.info, 0, 2 * sizeof(unsigned), stream));
 	}
 	CK(cudaMemsetAsync(d_numTS, 0, sizeof(unsigned), stream));
-	CK(cudaMemsetAsync(d_flagE, 0, 8 * sizeof(unsigned), stream));
+	CK(cudaMemsetAsync(d_flagE, 0, FLAG_WORDS * sizeof(unsigned), stream));
+	ghost_seq = 0; ghost_ts = 0; ghost_open = false;
 	numTS_host = 0;
 	rec_count = 0;
 	rec_ts.clear();
@@ -2170,13 +2337,23 @@ int Engine::add_dump(int is_H, int interp, unsigned nx, unsigned ny, unsigned nz
 {
 	if (!finalized) return fail("add_dump: engine not finalized");
 	if (interp < 0 || interp > 2) return fail("add_dump: bad interpolation type");
-	if (slab_set) return fail("add_dump: dumps on a z-slab engine are not supported yet");
 	CK(cudaSetDevice(device));
 	for (unsigned i = 0; i < nx; ++i) if (px[i] >= gn[0]) return fail("add_dump: x index outside the mesh");
 	for (unsigned i = 0; i < ny; ++i) if (py[i] >= gn[1]) return fail("add_dump: y index outside the mesh");
 	for (unsigned i = 0; i < nz; ++i) if (pz[i] >= gn[2]) return fail("add_dump: z index outside the mesh");
 	DumpHost D;
 	memset(&D.p, 0, sizeof(D.p));
+	// a z-slab engine evaluates the z lines it owns: a contiguous piece [z_first, z_first + nz) of the caller's list
+	// (oems_cuda_dump_own_range), in the caller's output order; the host concatenates the slabs along z
+	D.z_first = 0;
+	if (slab_set) {
+		for (unsigned i = 1; i < nz; ++i) if (pz[i] <= pz[i - 1]) return fail("add_dump: on a z-slab engine the z lines must ascend");
+		unsigned a = 0, b = nz;
+		while (a < nz && pz[a] < zb) ++a;
+		b = a;
+		while (b < nz && pz[b] < ze) ++b;
+		D.z_first = a; pz += a; nz = b - a;
+	}
 	D.count = (size_t)nx * ny * nz;
 	D.p.V = d_V; D.p.I = d_I;
 	D.p.px = upload(std::vector<unsigned>(px, px + nx));
@@ -2186,16 +2363,24 @@ int Engine::add_dump(int is_H, int interp, unsigned nx, unsigned ny, unsigned nz
 		D.p.el[a] = upload(std::vector<double>(el[a], el[a] + gn[a]));
 		D.p.del[a] = upload(std::vector<double>(del[a], del[a] + gn[a]));
 	}
-	D.d_out = dalloc<float>(3 * D.count);
+	D.d_out = dalloc<float>(std::max<size_t>(1, 3 * D.count));
 	D.p.out = D.d_out;
 	D.p.is_H = is_H; D.p.interp = interp;
 	D.p.onx = nx; D.p.ony = ny; D.p.onz = nz;
 	D.p.nx = (int)gn[0]; D.p.ny = (int)gn[1]; D.p.gnz = (int)gn[2]; D.p.z0 = z0;
 	D.p.pitch = pitch; D.p.plane = plane; D.p.comp = comp;
 	D.h_pinned = nullptr;
-	CK(cudaMallocHost(&D.h_pinned, 3 * D.count * sizeof(float)));
+	CK(cudaMallocHost(&D.h_pinned, std::max<size_t>(1, 3 * D.count) * sizeof(float)));
 	if (id) *id = (int)dumps.size();
 	dumps.push_back(D);
+	return 0;
+}
+
+int Engine::dump_own_range(int id, unsigned* first, unsigned* n)
+{
+	if (id < 0 || id >= (int)dumps.size()) return fail("dump_own_range: bad id");
+	if (first) *first = dumps[id].z_first;
+	if (n) *n = dumps[id].p.onz;
 	return 0;
 }
 
@@ -2226,12 +2411,12 @@ int Engine::read_dump_async(int id, float* pinned_out, long long* ticket)
 		CK(cudaEventCreateWithFlags(&D.ev_copied, cudaEventDisableTiming));
 	}
 	if (D.copy_pending) CK(cudaStreamWaitEvent(stream, D.ev_copied, 0)); // d_out still being read by the last copy
+	if (ghosts_for_readout()) return 1;
 	D.p.V = sV[cur()]; D.p.I = sI[cur()];
-	launch1d(k_dump, D.p, (long long)D.count, stream);
-	++kernels_launched;
+	if (D.count) { launch1d(k_dump, D.p, (long long)D.count, stream); ++kernels_launched; }
 	CK(cudaEventRecord(D.ev_computed, stream));
 	CK(cudaStreamWaitEvent(copy_stream, D.ev_computed, 0));
-	CK(cudaMemcpyAsync(pinned_out, D.d_out, 3 * D.count * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
+	if (D.count) CK(cudaMemcpyAsync(pinned_out, D.d_out, 3 * D.count * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
 	CK(cudaEventRecord(D.ev_copied, copy_stream));
 	D.copy_pending = true;
 	++D.seq;
@@ -2264,13 +2449,13 @@ int Engine::add_fd_dump(int dump_id, unsigned nfreq, int* id)
 	FdHost F;
 	F.dump = dump_id; F.nfreq = nfreq; F.samples = 0;
 	const size_t n = 3 * dumps[dump_id].count;
-	F.d_acc = dalloc<float2>(n * nfreq);
+	F.d_acc = dalloc<float2>(std::max<size_t>(1, n * nfreq));
 	F.d_w = dalloc<float2>((size_t)FdHost::RING * nfreq);
 	if (!F.d_acc || !F.d_w) return fail("out of device memory (FD dump)");
 	F.h_w = nullptr;
 	CK(cudaMallocHost((void**)&F.h_w, (size_t)FdHost::RING * nfreq * sizeof(float2)));
 	for (int r = 0; r < FdHost::RING; ++r) CK(cudaEventCreateWithFlags(&F.ev[r], cudaEventDisableTiming));
-	CK(cudaMemsetAsync(F.d_acc, 0, n * nfreq * sizeof(float2), stream));
+	if (n) CK(cudaMemsetAsync(F.d_acc, 0, n * nfreq * sizeof(float2), stream));
 	if (id) *id = (int)fds.size();
 	fds.push_back(F);
 	return 0;
@@ -2291,14 +2476,14 @@ int Engine::fd_accumulate(int fd_id, const float* w)
 	float2* dw = F.d_w + (size_t)slot * F.nfreq;
 	memcpy(hw, w, F.nfreq * sizeof(float2));
 	if (D.copy_pending) CK(cudaStreamWaitEvent(stream, D.ev_copied, 0));
+	if (ghosts_for_readout()) return 1;
 	D.p.V = sV[cur()]; D.p.I = sI[cur()];
-	launch1d(k_dump, D.p, (long long)D.count, stream);
+	if (D.count) launch1d(k_dump, D.p, (long long)D.count, stream);
 	CK(cudaMemcpyAsync(dw, hw, F.nfreq * sizeof(float2), cudaMemcpyHostToDevice, stream));
 	CK(cudaEventRecord(F.ev[slot], stream));
 	FdParams q;
 	q.td = D.d_out; q.acc = F.d_acc; q.w = dw; q.n = (long long)(3 * D.count); q.nfreq = F.nfreq;
-	launch1d(k_fd_accumulate, q, q.n, stream);
-	kernels_launched += 2;
+	if (D.count) { launch1d(k_fd_accumulate, q, q.n, stream); kernels_launched += 2; }
 	++F.samples;
 	return 0;
 }
@@ -2309,7 +2494,7 @@ int Engine::read_fd(int fd_id, float* out, unsigned* samples)
 	CK(cudaSetDevice(device));
 	FdHost& F = fds[fd_id];
 	const size_t n = 3 * dumps[F.dump].count * F.nfreq;
-	if (out) CK(cudaMemcpyAsync(out, F.d_acc, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+	if (out && n) CK(cudaMemcpyAsync(out, F.d_acc, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
 	CK(cudaStreamSynchronize(stream));
 	if (samples) *samples = F.samples;
 	return 0;
@@ -2323,7 +2508,6 @@ int Engine::add_mode_match(int is_H, int ny, const unsigned start[3], const unsi
                            const double* dist1, const double* area, const double* const el[3], const double* const del[3], int* id)
 {
 	if (!finalized) return fail("add_mode_match: engine not finalized");
-	if (slab_set) return fail("add_mode_match: not supported on a z-slab engine yet");
 	if (ny < 0 || ny > 2 || !dist0 || !dist1 || !area) return fail("add_mode_match: bad arguments");
 	for (int a = 0; a < 3; ++a)
 		if (start[a] > stop[a] || stop[a] >= gn[a]) return fail("add_mode_match: box outside the mesh");
@@ -2347,24 +2531,94 @@ int Engine::add_mode_match(int is_H, int ny, const unsigned start[3], const unsi
 	M.dist0 = upload(std::vector<double>(dist0, dist0 + n));
 	M.dist1 = upload(std::vector<double>(dist1, dist1 + n));
 	M.area = upload(std::vector<double>(area, area + n));
-	M.out = dalloc<double>(2);
+	M.out = dalloc<double>(3);
+	M.own_z0 = (int)zb; M.own_z1 = (int)ze; // a z-slab engine integrates over the planes it owns (read_mode_match_raw)
 	if (!M.dist0 || !M.dist1 || !M.area || !M.out) return fail("out of device memory (mode match)");
 	if (id) *id = (int)modes.size();
 	modes.push_back(M);
 	return 0;
 }
 
-int Engine::read_mode_match(int id, double out[2])
+int Engine::read_mode_match_raw(int id, double out[3])
 {
 	if (id < 0 || id >= (int)modes.size()) return fail("read_mode_match: bad id");
 	CK(cudaSetDevice(device));
 	ModeParams& M = modes[id];
+	if (ghosts_for_readout()) return 1;
 	M.d.V = sV[cur()]; M.d.I = sI[cur()];
 	k_mode_match<<<1, 32, 0, stream>>>(M);
 	++kernels_launched;
-	CK(cudaMemcpyAsync(out, M.out, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+	CK(cudaMemcpyAsync(out, M.out, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
 	CK(cudaStreamSynchronize(stream));
 	return 0;
+}
+
+int Engine::read_mode_match(int id, double out[2])
+{
+	double r[3];
+	if (read_mode_match_raw(id, r)) return 1;
+	out[0] = r[0]; out[1] = r[1];
+	return 0;
+}
+
+// ------------------------------------------------------------------------------ complete ghost planes
+// z-slab engines: before an interpolating readout both ghost planes are completed (all components of E and H, see
+// k_ghost_push).  Only enqueues.  One exchange serves every readout of the same timestep.  Protocol per slab:
+//   push my lowest / highest owned plane -> publish exchange number q in the neighbours' flags -> wait for theirs
+//   ... readout kernels ...
+//   (release, enqueued by the next iterate / exchange) publish "done reading q" -> wait for the neighbours' "done":
+//   only then may this slab's time loop write into the neighbours' ghost planes again.
+// Why the pushes cannot disturb a neighbour that lags: a slab that has finished timestep n has consumed its
+// neighbours' step-n halos, so both neighbours are past the phases of step n that read the ghost values the push
+// rewrites, and those values are rewritten with the same bits.
+int Engine::exchange_ghosts()
+{
+	if (!finalized) return fail("exchange_ghosts: engine not finalized");
+	if (!peers_linked) return 0;
+	CK(cudaSetDevice(device));
+	if (ghost_open && ghost_ts == numTS_host) return 0;
+	if (ghost_open && release_ghosts()) return 1;
+	if (peer_lo && !peer_lo_Is[0]) return fail("exchange_ghosts: the lower neighbour's buffers are not mapped");
+	++ghost_seq;
+	const int c = cur();
+	if (peer_lo) {
+		GhostPushParams g{sV[c], sI[c], peer_lo_Vs[c], peer_lo_Is[c], (long long)((int)zb - z0) * plane, peer_lo_ghostE_off, comp, peer_lo_comp,
+		                  plane, d_flagE + FLAG_GCNT, peer_lo_flags + FLAG_G_HI, ghost_seq};
+		k_ghost_push<<<64, 256, 0, stream>>>(g);
+	}
+	if (peer_hi) {
+		GhostPushParams g{sV[c], sI[c], peer_hi_Vs[c], peer_hi_Is[c], (long long)((int)ze - 1 - z0) * plane, peer_hi_ghostH_off, comp, peer_hi_comp,
+		                  plane, d_flagE + FLAG_GCNT + 1, peer_hi_flags + FLAG_G_LO, ghost_seq};
+		k_ghost_push<<<64, 256, 0, stream>>>(g);
+	}
+	FlagParams w{{peer_lo ? d_flagE + FLAG_G_LO : nullptr, peer_hi ? d_flagE + FLAG_G_HI : nullptr}, ghost_seq, d_halo_err, halo_timeout_cycles()};
+	k_flag_wait<<<1, 1, 0, stream>>>(w);
+	kernels_launched += 1 + (peer_lo != nullptr) + (peer_hi != nullptr);
+	ghost_open = true;
+	ghost_ts = numTS_host;
+	CK(cudaGetLastError());
+	return 0;
+}
+
+int Engine::release_ghosts()
+{
+	if (!ghost_open) return 0;
+	CK(cudaSetDevice(device));
+	FlagParams a{{peer_lo ? peer_lo_flags + FLAG_ACK_HI : nullptr, peer_hi ? peer_hi_flags + FLAG_ACK_LO : nullptr}, ghost_seq, d_halo_err, 0};
+	k_flag_set<<<1, 1, 0, stream>>>(a);
+	FlagParams w{{peer_lo ? d_flagE + FLAG_ACK_LO : nullptr, peer_hi ? d_flagE + FLAG_ACK_HI : nullptr}, ghost_seq, d_halo_err, halo_timeout_cycles()};
+	k_flag_wait<<<1, 1, 0, stream>>>(w);
+	kernels_launched += 2;
+	ghost_open = false;
+	CK(cudaGetLastError());
+	return 0;
+}
+
+// readers call this: a slab with neighbours needs complete ghost planes of the current timestep
+int Engine::ghosts_for_readout()
+{
+	if (!peers_linked) return 0;
+	return exchange_ghosts();
 }
 
 // ------------------------------------------------------------------------------ field access
@@ -2594,6 +2848,19 @@ int Engine::open_peers(const unsigned char* lower, const unsigned char* upper)
 			peer_lo_Vs[1] = (float*)pV1;
 		} else fused_possible = false;
 		peer_lo_flagE = (unsigned*)pF; // neighbour's flagE
+		peer_lo_flags = (unsigned*)pF;
+		{   // the other field of the neighbour: only the ghost exchange of the readout writes it
+			void* pI = nullptr;
+			CK(cudaIpcOpenMemHandle(&pI, b.hI, cudaIpcMemLazyEnablePeerAccess));
+			ipc_opened.push_back(pI);
+			peer_lo_Is[0] = (float*)pI; peer_lo_Is[1] = nullptr;
+			if (b.has_set1) {
+				void* pI1 = nullptr;
+				CK(cudaIpcOpenMemHandle(&pI1, b.hI1, cudaIpcMemLazyEnablePeerAccess));
+				ipc_opened.push_back(pI1);
+				peer_lo_Is[1] = (float*)pI1;
+			}
+		}
 		peer_lo_comp = b.comp;
 		peer_lo_ghostE_off = (long long)((int)zb - b.z0) * plane;
 		peer_lo = this; // marker: has a lower neighbour
@@ -2615,6 +2882,19 @@ int Engine::open_peers(const unsigned char* lower, const unsigned char* upper)
 			peer_hi_Is[1] = (float*)pI1;
 		} else fused_possible = false;
 		peer_hi_flagH = (unsigned*)pF + 1; // neighbour's flagH
+		peer_hi_flags = (unsigned*)pF;
+		{
+			void* pV = nullptr;
+			CK(cudaIpcOpenMemHandle(&pV, b.hV, cudaIpcMemLazyEnablePeerAccess));
+			ipc_opened.push_back(pV);
+			peer_hi_Vs[0] = (float*)pV; peer_hi_Vs[1] = nullptr;
+			if (b.has_set1) {
+				void* pV1 = nullptr;
+				CK(cudaIpcOpenMemHandle(&pV1, b.hV1, cudaIpcMemLazyEnablePeerAccess));
+				ipc_opened.push_back(pV1);
+				peer_hi_Vs[1] = (float*)pV1;
+			}
+		}
 		peer_hi_comp = b.comp;
 		peer_hi_ghostH_off = (long long)((int)ze - 1 - b.z0) * plane;
 		peer_hi = this;
@@ -2646,6 +2926,8 @@ int Engine::link_peers(Engine* lower, Engine* upper)
 		if (lower->pitch != pitch || lower->ze != zb) return fail("link_peers: lower neighbour does not match");
 		peer_lo_V = lower->d_V; peer_lo_flagE = lower->d_flagE; peer_lo_comp = lower->comp;
 		peer_lo_Vs[0] = lower->sV[0]; peer_lo_Vs[1] = lower->sV[1];
+		peer_lo_Is[0] = lower->sI[0]; peer_lo_Is[1] = lower->sI[1];
+		peer_lo_flags = lower->d_flagE;
 		if (!lower->sV[1] || !lower->fused_possible) fused_possible = false;
 		peer_lo_ghostE_off = (long long)((int)zb - lower->z0) * plane;
 	}
@@ -2653,6 +2935,8 @@ int Engine::link_peers(Engine* lower, Engine* upper)
 		if (upper->pitch != pitch || upper->zb != ze) return fail("link_peers: upper neighbour does not match");
 		peer_hi_I = upper->d_I; peer_hi_flagH = upper->d_flagH; peer_hi_comp = upper->comp;
 		peer_hi_Is[0] = upper->sI[0]; peer_hi_Is[1] = upper->sI[1];
+		peer_hi_Vs[0] = upper->sV[0]; peer_hi_Vs[1] = upper->sV[1];
+		peer_hi_flags = upper->d_flagE;
 		if (!upper->sI[1] || !upper->fused_possible) fused_possible = false;
 		peer_hi_ghostH_off = (long long)((int)ze - 1 - upper->z0) * plane;
 	}

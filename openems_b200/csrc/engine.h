@@ -50,6 +50,7 @@ struct ProbeHost {
 struct DumpHost {
 	DumpParams p;
 	size_t count;
+	unsigned z_first = 0;   // z-slab engines: first entry of the caller's z list this engine evaluates
 	float* d_out;
 	float* h_pinned;
 	std::vector<void*> dev_allocs;
@@ -90,6 +91,9 @@ struct FdHost {
 struct LorDev {
 	LorParams v, i;
 	bool v_on, i_on;
+	int2* d_rows = nullptr;          // one-pass schedule: per (local plane, row) {x0 | n << 16, first list index}
+	std::vector<int2> h_rows;
+	unsigned top_first = 0;          // list entries [top_first, count) lie on the slab's top owned plane
 };
 
 class Engine {
@@ -112,6 +116,10 @@ public:
 	int add_rlc(unsigned count, const int* dir, const unsigned* pos3, const float* const c[9]);
 	int add_steadystate(unsigned period_ts, unsigned count, const unsigned* pos3, const unsigned* dir);
 	int steadystate_check(double* last_diff, unsigned* n_checks);
+	int steadystate_raw(unsigned info[2], double en[4], double* snap, unsigned cap, unsigned* count);
+	static int steadystate_eval(unsigned period, unsigned count, const unsigned info[2], const double en[4], const double* snap, double* last_diff);
+	int dump_own_range(int id, unsigned* first, unsigned* n);
+	int read_mode_match_raw(int id, double out[3]);
 	int finalize();
 
 	int iterate(unsigned n);
@@ -225,6 +233,9 @@ private:
 	MurParams pMur{};
 	ExcParams pExc[2]{};
 	std::vector<LorDev> lor_dev;
+	bool lor_fused = false;          // Lorentz/Drude ADE applied inside the one-pass kernel (kernels_fused_tma.cuh, LOR)
+	bool lorentz_fusable() const;
+	std::string sched_error;         // a schedule that cannot run (reported by iterate)
 	std::vector<RlcParams> rlc_dev;
 	// probes
 	ProbeParams pProbe{};
@@ -303,6 +314,18 @@ private:
 	bool peers_linked = false;
 	int halo_timeout_s = 600;
 	long long halo_timeout_cycles() const;
+	// complete ghost planes for the readout (k_ghost_push): the neighbours' other field bases and the flags
+	float *peer_lo_Is[2] = {nullptr, nullptr}, *peer_hi_Vs[2] = {nullptr, nullptr};
+	unsigned *peer_lo_flags = nullptr, *peer_hi_flags = nullptr; // the neighbours' flag blocks (index: FLAG_*)
+	enum { FLAG_E = 0, FLAG_H = 1, FLAG_CNT = 2, FLAG_ERR = 4, FLAG_G_LO = 5, FLAG_G_HI = 6, FLAG_ACK_LO = 7, FLAG_ACK_HI = 8, FLAG_GCNT = 9, FLAG_WORDS = 16 };
+	unsigned ghost_seq = 0;       // exchanges issued so far
+	unsigned ghost_ts = 0;        // numTS of the last one
+	bool ghost_open = false;      // the neighbours have not been told yet that this slab is done reading
+	int ghosts_for_readout();
+public:
+	int exchange_ghosts();
+	int release_ghosts();
+private:
 	std::vector<void*> ipc_opened;
 
 	template <typename T> T* dalloc(size_t n, bool zero = true);

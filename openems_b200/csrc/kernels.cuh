@@ -479,6 +479,7 @@ struct LorParams {
 	float* lor_ade;         // [3][count] or NULL
 	unsigned count;
 	long long comp;
+	unsigned first;         // k_lorentz_apply: entries [first, count) only (the slab's top plane in the one-pass schedule)
 };
 __global__ void k_lorentz_pre(const __grid_constant__ LorParams p)
 {
@@ -504,7 +505,7 @@ __global__ void k_lorentz_pre(const __grid_constant__ LorParams p)
 }
 __global__ void k_lorentz_apply(const __grid_constant__ LorParams p)
 {
-	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned i = p.first + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= p.count) return;
 	const long long c = p.cell[i];
 #pragma unroll
@@ -1039,7 +1040,8 @@ struct ModeParams {
 	const double* dist0;   // [nl0*nl1] normalised mode template of component nP
 	const double* dist1;   // component nPP
 	const double* area;    // Op->GetNodeArea(ny, pos, dualMesh)
-	double* out;           // [2]: value, value^2 / purity
+	double* out;           // [3]: value, value^2 / purity, purity (raw sum: z-slab partial results are added on the host)
+	int own_z0, own_z1;    // only points with own_z0 <= z < own_z1 contribute (the planes a z-slab engine owns)
 };
 __global__ void k_mode_match(const __grid_constant__ ModeParams p)
 {
@@ -1055,11 +1057,13 @@ __global__ void k_mode_match(const __grid_constant__ ModeParams p)
 			pos[p.ny] = p.line;
 			pos[nP] = p.startP + (int)(q / p.nl1);
 			pos[nPP] = p.startPP + (int)(q % p.nl1);
-			double f[3];
-			field_interp(p.d, pos, f);
-			const double a = p.area[q], f0 = f[nP], f1 = f[nPP];
-			tv0 = __dmul_rn(__dmul_rn(f0, p.dist0[q]), a); tp0 = __dmul_rn(__dmul_rn(f0, f0), a);
-			tv1 = __dmul_rn(__dmul_rn(f1, p.dist1[q]), a); tp1 = __dmul_rn(__dmul_rn(f1, f1), a);
+			if (pos[2] >= p.own_z0 && pos[2] < p.own_z1) {
+				double f[3];
+				field_interp(p.d, pos, f);
+				const double a = p.area[q], f0 = f[nP], f1 = f[nPP];
+				tv0 = __dmul_rn(__dmul_rn(f0, p.dist0[q]), a); tp0 = __dmul_rn(__dmul_rn(f0, f0), a);
+				tv1 = __dmul_rn(__dmul_rn(f1, p.dist1[q]), a); tp1 = __dmul_rn(__dmul_rn(f1, f1), a);
+			}
 		}
 		const unsigned cnt = min(32u, npts - base);
 		for (unsigned s = 0; s < cnt; ++s) {
@@ -1072,6 +1076,7 @@ __global__ void k_mode_match(const __grid_constant__ ModeParams p)
 	if (lane == 0) {
 		p.out[0] = value;
 		p.out[1] = purity != 0.0 ? __ddiv_rn(__dmul_rn(value, value), purity) : 0.0;
+		p.out[2] = purity;
 	}
 }
 
@@ -1133,6 +1138,81 @@ __global__ void k_halo_wait(const __grid_constant__ WaitParams p)
 			__trap();
 		}
 		__nanosleep(200);
+	}
+	__threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------------
+// Complete ghost planes for the readout (field dumps, FD dumps, mode matching on z-slab engines): the time
+// loop only exchanges what the stencil needs (tangential E down, tangential H up).  The interpolating
+// readers (engine_interface_fdtd.cpp:63-124,150-204) also take the normal components and E of the plane
+// below / H of the plane above, so before a readout every slab pushes all three components of E AND H of its
+// lowest owned plane into the lower neighbour's upper ghost plane and of its highest owned plane into the upper
+// neighbour's lower ghost plane, then publishes the exchange number.  The values the time loop reads from the
+// ghost planes are rewritten with the same bits; the parts it never reads (E below, H above, normal
+// components) are free.  Template: the full-plane exchange Engine_MPI does every timestep
+// (engine_mpi.cpp:84-182).
+// ---------------------------------------------------------------------------------------
+struct GhostPushParams {
+	const float* srcV; const float* srcI;   // local field bases
+	float* dstV; float* dstI;               // peer field bases (mapped)
+	long long src_plane_off, dst_plane_off;
+	long long src_comp, dst_comp;
+	long long n;                            // floats per plane, multiple of 4
+	unsigned* done_counter;
+	volatile unsigned* peer_flag;
+	unsigned value;
+};
+__global__ void k_ghost_push(const __grid_constant__ GhostPushParams p)
+{
+	const long long n4 = p.n / 4;
+	for (int c = 0; c < 6; ++c) {
+		const float* sb = c < 3 ? p.srcV : p.srcI;
+		float* db = c < 3 ? p.dstV : p.dstI;
+		const float4* s = reinterpret_cast<const float4*>(sb + (c % 3) * p.src_comp + p.src_plane_off);
+		float4* d = reinterpret_cast<float4*>(db + (c % 3) * p.dst_comp + p.dst_plane_off);
+		for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x)
+			d[q] = s[q];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const unsigned prev = atomicAdd(p.done_counter, 1u);
+		if (prev == gridDim.x - 1) {
+			*p.done_counter = 0;
+			__threadfence_system();
+			*p.peer_flag = p.value;
+			__threadfence_system();
+		}
+	}
+}
+// publish / wait for an exchange number (flags of the ghost exchange; the step flags use k_halo_wait)
+struct FlagParams {
+	volatile unsigned* flag[2];
+	unsigned value;
+	unsigned* error;
+	long long timeout_cycles;
+};
+__global__ void k_flag_set(const __grid_constant__ FlagParams p)
+{
+	__threadfence_system();
+	for (int q = 0; q < 2; ++q)
+		if (p.flag[q]) *p.flag[q] = p.value;
+	__threadfence_system();
+}
+__global__ void k_flag_wait(const __grid_constant__ FlagParams p)
+{
+	const long long t0 = clock64();
+	for (int q = 0; q < 2; ++q) {
+		if (!p.flag[q]) continue;
+		while ((int)(*p.flag[q] - p.value) < 0) {
+			if (clock64() - t0 > p.timeout_cycles) {
+				*p.error = 1;
+				__threadfence_system();
+				__trap();
+			}
+			__nanosleep(200);
+		}
 	}
 	__threadfence_system();
 }

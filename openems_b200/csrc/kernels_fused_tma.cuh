@@ -37,7 +37,24 @@ struct XSlabFoot {
 	int x0, x1;          // lines of the box itself [x0, x1)
 };
 
+// Lorentz / Drude ADE applied inside the one-pass kernel (template flag LOR): per order the auxiliary values the list
+// kernels k_lorentz_pre have just advanced (engine_ext_lorentzmaterial.cpp:79-127), and per (plane, row) the one x
+// segment of dispersive cells: rows[k * ny + j] = {x0 | n << 16, list index of the first}.  E_new = stencil - ADE
+// (Apply2Voltages, :129-148) before H is computed from it, H_new = stencil - ADE (Apply2Current, :150-168).
+#define LOR_FUSED_MAX 2
+struct LorFusedOrder {
+	const int2* rows;
+	const float* ade_v;   // [3][count] or NULL
+	const float* ade_i;
+	unsigned count;
+};
+struct LorFusedParams {
+	int nord;
+	LorFusedOrder o[LOR_FUSED_MAX];
+};
+
 struct alignas(64) FusedTmaParams {
+	LorFusedParams lor;
 	XSlabFoot xs[2];
 	CUtensorMap mI;   // H_old of the source set: (x, y, z, component) float, box 136 x 9 x 1 x 3
 	CUtensorMap mV;   // E_old of the source set (shell cells: already E_new), box 136 x 8 x 1 x 3
@@ -107,7 +124,7 @@ template <> struct SIdx4<uint32_t> {
 	}
 };
 
-template <typename IdxT, bool HAS_PML, int STAGES>
+template <typename IdxT, bool HAS_PML, int STAGES, bool LOR = false>
 __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tma(const __grid_constant__ FusedTmaParams P)
 {
 	extern __shared__ __align__(128) unsigned char ft_smem[];
@@ -198,8 +215,18 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 		if (hcol) hcI0 = p.Is[o + 4];
 	}
 
+	int2 lorR[LOR ? LOR_FUSED_MAX : 1], lorRk[LOR ? LOR_FUSED_MAX : 1]; // row segments of plane kk / plane kk-1
+	if (LOR)
+		for (int o = 0; o < LOR_FUSED_MAX; ++o) lorR[o] = lorRk[o] = make_int2(0, 0);
+	const long long lor_row = row_ok ? j : p.ny - 1;
+
 	for (int kk = kb; kk <= e_last; ++kk) {
 		// ------------------------------------------------------------ E_new(kk)
+		if (LOR) {
+#pragma unroll
+			for (int o = 0; o < LOR_FUSED_MAX; ++o)
+				if (o < P.lor.nord) lorR[o] = __ldg(P.lor.o[o].rows + (long long)kk * p.ny + lor_row);
+		}
 		const int s = (kk - kb) % STAGES;
 		mbar_wait(bar0 + 8 * s, ((kk - kb) / STAGES) & 1);
 		const unsigned char* stg = ft_smem + s * ST::BYTES;
@@ -238,6 +265,23 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 				setcomp(v1, c, sh ? comp(v1, c) : n1);
 				setcomp(v2, c, sh ? comp(v2, c) : n2);
 			}
+			if (LOR) {
+#pragma unroll
+				for (int o = 0; o < LOR_FUSED_MAX; ++o) {
+					const LorFusedOrder& Lo = P.lor.o[o];
+					const int d = ic - (lorR[o].x & 0xffff), n = lorR[o].x >> 16;
+					if (o < P.lor.nord && Lo.ade_v && d + 3 >= 0 && d < n) {
+						const float* a = Lo.ade_v + lorR[o].y + d;
+#pragma unroll
+						for (int c = 0; c < 4; ++c)
+							if ((unsigned)(d + c) < (unsigned)n) {
+								setcomp(v0, c, fsub(comp(v0, c), __ldg(a + c)));
+								setcomp(v1, c, fsub(comp(v1, c), __ldg(a + c + Lo.count)));
+								setcomp(v2, c, fsub(comp(v2, c), __ldg(a + c + 2ll * Lo.count)));
+							}
+					}
+				}
+			}
 			if (!halo_row && kk < ke) {
 				const long long o = (long long)kk * p.plane + row;
 				if (!xsc) { // x-slab chunks are stored by k_xslab_EH
@@ -257,6 +301,18 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 				const float n1 = leap(b1, Ax.y, Bx.y, c1x), n2 = leap(b2, Ax.z, Bx.z, c2x);
 				nV1 = shx ? b1 : n1;
 				nV2 = shx ? b2 : n2;
+				if (LOR) {
+#pragma unroll
+					for (int o = 0; o < LOR_FUSED_MAX; ++o) {
+						const LorFusedOrder& Lo = P.lor.o[o];
+						const int d = xe - (lorR[o].x & 0xffff), n = lorR[o].x >> 16;
+						if (o < P.lor.nord && Lo.ade_v && (unsigned)d < (unsigned)n) {
+							const float* a = Lo.ade_v + lorR[o].y + d;
+							nV1 = fsub(nV1, __ldg(a + Lo.count));
+							nV2 = fsub(nV2, __ldg(a + 2ll * Lo.count));
+						}
+					}
+				}
 				nI0 = xi0;
 			}
 		}
@@ -293,6 +349,25 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 					}
 				}
 			}
+			if (LOR && k < he) {
+				// Apply2Current on the planes this kernel updates (the slab's top plane: list kernel after update_H_top);
+				// cells whose H is never updated carry a zero ADE
+#pragma unroll
+				for (int o = 0; o < LOR_FUSED_MAX; ++o) {
+					const LorFusedOrder& Lo = P.lor.o[o];
+					const int d = ic - (lorRk[o].x & 0xffff), n = lorRk[o].x >> 16;
+					if (o < P.lor.nord && Lo.ade_i && d + 3 >= 0 && d < n) {
+						const float* a = Lo.ade_i + lorRk[o].y + d;
+#pragma unroll
+						for (int c = 0; c < 4; ++c)
+							if ((unsigned)(d + c) < (unsigned)n) {
+								setcomp(c0, c, fsub(comp(c0, c), __ldg(a + c)));
+								setcomp(c1, c, fsub(comp(c1, c), __ldg(a + c + Lo.count)));
+								setcomp(c2, c, fsub(comp(c2, c), __ldg(a + c + 2ll * Lo.count)));
+							}
+					}
+				}
+			}
 			if (k < p.kHc1) {
 				if (!xsk) {
 					st4(p.Id + oh, c0);
@@ -308,6 +383,8 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 		for (int c = 0; c < 4; ++c) ek_idx[c] = e[c];
 		hcV1 = nV1; hcV2 = nV2; hcI0 = nI0;
 		shk = sh; xsk = xsc;
+		if (LOR)
+			for (int o = 0; o < LOR_FUSED_MAX; ++o) lorRk[o] = lorR[o];
 	}
 	const int k = e_last;
 	if (k == ke - 1 && k >= kb && !halo_row && active && k < p.kHc1) {

@@ -250,6 +250,7 @@ class Engine_CUDA:
                                                          None if k2p is None else _ptr(k2p, _fp), None if k2pp is None else _ptr(k2pp, _fp)))
             if op.steadystate is not None:
                 per, pos3, d = op.steadystate
+                self._ss_period = per
                 self._ck(L.oems_cuda_add_steadystate(h, per, len(d), _ptr(pos3, _up), _ptr(d, _up)))
             self._ck(L.oems_cuda_finalize(h))
         self._initialized = True
@@ -394,12 +395,31 @@ class Engine_CUDA:
                                             _ptr(px, _up), _ptr(py, _up), _ptr(pz, _up), elp, dlp, C.byref(i)))
         if not hasattr(self, "_dump_shapes"):
             self._dump_shapes = {}
-        self._dump_shapes[i.value] = (3, len(pz), len(py), len(px))
+        first, n = C.c_uint(), C.c_uint()
+        self._ck(self._L.oems_cuda_dump_own_range(self._h, i.value, C.byref(first), C.byref(n)))
+        self._dump_shapes[i.value] = (3, n.value, len(py), len(px))   # a z-slab engine dumps the z lines it owns
+        if not hasattr(self, "_dump_own"):
+            self._dump_own = {}
+        self._dump_own[i.value] = (first.value, n.value)
         return i.value
+
+    def DumpOwnRange(self, dump_id):
+        """(first, n): the entries of the dump's z list this engine evaluates (all of them on a single GPU)"""
+        return self._dump_own[dump_id]
+
+    def ExchangeGhosts(self):
+        """z-slab engines: complete the neighbours' ghost planes for an interpolating readout (enqueue only; collective)"""
+        self._ck(self._L.oems_cuda_exchange_ghosts(self._h))
+
+    def ReleaseGhosts(self):
+        self._ck(self._L.oems_cuda_release_ghosts(self._h))
 
     def ReadDump(self, dump_id):
         out = np.zeros(self._dump_shapes[dump_id], np.float32)
-        self._ck(self._L.oems_cuda_read_dump(self._h, dump_id, _ptr(out, _fp)))
+        if out.size:
+            self._ck(self._L.oems_cuda_read_dump(self._h, dump_id, _ptr(out, _fp)))
+        else:   # a slab that owns none of the box still takes part in the ghost exchange
+            self.ExchangeGhosts()
         return out
 
     def FillFields(self, seed=0):
@@ -423,7 +443,7 @@ class Engine_CUDA:
             self._dump_pinned = {}
         if dump_id not in self._dump_pinned:
             p = C.c_void_p()
-            if self._L.oems_cuda_host_alloc(int(np.prod(shape)) * 4, C.byref(p)):
+            if self._L.oems_cuda_host_alloc(max(1, int(np.prod(shape))) * 4, C.byref(p)):
                 raise EngineError("oems_cuda_host_alloc failed")
             self._dump_pinned[dump_id] = p
         t = C.c_longlong()
@@ -434,6 +454,8 @@ class Engine_CUDA:
         dump_id, t = ticket
         self._ck(self._L.oems_cuda_wait(self._h, t))
         shape = self._dump_shapes[dump_id]
+        if not int(np.prod(shape)):
+            return np.zeros(shape, np.float32)
         buf = (C.c_float * int(np.prod(shape))).from_address(self._dump_pinned[dump_id].value)
         return np.frombuffer(buf, np.float32).reshape(shape).copy()
 
@@ -458,7 +480,7 @@ class Engine_CUDA:
         """the accumulated spectra, complex64 [n_freq][3][nz][ny][nx], and the sample count"""
         out = np.zeros(self._fd_shapes[fd_id], np.complex64)
         n = C.c_uint()
-        self._ck(self._L.oems_cuda_read_fd(self._h, fd_id, _ptr(out.view(np.float32), _fp), C.byref(n)))
+        self._ck(self._L.oems_cuda_read_fd(self._h, fd_id, _ptr(out.view(np.float32), _fp) if out.size else None, C.byref(n)))
         return out, n.value
 
     def AddModeMatch(self, is_H, ny, start, stop, dist0, dist1, area, edge_len, dual_edge_len):
@@ -479,6 +501,24 @@ class Engine_CUDA:
         out = np.zeros(2, np.float64)
         self._ck(self._L.oems_cuda_read_mode_match(self._h, mode_id, _ptr(out, _dp)))
         return float(out[0]), float(out[1])
+
+    def ReadModeMatchRaw(self, mode_id):
+        """(value, value^2/purity, purity) over the planes this engine owns (z-slab partial result)"""
+        out = np.zeros(3, np.float64)
+        self._ck(self._L.oems_cuda_read_mode_match_raw(self._h, mode_id, _ptr(out, _dp)))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def SteadyStateRaw(self):
+        """(info[2], energy[4], snap[2*period][count]) of this engine: see oems_cuda_steadystate_raw"""
+        info = np.zeros(2, np.uint32)
+        en = np.zeros(4, np.float64)
+        cnt = C.c_uint()
+        self._ck(self._L.oems_cuda_steadystate_raw(self._h, _ptr(info, _up), _ptr(en, _dp), None, 0, C.byref(cnt)))
+        period = self._ss_period
+        snap = np.zeros((2 * period, cnt.value), np.float64)
+        if cnt.value:
+            self._ck(self._L.oems_cuda_steadystate_raw(self._h, _ptr(info, _up), _ptr(en, _dp), _ptr(snap, _dp), snap.size, C.byref(cnt)))
+        return info, en, snap
 
     def GetStats(self):
         s = Stats()

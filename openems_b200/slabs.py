@@ -57,3 +57,91 @@ def link_engines_distributed(eng, dist, rank, world):
     dist.all_gather_object(blobs, eng.ExportIPC())
     eng.OpenPeers(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
     dist.barrier()
+
+
+# ---------------------------------------------------------------------------------------------
+# readout on z-slab engines: every slab evaluates the part of a dump box / mode plane / probe set it
+# owns (template: the reference's MPI ranks each process their sub-domain, openems_fdtd_mpi.cpp:201-299);
+# the pieces are put together here.  `engines` = the slab engines of ONE process in z order; the
+# *_distributed variants take this rank's engine and a torch.distributed-like module.
+# ---------------------------------------------------------------------------------------------
+def exchange_ghosts(engines):
+    """complete every slab's ghost planes for an interpolating readout (enqueue only, all slabs first: a single host
+    thread must not block on one slab before the others have been enqueued)"""
+    for e in engines:
+        e.ExchangeGhosts()
+
+
+def read_dump_slabs(engines, dump_ids):
+    """ProcessFields::CalcField over slabs: dump_ids[r] = the id AddDump returned on engines[r] (same box on all);
+    returns the whole box {3, nz, ny, nx}"""
+    import numpy as np
+    exchange_ghosts(engines)
+    return np.concatenate([e.ReadDump(d) for e, d in zip(engines, dump_ids)], axis=1)
+
+
+def accumulate_fd_slabs(engines, fd_ids, weights):
+    exchange_ghosts(engines)
+    for e, f in zip(engines, fd_ids):
+        e.AccumulateFD(f, weights)
+
+
+def read_fd_slabs(engines, fd_ids):
+    import numpy as np
+    parts = [e.ReadFD(f) for e, f in zip(engines, fd_ids)]
+    return np.concatenate([p[0] for p in parts], axis=2), parts[0][1]
+
+
+def combine_mode_match(parts):
+    """parts = (value, _, purity) of every slab -> (value, value^2/purity)"""
+    value = sum(p[0] for p in parts)
+    purity = sum(p[2] for p in parts)
+    return value, (value * value / purity if purity != 0.0 else 0.0)
+
+
+def mode_match_slabs(engines, mode_ids):
+    exchange_ghosts(engines)
+    return combine_mode_match([e.ReadModeMatchRaw(m) for e, m in zip(engines, mode_ids)])
+
+
+def combine_steadystate(parts, period):
+    """parts = SteadyStateRaw() of every slab -> (last_diff, checks): energies add up, records are concatenated"""
+    import ctypes as C
+    import numpy as np
+    from ._lib import load_library as load
+    L = load()
+    info = parts[0][0].copy()
+    en = np.sum([p[1] for p in parts], axis=0)
+    snap = np.ascontiguousarray(np.concatenate([p[2] for p in parts], axis=1), np.float64)
+    d = C.c_double()
+    dp, up = C.POINTER(C.c_double), C.POINTER(C.c_uint)
+    rc = L.oems_cuda_steadystate_eval(int(period), snap.shape[1], info.ctypes.data_as(up), en.ctypes.data_as(dp),
+                                      snap.ctypes.data_as(dp) if snap.size else None, C.byref(d))
+    if rc:
+        raise RuntimeError("oems_cuda_steadystate_eval failed")
+    return d.value, int(info[0])
+
+
+def steadystate_slabs(engines, period):
+    return combine_steadystate([e.SteadyStateRaw() for e in engines], period)
+
+
+def read_dump_distributed(eng, dump_id, dist, world):
+    """one process per GPU: every rank reads its piece, rank pieces are all-gathered and concatenated along z"""
+    import numpy as np
+    mine = eng.ReadDump(dump_id)
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    return np.concatenate(parts, axis=1)
+
+
+def mode_match_distributed(eng, mode_id, dist, world):
+    parts = [None] * world
+    dist.all_gather_object(parts, eng.ReadModeMatchRaw(mode_id))
+    return combine_mode_match(parts)
+
+
+def steadystate_distributed(eng, period, dist, world):
+    parts = [None] * world
+    dist.all_gather_object(parts, eng.SteadyStateRaw())
+    return combine_steadystate(parts, period)

@@ -40,7 +40,14 @@ def main():
     dist.all_gather_object(blobs, eng.ExportIPC())
     eng.OpenPeers(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
     dist.barrier()
-    result = {"ok": True, "schedule": [n for n, _ in eng.TimeSchedule(0)], "checked": []}
+    result = {"ok": True, "schedule": [n for n, _ in eng.TimeSchedule(0)], "checked": [], "dumps": []}
+    # readout across the process boundary: node-/cell-interpolated E and H dumps of the whole mesh (they read the
+    # neighbour rank's plane, completed through the IPC mappings by oems_cuda_exchange_ghosts)
+    from openems_b200.slabs import read_dump_distributed
+    el = [[s.edge_length(a, [p if b == a else 0 for b in range(3)], False) for p in range(s.N[a])] for a in range(3)]
+    dl = [[s.edge_length(a, [p if b == a else 0 for b in range(3)], True) for p in range(s.N[a])] for a in range(3)]
+    dump_kinds = [(0, 1), (1, 1), (0, 2), (1, 2)]
+    dump_ids = [eng.AddDump(is_H, interp, np.arange(s.N[0]), np.arange(s.N[1]), np.arange(nz), el, dl) for is_H, interp in dump_kinds]
     for n in steps:
         eng.IterateTS(n)          # a whole burst per process: the flags order the halos, not the hosts
         eng.Synchronize()
@@ -56,6 +63,14 @@ def main():
                     got[..., b:e] = f[w]
                 bad = int((got.view(np.uint32) != ref.view(np.uint32)).sum())
                 result["checked"].append({"ts": int(s.num_ts), "field": w, "differing_values": bad, "max_abs": float(np.abs(ref).max())})
+                if bad:
+                    result["ok"] = False
+        for (is_H, interp), d in zip(dump_kinds, dump_ids):
+            got = read_dump_distributed(eng, d, dist, world)
+            if rank == 0:
+                ref = s.dump_field(is_H, interp, (0, 0, 0), tuple(m - 1 for m in s.N))
+                bad = int((got.view(np.uint32) != ref.view(np.uint32)).sum())
+                result["dumps"].append({"ts": int(s.num_ts), "is_H": is_H, "interp": interp, "differing_values": bad, "max_abs": float(np.abs(ref).max())})
                 if bad:
                     result["ok"] = False
         dist.barrier()

@@ -31,4 +31,6 @@ def test_ipc_slabs_equal_oracle(tmp_path, world, fused, case):
     assert r["ok"], r
     assert len(r["checked"]) == 6 and all(c["differing_values"] == 0 for c in r["checked"])
     assert r["checked"][-1]["max_abs"] > 0
+    # field dumps across the process boundary (ghost planes completed through the IPC mappings)
+    assert len(r["dumps"]) == 12 and all(c["differing_values"] == 0 for c in r["dumps"]) and r["dumps"][-1]["max_abs"] > 0
     assert ("fused_EH" in r["schedule"]) == bool(fused)

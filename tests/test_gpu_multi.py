@@ -74,3 +74,15 @@ def test_two_gpus(fused):
     engines = run_slabs(s, [0, 22, 44], [0, 1], steps=(1, 5, 80), fused=fused)
     if fused:
         assert all(e.GetOption("tma") == 1 for e in engines)
+
+
+def test_dispersive_block_across_slabs_one_pass():
+    """C4 in small on 3 slabs, one-pass schedule: the Drude block crosses both interfaces (the ADE of a slab's top
+    plane is applied by the list kernel after update_H_top, everything else inside the one-pass kernel)"""
+    from tests import configs
+    s = configs.c4_drude_block()
+    engines = run_slabs(s, [0, 17, 30, 48], [0, 0, 0], steps=(1, 2, 60), fused=1)
+    for e in engines:
+        names = [n for n, _ in e.TimeSchedule(0)]
+        assert e.GetOption("fused") == 1 and "lorentz_pre_V" in names
+    assert "lorentz_apply_I_top" in [n for n, _ in engines[0].TimeSchedule(0)]

@@ -165,6 +165,52 @@ def test_lorentz_drude_block():
     assert mv > 0
 
 
+@pytest.mark.parametrize("case", ["c4", "two_boxes", "into_pml", "next_to_mur"])
+def test_lorentz_drude_in_the_one_pass_schedule(case):
+    """the one-pass kernel applies the ADE of dispersive cells itself (LOR instance of k_fused_tma; the pre hooks run as
+    list kernels on the source set): C4 in small (Drude eps+mue block), a Drude block plus a 2-pole Lorentz block
+    (two orders); both schedules bit-equal to the oracle, switched mid-run at odd and even timestep counts.  Dispersive
+    cells inside a UPML box or on a Mur plane's lines keep the two-pass schedule (the hook order could not be kept)"""
+    from tests import configs
+    from tests.test_gpu_parity import run_both
+    fc = C0 / (20 * 1e-3) / 2
+    fusable = True
+    if case == "c4":
+        s = configs.c4_drude_block()
+    elif case == "two_boxes":
+        lor = [dict(start=(0.010, 0.008, 0.012), stop=(0.022, 0.020, 0.026), eps_fp=(5e9,), eps_tau=(5e-9,), mue_fp=(5e9,), mue_tau=(5e-9,)),
+               dict(start=(0.004, 0.004, 0.004), stop=(0.008, 0.012, 0.010), epsR=2.0, eps_fp=(3e9, 6e9), eps_tau=(2e-9, 0.0),
+                    eps_flor=(0.0, 9e9), prio=3)]
+        s = cases.uniform_box(n=(34, 30, 38), bc=(BC_PML,) * 6, pml=6, f0=fc, fc=fc, lorentz=lor, src_pos=(6, 15, 19))
+    elif case == "into_pml":
+        lor = [dict(start=(0.0, 0.008, 0.012), stop=(0.012, 0.020, 0.026), eps_fp=(5e9,), eps_tau=(5e-9,))]
+        s = cases.uniform_box(n=(34, 30, 38), bc=(BC_PML,) * 6, pml=6, f0=fc, fc=fc, lorentz=lor, src_pos=(20, 15, 19))
+        fusable = False
+    else:
+        lor = [dict(start=(0.0, 0.008, 0.012), stop=(0.012, 0.020, 0.026), eps_fp=(5e9,), eps_tau=(5e-9,), mue_fp=(4e9,), mue_tau=(3e-9,))]
+        s = cases.uniform_box(n=(34, 30, 38), bc=(BC_MUR, BC_PML, BC_PEC, BC_PML, BC_PMC, BC_PML), pml=6, f0=fc, fc=fc, lorentz=lor, src_pos=(20, 15, 19))
+        fusable = False
+    assert s.lorentz()[0]["count"] > 500
+    eng = run_both(s, steps=(1, 2, 37, 120), what="dispersive " + case)
+    names = [n for n, _ in eng.TimeSchedule(0)]
+    assert eng.GetOption("fused") == int(fusable)
+    if fusable:
+        assert "fused_EH" in names and "lorentz_pre_V" in names and "lorentz_apply_V" not in names
+        for steps, fused in ((3, 0), (4, 1), (5, 0), (2, 1), (30, 1)):
+            eng.SetOption("fused", fused)
+            assert eng.GetOption("fused") == fused
+            s.iterate(steps)
+            eng.IterateTS(steps)
+            assert_fields_equal(eng, s, "dispersive %s, schedule switched to %d" % (case, fused))
+        eng.SetOption("tma", 0)   # no ADE instance of the register-staged kernel: two-pass
+        assert eng.GetOption("fused") == 0
+        s.iterate(7)
+        eng.IterateTS(7)
+        assert_fields_equal(eng, s, "dispersive %s, tma off" % case)
+    else:
+        assert "lorentz_apply_V" in names and "fused_EH" not in names
+
+
 def test_lumped_rlc_raw():
     rng = np.random.default_rng(7)
     n = (24, 22, 26)
