@@ -909,7 +909,8 @@ int Engine::build_exc()
 // run as list kernels before it).  That reproduces the reference's hook order as long as no OTHER hook reads or
 // changes a dispersive cell between the stencil and Apply2Voltages / Apply2Current:
 //   * at most two orders (poles); in every row the cells of an order are contiguous in x (one segment per row);
-//   * no dispersive cell inside a UPML box (its post-voltage hook precedes the ADE subtraction);
+//   * no dispersive cell inside a UPML box (its post-voltage hook precedes the ADE subtraction) or in the float4
+//     chunks / 16-line window such a box touches in x (plain cells there are updated by the shell / window kernels);
 //   * none on a Mur plane's boundary or shifted line (k_mur_post reads the stencil value before the subtraction),
 //     no absorbing sheets and no TFSF box together with dispersive material;
 //   * no H cell of the fix-up list is dispersive (checked with the list, build_fix_list).
@@ -923,8 +924,12 @@ bool Engine::lorentz_fusable() const
 		const unsigned* py = px + L.count;
 		const unsigned* pz = py + L.count;
 		for (unsigned i = 0; i < L.count; ++i) {
-			for (const UpmlBoxHost& B : h_upml)
-				if (px[i] - B.start[0] < B.n[0] && py[i] - B.start[1] < B.n[1] && pz[i] - B.start[2] < B.n[2]) return false;
+			for (const UpmlBoxHost& B : h_upml) {
+				// in x the shell launches also own the plain cells of the float4 chunks a box touches (the 16-line
+				// windows of k_xslab_tma are not used next to dispersive cells: build_schedule_fused)
+				const unsigned lo = B.start[0] / 4 * 4, hi = (B.start[0] + B.n[0] + 3) / 4 * 4;
+				if (px[i] >= lo && px[i] < hi && py[i] - B.start[1] < B.n[1] && pz[i] - B.start[2] < B.n[2]) return false;
+			}
 			const unsigned pos[3] = {px[i], py[i], pz[i]};
 			for (const MurHost& M : h_mur)
 				if (pos[M.ny] == M.line || pos[M.ny] == M.shift) return false;
@@ -936,6 +941,7 @@ bool Engine::lorentz_fusable() const
 int Engine::build_lorentz()
 {
 	lor_dev.clear();
+	lor_xmin = 1 << 30; lor_xmax = -1;
 	for (const LorHost& L : h_lor) {
 		// keep only the cells on owned planes, in storage order (z, y, x): the list kernels then read the fields
 		// coalesced, and the one-pass kernel finds a cell's ADE through one {first x, cells, first index} per row
@@ -947,6 +953,7 @@ int Engine::build_lorentz()
 		const unsigned cnt = (unsigned)keep.size();
 		std::vector<long long> cell(cnt);
 		for (unsigned q = 0; q < cnt; ++q) cell[q] = off_of(keep[q]);
+		for (unsigned i : keep) { lor_xmin = std::min(lor_xmin, (int)L.pos[i]); lor_xmax = std::max(lor_xmax, (int)L.pos[i]); }
 		for (unsigned q = 1; q < cnt; ++q)
 			if (cell[q] == cell[q - 1]) return fail("add_lorentz: a cell is listed twice");
 		auto pick = [&](const std::vector<float>& src) {
@@ -1495,6 +1502,8 @@ void Engine::build_schedule_fused()
 				const int ws = B.s[0] / 8 * 8;
 				if (B.s[0] == 0 && B.n[0] + 1 <= 16 && (int)gn[0] >= 48) { g = 0; xs_win[0] = 0; }
 				else if (B.s[0] + B.n[0] == (int)gn[0] && ws >= 32 && ws + 16 >= (int)gn[0] && ws + 16 <= pitch) { g = 1; xs_win[1] = ws; }
+				// plain cells of a window are updated by k_xslab_tma, which has no ADE branch
+				if (g >= 0 && lor_fused && lor_xmax >= xs_win[g] - 1 && lor_xmin <= xs_win[g] + 16) g = -1;
 			} else {
 				if (B.s[0] == 0 && (B.n[0] + 3) / 4 * 4 + 1 <= 16 && (B.n[0] + 3) / 4 * 4 < (int)gn[0]) g = 0;
 				else if (B.s[0] + B.n[0] == (int)gn[0] && B.s[0] % 4 != 0 && (int)gn[0] - B.s[0] / 4 * 4 <= 16 && B.s[0] / 4 * 4 > 0) g = 1;

@@ -80,7 +80,7 @@ def test_dispersive_block_across_slabs_one_pass():
     """C4 in small on 3 slabs, one-pass schedule: the Drude block crosses both interfaces (the ADE of a slab's top
     plane is applied by the list kernel after update_H_top, everything else inside the one-pass kernel)"""
     from tests import configs
-    s = configs.c4_drude_block()
+    s = configs.c4_drude_block(block=(12, 35))
     engines = run_slabs(s, [0, 17, 30, 48], [0, 0, 0], steps=(1, 2, 60), fused=1)
     for e in engines:
         names = [n for n, _ in e.TimeSchedule(0)]

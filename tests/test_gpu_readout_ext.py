@@ -176,10 +176,10 @@ def test_lorentz_drude_in_the_one_pass_schedule(case):
     fc = C0 / (20 * 1e-3) / 2
     fusable = True
     if case == "c4":
-        s = configs.c4_drude_block()
+        s = configs.c4_drude_block(block=(12, 35))   # (x = 36 .. 39 is the float4 chunk the x-high UPML box starts in)
     elif case == "two_boxes":
         lor = [dict(start=(0.010, 0.008, 0.012), stop=(0.022, 0.020, 0.026), eps_fp=(5e9,), eps_tau=(5e-9,), mue_fp=(5e9,), mue_tau=(5e-9,)),
-               dict(start=(0.004, 0.004, 0.004), stop=(0.008, 0.012, 0.010), epsR=2.0, eps_fp=(3e9, 6e9), eps_tau=(2e-9, 0.0),
+               dict(start=(0.008, 0.007, 0.007), stop=(0.012, 0.012, 0.010), epsR=2.0, eps_fp=(3e9, 6e9), eps_tau=(2e-9, 0.0),
                     eps_flor=(0.0, 9e9), prio=3)]
         s = cases.uniform_box(n=(34, 30, 38), bc=(BC_PML,) * 6, pml=6, f0=fc, fc=fc, lorentz=lor, src_pos=(6, 15, 19))
     elif case == "into_pml":

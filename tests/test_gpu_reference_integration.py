@@ -67,10 +67,11 @@ def test_engine_cuda_equals_reference_engine_fields(case):
     # carries tangential E on a Mur face (C1: +1.6 %) -- so the reference value is bracketed by the two sums of the
     # (bit-equal) fields instead of being compared directly
     ec, eg = c.energy(), g.energy()
-    v, i = c.volt.astype(np.float64), c.curr.astype(np.float64)
-    def esum(zend):
-        return 8.85418781762e-12 * (v[:, :-1, :-1, :zend] ** 2).sum() + 1.256637062e-6 * (i[:, :-1, :-1, :zend] ** 2).sum()
-    assert eg > 0 and abs(eg - esum(-1)) <= 1e-12 * eg
+    v, i = np.asarray(c.volt, np.float32), np.asarray(c.curr, np.float32)
+    def esum(zend):   # float products, fp64 sums (FDTD_FLOAT * FDTD_FLOAT added to a double)
+        return 8.85418781762e-12 * (v[:, :-1, :-1, :zend] * v[:, :-1, :-1, :zend]).sum(dtype=np.float64) \
+            + 1.256637062e-6 * (i[:, :-1, :-1, :zend] * i[:, :-1, :-1, :zend]).sum(dtype=np.float64)
+    assert eg > 0 and abs(eg - esum(-1)) <= 1e-11 * eg
     assert abs(ec - esum(None)) <= 1e-4 * ec
 
 
