@@ -980,6 +980,39 @@ int Engine::build_lorentz()
 			D.i.ade = dalloc<float>((size_t)3 * cnt);
 			if (!L.c[5].empty()) { D.i.c_lor = upload(pick(L.c[5])); D.i.lor_ade = dalloc<float>((size_t)3 * cnt); }
 		}
+		// coefficient compression (ADE coefficients table-compressed): the distinct {int, ext, lor} x 3 tuples
+		// of a list -- interior, faces, edges, corners of a homogeneous block -- form a small table, the list kernels read
+		// a 16-bit index per cell instead of 24 .. 36 bytes of coefficients
+		auto compress = [&](LorParams& P, const std::vector<float>& ci, const std::vector<float>& ce, const std::vector<float>& cl) {
+			P.pidx = nullptr; P.ptab = nullptr;
+			if (!cnt) return;
+			std::map<std::array<uint32_t, 9>, unsigned> seen;
+			std::array<uint32_t, 9> last_key{};
+			std::vector<unsigned short> idx(cnt);
+			std::vector<float> tab;
+			for (unsigned q = 0; q < cnt; ++q) {
+				std::array<uint32_t, 9> key;
+				float f[9];
+				for (int n = 0; n < 3; ++n) {
+					const size_t i = (size_t)n * L.count + keep[q];
+					f[n] = ci[i]; f[3 + n] = ce[i]; f[6 + n] = cl.empty() ? 0.0f : cl[i];
+				}
+				memcpy(key.data(), f, sizeof(f));
+				if (q && key == last_key) { idx[q] = idx[q - 1]; continue; } // runs of equal cells: no lookup
+				last_key = key;
+				auto it = seen.find(key);
+				if (it == seen.end()) {
+					if (seen.size() >= 65536) return; // too many: keep the per-cell arrays
+					it = seen.emplace(key, (unsigned)seen.size()).first;
+					tab.insert(tab.end(), f, f + 9);
+				}
+				idx[q] = (unsigned short)it->second;
+			}
+			P.pidx = upload(idx); P.ptab = upload(tab);
+			if (!P.pidx || !P.ptab) { P.pidx = nullptr; P.ptab = nullptr; }
+		};
+		if (D.v_on) compress(D.v, L.c[0], L.c[1], L.c[2]);
+		if (D.i_on) compress(D.i, L.c[3], L.c[4], L.c[5]);
 		// entries on the slab's top owned plane (its H is done after the neighbour's E plane has arrived)
 		D.top_first = cnt;
 		{
@@ -1577,6 +1610,81 @@ void Engine::build_schedule_fused()
 		XP.kE0 = F.kE0; XP.kE1 = F.kE1; XP.kH1 = F.kH1; XP.kHc1 = F.kHc1;
 		XP.zchunk = xslab_tma ? xt_zchunk : 16;
 		nxs = 0;
+		const int pH_k1 = F.kH1;
+		// ---- whole planes / whole rows at the ends of the mesh that consist of UPML cells only (the z-low / z-high
+		// boxes together with the parts of the x and y boxes next to them; the y boxes with the x boxes' ends): the
+		// one-pass kernel (and the x-window kernel) skip them altogether instead of passing them through --
+		// k_shell_E stores E_new of those cells in both field sets (the source set in place for the neighbours'
+		// curls, the destination set as the result), k_shell_H stores their H_new.  Saves 50 - 12 bytes per cell.
+		F.jb = 0; F.je = (int)gn[1];
+		SE.sk0 = F.kE0; SE.sk1 = F.kE1; SE.sjb = 0; SE.sje = (int)gn[1]; SE.Xd2 = nullptr;
+		if (par == 0) skip_active = 0;
+		if (tma_active && skip_req && pE.nboxes && xslab_req != 1) {
+			const int nx = (int)gn[0], ny = (int)gn[1];
+			// cells of all UPML boxes inside a region (the boxes are disjoint)
+			auto covered = [&](int j0, int j1, int k0, int k1) {
+				long long c = 0;
+				for (int q = 0; q < pE.nboxes; ++q) {
+					const PmlBox& B = pE.box[q];
+					const long long dj = std::min(j1, B.s[1] + B.n[1]) - std::max(j0, B.s[1]);
+					const long long dk = std::min(k1, B.s[2] + B.n[2]) - std::max(k0, B.s[2]);
+					if (dj > 0 && dk > 0) c += dj * dk * B.n[0];
+				}
+				return c == (long long)(j1 - j0) * (k1 - k0) * nx;
+			};
+			int k0 = F.kE0, k1 = F.kE1, jb = 0, je = ny;
+			for (int q = 0; q < pE.nboxes; ++q) { // thinnest box that starts at the bottom / ends at the top
+				const PmlBox& B = pE.box[q];
+				if (B.s[2] == F.kE0 && B.s[2] + B.n[2] < F.kE1 && covered(0, ny, F.kE0, B.s[2] + B.n[2])) k0 = std::max(k0, B.s[2] + B.n[2]);
+				if (B.s[2] + B.n[2] == F.kE1 && B.s[2] > F.kE0 && covered(0, ny, B.s[2], F.kE1)) k1 = std::min(k1, B.s[2]);
+			}
+			if (k1 - k0 < 2) { k0 = F.kE0; k1 = F.kE1; }
+			for (int q = 0; q < pE.nboxes; ++q) {
+				const PmlBox& B = pE.box[q];
+				if (B.s[1] == 0 && B.n[1] < ny && covered(0, B.n[1], k0, k1)) jb = std::max(jb, B.n[1]);
+				if (B.s[1] + B.n[1] == ny && B.s[1] > 0 && covered(B.s[1], ny, k0, k1)) je = std::min(je, B.s[1]);
+			}
+			if (je - jb < 2) { jb = 0; je = ny; }
+			if (k0 > F.kE0 || k1 < F.kE1 || jb > 0 || je < ny) {
+				SE.sk0 = k0; SE.sk1 = k1; SE.sjb = jb; SE.sje = je; SE.Xd2 = sV[D];
+				F.kE0 = k0; F.kE1 = k1; F.jb = jb; F.je = je;
+				F.kH1 = std::min(F.kH1, k1); F.kHc1 = std::min(F.kHc1, k1);
+				XP.kE0 = F.kE0; XP.kE1 = F.kE1; XP.kH1 = F.kH1; XP.kHc1 = F.kHc1;
+				skip_active = (k0 > pE.k0) + (k1 < pE.k1) + (jb > 0) + (je < ny);
+			}
+		}
+		// one entry of the two shell launches: rows [jr0, jr1) (box-local) and local planes [k0, k1) of box B
+		int nent = 0;
+		auto add_shell = [&](const PmlBox& B, int jr0, int jr1, int k0, int k1, bool pingpong = false) {
+			if (jr1 <= jr0 || k1 <= k0 || nent >= OEMS_MAX_SHELL_ENTRIES) return;
+			ShellBoxParams q;
+			memset(&q, 0, sizeof(q));
+			q.cs = (long long)B.n[0] * B.n[1] * B.n[2];
+			q.bs0 = B.s[0]; q.bs1 = B.s[1]; q.bs2 = B.s[2]; q.bn0 = B.n[0]; q.bn1 = B.n[1];
+			q.jr0 = jr0; q.jr1 = jr1;
+			q.c0 = B.s[0] / 4; q.nchunk = (B.s[0] + B.n[0] - 1) / 4 - q.c0 + 1;
+			// lanes side by side in x: the smallest power of two that covers the box
+			q.xl = q.nchunk <= 4 ? 4 : q.nchunk <= 8 ? 8 : q.nchunk <= 16 ? 16 : 32;
+			const int rows = 8 * (32 / q.xl);
+			q.gx = (q.nchunk + q.xl - 1) / q.xl;
+			q.gy = (jr1 - jr0 + rows - 1) / rows;
+			ShellBoxParams e = q, h = q;
+			e.flux = (pingpong ? fluxV[S] : d_flux_v) + B.off;
+			e.flux_out = (pingpong ? fluxV[D] : d_flux_v) + B.off;
+			e.k0 = k0; e.k1 = k1;
+			h.flux = h.flux_out = d_flux_i + B.off;
+			h.k0 = std::max(k0, F.kH0); h.k1 = std::min(k1, pH_k1);
+			// z chunk: long marches save the re-read of the carried plane, short ones give more blocks
+			for (ShellBoxParams* w : {&e, &h}) {
+				const int nk = std::max(0, w->k1 - w->k0);
+				int zc = shell_zchunk;
+				while (zc > 4 && (long long)w->gx * w->gy * ((nk + zc - 1) / zc) < 4 * 148) zc /= 2;
+				w->zchunk = std::max(1, std::min(zc, nk));
+			}
+			SE.box[nent] = e;
+			SH.box[nent] = h;
+			++nent;
+		};
 		for (int b = 0; b < pE.nboxes; ++b) {
 			const PmlBox& B = pE.box[b];
 			if (b == xs_box[0] || b == xs_box[1]) {
@@ -1592,39 +1700,28 @@ void Engine::build_schedule_fused()
 				Q.s1 = B.s[1]; Q.n1 = B.n[1]; Q.s2 = B.s[2]; Q.n2 = B.n[2];
 				Q.cs = (long long)B.n[0] * B.n[1] * B.n[2];
 				Q.fVs = fluxV[S] + B.off; Q.fVd = fluxV[D] + B.off; Q.fI = d_flux_i + B.off;
+				// the window kernel owns the box cells on the rows / planes the one-pass kernels work on; the pieces in
+				// skipped planes / rows go through the shell launches like the other boxes' cells there
+				Q.oj0 = std::max(B.s[1], F.jb); Q.oj1 = std::min(B.s[1] + B.n[1], F.je);
+				Q.ok0 = std::max(B.s[2], F.kE0); Q.ok1 = std::min(B.s[2] + B.n[2], F.kE1);
+				if (xslab_tma) {
+					add_shell(B, 0, B.n[1], B.s[2], Q.ok0, true);
+					add_shell(B, 0, B.n[1], Q.ok1, B.s[2] + B.n[2], true);
+					add_shell(B, 0, Q.oj0 - B.s[1], Q.ok0, Q.ok1, true);
+					add_shell(B, Q.oj1 - B.s[1], B.n[1], Q.ok0, Q.ok1, true);
+				}
 				continue;
 			}
 			F.sh[ns].c0 = B.s[0] / 4; F.sh[ns].cn = (B.s[0] + B.n[0] - 1) / 4 - F.sh[ns].c0 + 1;
 			F.sh[ns].j0 = B.s[1]; F.sh[ns].jn = B.n[1];
 			F.sh[ns].k0 = B.s[2]; F.sh[ns].kn = B.n[2];
-			ShellBoxParams q;
-			memset(&q, 0, sizeof(q));
-			q.cs = (long long)B.n[0] * B.n[1] * B.n[2];
-			q.bs0 = B.s[0]; q.bs1 = B.s[1]; q.bs2 = B.s[2]; q.bn0 = B.n[0]; q.bn1 = B.n[1];
-			q.c0 = F.sh[ns].c0; q.nchunk = F.sh[ns].cn;
-			// lanes side by side in x: the smallest power of two that covers the box
-			q.xl = q.nchunk <= 4 ? 4 : q.nchunk <= 8 ? 8 : q.nchunk <= 16 ? 16 : 32;
-			const int rows = 8 * (32 / q.xl);
-			q.gx = (q.nchunk + q.xl - 1) / q.xl;
-			q.gy = (q.bn1 + rows - 1) / rows;
-			ShellBoxParams e = q, h = q;
-			e.flux = d_flux_v + B.off;
-			e.k0 = B.s[2]; e.k1 = B.s[2] + B.n[2];
-			h.flux = d_flux_i + B.off;
-			h.k0 = std::max(B.s[2], F.kH0); h.k1 = std::min(B.s[2] + B.n[2], F.kH1);
-			// z chunk: long marches save the re-read of the carried plane, short ones give more blocks
-			for (ShellBoxParams* w : {&e, &h}) {
-				const int nk = std::max(0, w->k1 - w->k0);
-				int zc = shell_zchunk;
-				while (zc > 4 && (long long)w->gx * w->gy * ((nk + zc - 1) / zc) < 4 * 148) zc /= 2;
-				w->zchunk = std::max(1, std::min(zc, nk));
-			}
-			SE.box[ns] = e;
-			SH.box[ns] = h;
 			++ns;
+			add_shell(B, 0, B.n[1], B.s[2], B.s[2] + B.n[2]);
 		}
-		F.nsh = SE.nboxes = SH.nboxes = ns;
+		F.nsh = ns;
+		SE.nboxes = SH.nboxes = nent;
 		XP.nsh = ns;
+		XP.jb = F.jb; XP.je = F.je;
 		for (int q = 0; q < ns; ++q) { XP.sh[q].c0 = F.sh[q].c0; XP.sh[q].cn = F.sh[q].cn; XP.sh[q].j0 = F.sh[q].j0; XP.sh[q].jn = F.sh[q].jn; XP.sh[q].k0 = F.sh[q].k0; XP.sh[q].kn = F.sh[q].kn; }
 		for (ShellParams* w : {&SE, &SH}) {
 			unsigned nb = 0;
@@ -1729,7 +1826,7 @@ void Engine::build_schedule_fused()
 		L.push_back([this, par, i16](cudaStream_t s) {
 			const FusedParams& q = pF[par];
 			const dim3 block(32, FUSED_TY + 1);
-			const dim3 g((unsigned)((pitch / 4 + 31) / 32), (unsigned)((q.ny + FUSED_TY - 1) / FUSED_TY),
+			const dim3 g((unsigned)((pitch / 4 + 31) / 32), (unsigned)((q.je - q.jb + FUSED_TY - 1) / FUSED_TY),
 			             (unsigned)std::max(1, (q.kE1 - q.kE0 + q.zchunk - 1) / q.zchunk));
 			if (tma_active) {
 				const FusedTmaParams& t = pFT[par];
@@ -1752,7 +1849,7 @@ void Engine::build_schedule_fused()
 			lab("xslab_EH");
 			L.push_back([this, par, i16](cudaStream_t s) {
 				const XTmaParams& q = pXt[par];
-				const dim3 g((unsigned)((q.x.ny + XT_TY - 1) / XT_TY), (unsigned)std::max(1, (q.x.kE1 - q.x.kE0 + q.x.zchunk - 1) / q.x.zchunk), (unsigned)nxs);
+				const dim3 g((unsigned)((q.x.je - q.x.jb + XT_TY - 1) / XT_TY), (unsigned)std::max(1, (q.x.kE1 - q.x.kE0 + q.x.zchunk - 1) / q.x.zchunk), (unsigned)nxs);
 				if (i16) k_xslab_tma<uint16_t, XT_STAGES><<<g, XT_THREADS, xt_smem_bytes<uint16_t, XT_STAGES>(), s>>>(q);
 				else k_xslab_tma<uint32_t, XT_STAGES><<<g, XT_THREADS, xt_smem_bytes<uint32_t, XT_STAGES>(), s>>>(q);
 			});
@@ -1989,6 +2086,11 @@ int Engine::set_option(const char* key, long long value)
 		if (finalized) return rebuild_schedule();
 		return 0;
 	}
+	if (k == "skip_shell") { // 1 (default): the one-pass kernel skips UPML boxes that span whole planes / rows, 0: passes them through
+		skip_req = value != 0;
+		if (finalized) return rebuild_schedule();
+		return 0;
+	}
 	if (k == "xslab_zchunk") {
 		xt_zchunk = (int)std::max<long long>(4, std::min<long long>(63, value)); // one shell bit per plane of a march
 		if (finalized) return rebuild_schedule();
@@ -2025,6 +2127,7 @@ int Engine::get_option(const char* key, long long* value)
 	if (!value) return fail("get_option: null pointer");
 	if (k == "fused") { *value = fused_active ? 1 : 0; return 0; }
 	if (k == "tma") { *value = (fused_active && tma_active) ? 1 : 0; return 0; }
+	if (k == "skip_shell") { *value = fused_active ? skip_active : 0; return 0; }
 	if (k == "xslab") { *value = fused_active ? (xs_box[0] >= 0) + (xs_box[1] >= 0) : 0; return 0; }
 	if (k == "h2d_bytes") { *value = (long long)h2d_bytes; return 0; } // bytes copied host -> device since oems_cuda_create (counted at the copy calls)
 	return fail("get_option: unknown key " + k);

@@ -280,12 +280,14 @@ private:
 	size_t h2d_index_bytes = 0;  // bytes of operator index copied host -> device
 	// UPML boxes updated inside the one-pass kernel ("x slabs", kernels_fused_tma.cuh): index into pE.box, -1 none
 	int xs_box[2] = {-1, -1};
-	int xslab_req = 0;           // option "xslab": thin UPML boxes at the x ends get their own one-pass kernel (off: not faster yet, experiments_r01.md #15)
+	int xslab_req = 2;           // option "xslab": thin UPML boxes at the x ends get their own one-pass kernel: 2 = k_xslab_tma (default), 1 = k_xslab_EH, 0 = shell launches
 	XSlabParams pXs[2];          // per parity
 	XTmaParams pXt[2];           // the same + TMA descriptors (k_xslab_tma)
 	bool xslab_tma = false;
+	bool skip_req = true;        // option "skip_shell"
+	int skip_active = 0;         // boxes the one-pass kernel skips
 	int xs_win[2] = {0, 0};      // first line of the 16-line windows of k_xslab_tma
-	int xt_zchunk = 32;
+	int xt_zchunk = 16;
 	int make_xslab_maps(int par);
 	int nxs = 0;                 // x slabs in pXs
 	float* d_flux_v2 = nullptr;  // second voltage-flux set (only the x-slab boxes use it)

@@ -480,6 +480,8 @@ struct LorParams {
 	unsigned count;
 	long long comp;
 	unsigned first;         // k_lorentz_apply: entries [first, count) only (the slab's top plane in the one-pass schedule)
+	const unsigned short* pidx; // [count] index into ptab, or NULL (more than 65536 distinct tuples: per-cell arrays)
+	const float* ptab;          // [n][9]: c_int[3], c_ext[3], c_lor[3]
 };
 __global__ void k_lorentz_pre(const __grid_constant__ LorParams p)
 {
@@ -491,14 +493,17 @@ __global__ void k_lorentz_pre(const __grid_constant__ LorParams p)
 		const size_t q = (size_t)n * p.count + i;
 		const float x = p.X[n * p.comp + c];
 		float a = p.ade[q];
+		// compressed coefficients: a table of the distinct {int, ext, lor} x 3 tuples of the list + a 16-bit index per cell
+		const float* t = p.pidx ? p.ptab + 9 * (size_t)p.pidx[i] : nullptr;
+		const float ci = t ? __ldg(t + n) : p.c_int[q], ce = t ? __ldg(t + 3 + n) : p.c_ext[q];
 		if (p.c_lor) {
-			const float l = fadd(p.lor_ade[q], fmul(p.c_lor[q], a));
+			const float l = fadd(p.lor_ade[q], fmul(t ? __ldg(t + 6 + n) : p.c_lor[q], a));
 			p.lor_ade[q] = l;
-			a = fmul(a, p.c_int[q]);
-			a = fadd(a, fmul(p.c_ext[q], fsub(x, l)));
+			a = fmul(a, ci);
+			a = fadd(a, fmul(ce, fsub(x, l)));
 		} else {
-			a = fmul(a, p.c_int[q]);
-			a = fadd(a, fmul(p.c_ext[q], x));
+			a = fmul(a, ci);
+			a = fadd(a, fmul(ce, x));
 		}
 		p.ade[q] = a;
 	}

@@ -50,6 +50,10 @@ struct FusedParams {
 	int kH0, kH1;        // local planes whose H is UPDATED here; other owned planes are copied through
 	int kHc1;            // H planes [kH1, kHc1) are copied through (top of the domain); [kHc1, kE1) left to the slab kernel
 	int zchunk;
+	// rows whose E and H this kernel stores: [jb, je) (default 0, ny).  UPML boxes that span whole rows / planes at
+	// the ends of the mesh are skipped altogether (the host also narrows kE0 / kE1): k_shell_E stores their E_new in
+	// both field sets, k_shell_H their H_new, so nothing of them has to be passed through here
+	int jb, je;
 	// UPML shell: regions (whole float4 chunks in x) whose E and H are produced by k_shell_E/H
 	int nsh;
 	struct ShellBox { int c0, cn, j0, jn, k0, kn; } sh[OEMS_MAX_PML_BOXES];
@@ -298,11 +302,14 @@ __global__ void k_fix_H(const __grid_constant__ FixParams p)
 #ifndef SHELL_MIN_BLOCKS
 #define SHELL_MIN_BLOCKS 3
 #endif
+#define OEMS_MAX_SHELL_ENTRIES 16   // boxes + the pieces of x-window boxes that lie in skipped planes / rows
 struct ShellBoxParams {
 	float* flux;       // component 0 of this box
+	float* flux_out;   // k_shell_E: where the new flux goes (= flux, except for the pieces of x-window boxes, whose voltage flux is ping-ponged with the field sets)
 	long long cs;      // flux component stride = cells of the box held here
 	int bs0, bs1, bs2; // box origin: x, y, local z (origin of the flux layout [k][j][i])
 	int bn0, bn1;      // box lines in x, y
+	int jr0, jr1;      // rows of the box to process (box-local), normally 0 .. bn1
 	int k0, k1;        // local planes to process
 	int c0, nchunk;    // float4 chunks that cover the box in x
 	int zchunk;
@@ -320,7 +327,11 @@ struct ShellParams {
 	long long plane, comp;
 	int nboxes;
 	unsigned nblocks;
-	ShellBoxParams box[OEMS_MAX_PML_BOXES];
+	// k_shell_E: cells outside the planes [sk0, sk1) / rows [sjb, sje) are skipped by the one-pass kernel: their E_new
+	// is also stored in the destination set Xd2 (NULL: nothing is skipped)
+	float* Xd2;
+	int sk0, sk1, sjb, sje;
+	ShellBoxParams box[OEMS_MAX_SHELL_ENTRIES];
 };
 
 // block -> (box, block coordinates inside the box)
@@ -355,14 +366,14 @@ __global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_E(const __grid_
 	const int XL = q.xl;
 	const int lane = threadIdx.x, sub = lane & (XL - 1);
 	const int ch = sb.bx * XL + sub;
-	const int lj = (sb.by * blockDim.y + threadIdx.y) * (32 / XL) + lane / XL;
+	const int lj = q.jr0 + (sb.by * blockDim.y + threadIdx.y) * (32 / XL) + lane / XL;
 	const int kb = q.k0 + sb.bz * q.zchunk;
 	const int ke = min(kb + q.zchunk, q.k1);
 	if (kb >= ke) return;
-	const bool active = ch < q.nchunk && lj < q.bn1;
+	const bool active = ch < q.nchunk && lj < q.jr1;
 	if (__all_sync(0xffffffffu, !active)) return;
 	const int ic = (q.c0 + (ch < q.nchunk ? ch : 0)) * 4;
-	const int j = q.bs1 + (lj < q.bn1 ? lj : 0);
+	const int j = q.bs1 + (lj < q.jr1 ? lj : q.jr0);
 	const int jm = j - (j > 0);
 	const long long row = (long long)j * p.pitch + ic;
 	const long long rowm = (long long)jm * p.pitch + ic;
@@ -424,17 +435,24 @@ __global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_E(const __grid_
 				} else {
 					if ((unsigned)li >= (unsigned)q.bn0) continue; // belongs to another box
 					const float4 P0 = __ldg(p.tP0 + e[c]), P1 = __ldg(p.tP1 + e[c]), P2 = __ldg(p.tP2 + e[c]);
-					float* f = q.flux + frow + li;
-					setcomp(v0, c, leap_pml(comp(v0, c), A.x, B.x, curl0, P0.x, P1.x, P2.x, f, f));
-					setcomp(v1, c, leap_pml(comp(v1, c), A.y, B.y, curl1, P0.y, P1.y, P2.y, f + q.cs, f + q.cs));
-					setcomp(v2, c, leap_pml(comp(v2, c), A.z, B.z, curl2, P0.z, P1.z, P2.z, f + 2 * q.cs, f + 2 * q.cs));
+					const float* f = q.flux + frow + li;
+					float* fo = q.flux_out + frow + li;
+					setcomp(v0, c, leap_pml(comp(v0, c), A.x, B.x, curl0, P0.x, P1.x, P2.x, f, fo));
+					setcomp(v1, c, leap_pml(comp(v1, c), A.y, B.y, curl1, P0.y, P1.y, P2.y, f + q.cs, fo + q.cs));
+					setcomp(v2, c, leap_pml(comp(v2, c), A.z, B.z, curl2, P0.z, P1.z, P2.z, f + 2 * q.cs, fo + 2 * q.cs));
 				}
 				done |= 1u << c;
 			}
+			const bool dual = p.Xd2 && (k < p.sk0 || k >= p.sk1 || j < p.sjb || j >= p.sje);
 			if (done == 15u) {
 				st4(p.Xd + o, v0);
 				st4(p.Xd + p.comp + o, v1);
 				st4(p.Xd + 2 * p.comp + o, v2);
+				if (dual) {
+					st4(p.Xd2 + o, v0);
+					st4(p.Xd2 + p.comp + o, v1);
+					st4(p.Xd2 + 2 * p.comp + o, v2);
+				}
 			} else {
 #pragma unroll
 				for (int c = 0; c < 4; ++c)
@@ -442,6 +460,11 @@ __global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_E(const __grid_
 						p.Xd[o + c] = comp(v0, c);
 						p.Xd[p.comp + o + c] = comp(v1, c);
 						p.Xd[2 * p.comp + o + c] = comp(v2, c);
+						if (dual) {
+							p.Xd2[o + c] = comp(v0, c);
+							p.Xd2[p.comp + o + c] = comp(v1, c);
+							p.Xd2[2 * p.comp + o + c] = comp(v2, c);
+						}
 					}
 			}
 		}
@@ -458,14 +481,14 @@ __global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_H(const __grid_
 	const int XL = q.xl;
 	const int lane = threadIdx.x, sub = lane & (XL - 1);
 	const int ch = sb.bx * XL + sub;
-	const int lj = (sb.by * blockDim.y + threadIdx.y) * (32 / XL) + lane / XL;
+	const int lj = q.jr0 + (sb.by * blockDim.y + threadIdx.y) * (32 / XL) + lane / XL;
 	const int kb = q.k0 + sb.bz * q.zchunk;
 	const int ke = min(kb + q.zchunk, q.k1);
 	if (kb >= ke) return;
-	const bool active = ch < q.nchunk && lj < q.bn1;
+	const bool active = ch < q.nchunk && lj < q.jr1;
 	if (__all_sync(0xffffffffu, !active)) return;
 	const int ic = (q.c0 + (ch < q.nchunk ? ch : 0)) * 4;
-	const int j = q.bs1 + (lj < q.bn1 ? lj : 0);
+	const int j = q.bs1 + (lj < q.jr1 ? lj : q.jr0);
 	const bool upd = active && j < p.ny - 1; // UpdateCurrents stops one line short (engine.cpp:179-183)
 	const long long row = (long long)j * p.pitch + ic;
 	const long long rowp = (long long)(j < p.ny - 1 ? j + 1 : j) * p.pitch + ic;

@@ -135,11 +135,11 @@ __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tm
 	const uint32_t bar0 = smem_u32(ft_smem + STAGES * ST::BYTES + 2 * 3 * (FUSED_TY + 1) * 32 * 16);
 
 	const int lane = threadIdx.x, ty = threadIdx.y;
-	const int x0 = blockIdx.x * 128, j0 = blockIdx.y * FUSED_TY;
+	const int x0 = blockIdx.x * 128, j0 = p.jb + blockIdx.y * FUSED_TY;
 	const int i0 = x0 + lane * 4;
 	const int j = j0 + ty;
-	const bool halo_row = ty == FUSED_TY;
-	const bool producer = halo_row && lane == 0;
+	const bool halo_row = ty == FUSED_TY || j >= p.je;   // rows whose E is only computed for the row below them
+	const bool producer = ty == FUSED_TY && lane == 0;
 	const int kb = p.kE0 + blockIdx.z * p.zchunk;
 	const int ke = min(kb + p.zchunk, p.kE1);
 	if (kb >= ke) return; // block-uniform

@@ -29,6 +29,7 @@ struct XSlabBox {
 	int own0, own1;      // lines stored by this kernel: the box's float4 chunks [own0, own1)
 	int bs0, bn0;        // the box: first line, lines in x
 	int s1, n1, s2, n2;  // rows / local planes of the box
+	int oj0, oj1, ok0, ok1; // k_xslab_tma: rows / local planes of the box this kernel updates (the rest: shell launches)
 	long long cs;        // flux component stride
 	const float* fVs;    // voltage flux of timestep n   (component 0)
 	float* fVd;          // voltage flux of timestep n+1
@@ -44,6 +45,7 @@ struct XSlabParams {
 	int pitch;
 	long long plane, comp;
 	int kE0, kE1, kH1, kHc1; // as in FusedParams
+	int jb, je;          // k_xslab_tma: rows stored, as in FusedParams
 	int zchunk;
 	XSlabBox box[2];
 	// chunk-aligned footprints of the boxes the shell launches handle: a cell of the slab's chunks that lies

@@ -32,10 +32,10 @@
 #define XT_ROWS_I (XT_TY + 2)          // H rows j0-1 .. j0+TY
 #define XT_ROWS_V (XT_TY + 1)          // E / index rows j0 .. j0+TY
 #ifndef XT_STAGES
-#define XT_STAGES 4
+#define XT_STAGES 2      // ring depth / resident blocks: 2 / 6 measured best at 1024^3 (0.97 ms; 4 / 4: 1.08, 3 / 6: 1.02, 2 / 8: 1.05 -- spills)
 #endif
 #ifndef XT_MIN_BLOCKS
-#define XT_MIN_BLOCKS 4
+#define XT_MIN_BLOCKS 6
 #endif
 
 struct alignas(64) XTmaParams {
@@ -72,10 +72,10 @@ __global__ void __launch_bounds__(XT_THREADS, XT_MIN_BLOCKS) k_xslab_tma(const _
 
 	const int tid = threadIdx.x;
 	const int lx = tid & (XT_WL - 1), ty = tid / XT_WL;
-	const int ws = B.w0, j0 = blockIdx.x * XT_TY;
+	const int ws = B.w0, j0 = p.jb + blockIdx.x * XT_TY;
 	const int ic = ws + lx * 4;
 	const int j = j0 + ty;
-	const bool halo_row = ty == XT_TY;
+	const bool halo_row = ty == XT_TY || j >= p.je;
 	const bool producer = tid == XT_THREADS - 1;
 	const int kb = p.kE0 + blockIdx.y * p.zchunk;
 	const int ke = min(kb + p.zchunk, p.kE1);
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(XT_THREADS, XT_MIN_BLOCKS) k_xslab_tma(const _
 	const int rI = ty + 1, rIm = (j > 0) ? ty : ty + 1, rV = ty;
 	const int xe = ic + 4;
 	const bool hcol = lx == XT_WL - 1 && !halo_row && active && xe < p.nx;
-	const bool row_in = (unsigned)(jc - B.s1) < (unsigned)B.n1;
+	const bool row_in = jc >= B.oj0 && jc < B.oj1;
 	const long long fplane = (long long)B.n1 * B.bn0;
 	const long long frow = (long long)(jc - B.s1) * B.bn0 + (ic - B.bs0);   // + (k - s2) * fplane + c
 	// flux of this chunk at plane kk (voltages: source / destination set) and kk-1 (currents), component 0;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(XT_THREADS, XT_MIN_BLOCKS) k_xslab_tma(const _
 	}
 
 	for (int kk = kb; kk <= e_last; ++kk) {
-		const bool plane_in = (unsigned)(kk - B.s2) < (unsigned)B.n2;
+		const bool plane_in = kk >= B.ok0 && kk < B.ok1;
 		// ---- flux of timestep n of this chunk's box cells: plane kk (voltage flux) and plane kk-1 (current flux),
 		// issued before the wait for the staged plane
 		float fv[3][4], fi[3][4];
