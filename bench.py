@@ -237,7 +237,7 @@ def parity_check(world, rank, local_rank, dist, reduce_min, reduce_sum_u64):
     from openems_b200.slabs import slab_range
     n = (192, 160, max(64, 48 * world))
     steps = 24
-    slab = slab_range(n[2], world, rank, pml_lo=PML, pml_hi=PML, pml_weight=2.4) if world > 1 else None
+    slab = slab_range(n[2], world, rank, pml_lo=PML, pml_hi=PML, pml_weight=1.7) if world > 1 else None
     so, _ = build_c5(n, slab=slab, reduce_min=reduce_min)
     eng = so.operator().CreateEngine(device=local_rank, slab=slab)
     eng.SetOption("fused", 1)
@@ -275,8 +275,13 @@ def run_gpu(args):
     if world > 1:  # keep stdout to the one JSON line (NCCL prints its version there at VERSION/INFO level)
         os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    if world > 1:  # the host-side operator build is OpenMP-parallel: share the cores between ranks
-        os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+    if world > 1 and "BENCH_KEEP_OMP" not in os.environ:
+        # the host-side operator build is OpenMP-parallel and very uneven between the ranks (the end slabs hold the
+        # graded z-PML planes: 12-15 distinct xy planes to evaluate, a middle slab 1-2): every rank may use all cores
+        # (the middle ranks are done in a fraction of a second), waiting threads sleep.  torchrun presets
+        # OMP_NUM_THREADS=1, which made the end ranks build single-threaded (16 s at N=2).
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+        os.environ["OMP_WAIT_POLICY"] = "passive"
     import torch
     from openems_b200 import load_library
     load_library()  # fail loudly when the CUDA library is missing
@@ -295,13 +300,11 @@ def run_gpu(args):
     nz = n[2]
     slab = None
     if world > 1:
-        # strong scaling: z-slabs of the same mesh.  In the one-pass schedule a full z-UPML plane costs about
-        # 3.4x a plain plane (shell E + H on top of the pass through the big kernel), so the two end slabs get
-        # fewer planes.  Weight 3.2 (from 1-GPU kernel times) left rank 0 waiting 0.08 ms per step for its
-        # neighbour at 4 and at 8 GPUs (halo_wait_E in profiles/bench_r01_{4,8}gpu_tma_balanced.json), i.e. 5-7
-        # planes too few: 2.4 evens that out
+        # strong scaling: z-slabs of the same mesh.  A z-UPML plane (all cells UPML: shell E with its second store +
+        # shell H = 136 B/cell) costs about 2.7x a plain plane (50 B/cell), so the two end slabs get fewer planes;
+        # the first split uses that estimate (weight 1.7), N > 2 then re-deals the planes from measured busy times
         from openems_b200.slabs import slab_range
-        slab = slab_range(nz, world, rank, pml_lo=PML, pml_hi=PML, pml_weight=2.4)
+        slab = slab_range(nz, world, rank, pml_lo=PML, pml_hi=PML, pml_weight=args.pml_weight)
 
     def reduce_min(v):
         t = torch.tensor([v], device="cuda", dtype=torch.float64)
@@ -319,6 +322,44 @@ def run_gpu(args):
     # every rank builds only the planes it holds (the ranks agree on the timestep by a MIN reduction)
     so, t_build = build_c5(n, slab=slab, reduce_min=reduce_min if world > 1 else None)
     op = so.operator()
+
+    # ---------------- slab sizes from MEASURED per-rank kernel times (N > 2): a short un-timed run on the first split
+    # gives every rank's busy time per timestep (all kernels but the halo waits); middle ranks give the cost of a
+    # plain plane, the end ranks the extra cost of a z-PML plane; the planes are re-dealt with that weight and the
+    # ranks whose range changed rebuild their operator
+    balance = None
+    if world > 2 and not args.no_rebalance:
+        from openems_b200.slabs import slab_range
+        e0 = op.CreateEngine(device=local_rank, slab=slab)
+        blobs = [None] * world
+        dist.all_gather_object(blobs, e0.ExportIPC())
+        e0.OpenPeers(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
+        dist.barrier()
+        e0.FillFields(0)
+        e0.IterateTS(3)
+        e0.Synchronize()
+        busy = sum(ms for name, ms in e0.TimeSchedule(4) if not name.startswith("halo_wait"))
+        e0.close()
+        del e0
+        parts = [None] * world
+        dist.all_gather_object(parts, (busy, slab[1] - slab[0]))
+        mid = [b / m for b, m in parts[1:-1]]
+        a = sum(mid) / len(mid)                                            # ms per plain plane
+        b = sum(p[0] - a * p[1] for p in (parts[0], parts[-1])) / 2 / (PML + 1)   # extra ms per z-PML plane
+        w = max(0.0, b / a)
+        new_slab = slab_range(nz, world, rank, pml_lo=PML, pml_hi=PML, pml_weight=w)
+        balance = {"first_split_weight": args.pml_weight, "busy_ms_per_rank": [round(p[0], 4) for p in parts],
+                   "planes_first_split": [p[1] for p in parts], "measured_weight": round(w, 3)}
+        changed = torch.tensor([int(tuple(new_slab) != tuple(slab))], device="cuda")
+        dist.all_reduce(changed)
+        if int(changed.item()):
+            slab = new_slab
+            so, t_build2 = build_c5(n, slab=slab, reduce_min=reduce_min)
+            t_build = max(t_build, t_build2)
+            op = so.operator()
+        allp = [None] * world
+        dist.all_gather_object(allp, slab[1] - slab[0])
+        balance["planes"] = allp
 
     # ---------------- e2e leg: engine creation from HOST buffers + K timesteps with probe readback
     def make_engine():
@@ -442,10 +483,58 @@ def run_gpu(args):
     e2e_val = cells * args.steps / t_e2e / 1e6
     probe_sample = [float(v) for v in vals[:4]]
 
+    # ---------------- asynchronous field dumps (north_star (4), N = 1): an NF2FF-style box -- 6 faces x E and H, cell
+    # interpolation -- sampled after EVERY burst with oems_cuda_read_dump_async while the time loop goes on; the host
+    # waits for a sample (and copies it out of the page-locked buffer) only while the next burst is running
+    dump_info = None
+    if world == 1 and not args.no_dump_leg:
+        m = 32
+        lo, hi = [m, m, m], [n[0] - 1 - m, n[1] - 1 - m, n[2] - 1 - m]
+        el = [np.full(k, 1e-3) for k in n]
+        ids = []
+        for a in range(3):
+            for side in (lo[a], hi[a]):
+                rng = [np.arange(lo[b], hi[b] + 1) if b != a else np.array([side]) for b in range(3)]
+                for is_H in (0, 1):
+                    ids.append(eng.AddDump(is_H, 2, rng[0], rng[1], rng[2], el, el))
+        nbytes = sum(int(np.prod(eng._dump_shapes[i])) * 4 for i in ids)
+        steps_d = max(burst * 10, (args.steps // burst) * burst)
+
+        def run(with_dumps):
+            eng.Synchronize()
+            t0 = time.perf_counter()
+            pending, done, got = [], 0, 0
+            while done < steps_d:
+                eng.IterateTS(burst)
+                done += burst
+                if with_dumps:
+                    # the PREVIOUS sample is taken out of the page-locked buffers while this burst runs on the GPU
+                    for t in pending:
+                        got += eng.WaitDump(t).nbytes
+                    # this burst's sample: evaluated on the engine stream behind the burst, copied on the copy stream
+                    pending = [eng.ReadDumpAsync(i) for i in ids]
+                else:
+                    eng.ReadProbes()
+            eng.Synchronize()                       # the time loop (and the last sample's evaluation) is through here
+            t_loop = time.perf_counter() - t0
+            for t in pending:                       # the last sample still has to arrive and be taken out
+                got += eng.WaitDump(t).nbytes
+            return t_loop / steps_d * 1e3, (time.perf_counter() - t0) / steps_d * 1e3, got
+
+        run(True)
+        ms_plain, _, _ = run(False)
+        ms_dump, ms_dump_drained, got = run(True)
+        dump_info = {"box": "6 faces %d cells inside the mesh, E and H, cell interpolation" % m, "samples": steps_d // burst,
+                     "bytes_per_sample": nbytes, "every_timesteps": burst, "ms_per_step_without": ms_plain, "ms_per_step_with": ms_dump,
+                     "overhead_frac": ms_dump / ms_plain - 1.0,
+                     "ms_per_step_with_incl_last_sample_drain": ms_dump_drained, "d2h_bytes_total": got,
+                     "note": "overhead_frac = what the dumps cost the time loop (their 12 interpolation kernels per sample + copy-stream "
+                             "contention); the last sample's D2H copy and host memcpy after the loop is reported separately"}
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C5 uniform vacuum %dx%dx%d PML_8x6 centre Ez Gauss source, 12 probes" % n,
                        "parallelism": "z-slabs x%d over NVLink peer memory" % world if world > 1 else "single GPU",
@@ -461,6 +550,8 @@ def run_gpu(args):
                                 "probe read-back" % (t_upload, args.steps, burst), "probe_sample": probe_sample},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "slab_balance": balance,
+            "async_dumps": dump_info,
             "parity_check": dict(parity, full_size_digest={"timesteps": args.warmup + args.steps, "prefill_seed": 0,
                                                            "E": "%016x" % dig[0], "H": "%016x" % dig[1],
                                                            "note": "same value at every N for the same --warmup/--steps (bit-exact slabs)"}),
@@ -630,11 +721,17 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, nargs=3, default=[1024, 1024, 1024], help="mesh lines (default: the 1024^3 headline config)")
+    ap.add_argument("--n", "--mesh", dest="n", type=int, nargs=3, default=[1024, 1024, 1024], help="mesh lines (default: the 1024^3 headline config)")
     ap.add_argument("--cpu-sample", type=int, nargs=3, default=None,
                     help="bounded sample mesh of the CPU arm (default 192^3 inside the GPU line, 256^3 for --impl reference)")
     ap.add_argument("--cpu-steps", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dump-leg", action="store_true", help="skip the asynchronous-dump overhead measurement (N = 1)")
+    ap.add_argument("--pml-weight", type=float, default=1.7,
+                    help="first z-slab split: extra cost of a z-PML plane relative to a plain plane (136 vs 50 bytes per cell)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="label of the line: weak when --n grows with --gpus (e.g. 1024 1024 1024*N)")
+    ap.add_argument("--no-rebalance", action="store_true", help="keep the first split (N > 2: otherwise re-dealt from measured busy times)")
     ap.add_argument("--config", default="c5", choices=["c5", "c4"], help="c5: the headline (default); c4: 512^3 Drude block")
     args = ap.parse_args()
     if args.config == "c4" and args.n == [1024, 1024, 1024]:
