@@ -428,6 +428,11 @@ def run_gpu(args):
     one_pass = "fused_EH" in kern
     per_half, per_step = algorithmic_bytes((n[0], n[1], local_cells // (n[0] * n[1])), pml_cells, index_bytes, one_pass)
     if one_pass:
+        # the one-pass kernel works on the interior rows x planes only (all-UPML planes / rows at the mesh ends go
+        # through the shell launches): its algorithmic bytes are those cells x (48 + index)
+        rows, planes = eng.GetOption("onepass_rows"), eng.GetOption("onepass_planes")
+        per_half = n[0] * rows * planes * (48 + index_bytes)
+    if one_pass:
         dom, t_dom = "fused_EH", kern["fused_EH"]
     else:
         t_E, t_H = kern.get("update_E", 0.0), kern.get("update_H", 0.0)
@@ -447,6 +452,7 @@ def run_gpu(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic,
                 "algorithmic_bytes_per_launch": per_half, "kernel_ms": t_dom, "peak_source": peak_src,
+                "kernel_cells": (n[0] * rows * planes) if one_pass else local_cells,
                 "kernels_ms": {k: round(v, 5) for k, v in kern.items()}, "step_ms_from_events": step_ms_sched,
                 "step_frac_of_peak": (per_step / (step_ms_sched * 1e-3) / 1e9 / peak) if step_ms_sched else None}
 

@@ -2128,6 +2128,9 @@ int Engine::get_option(const char* key, long long* value)
 	if (k == "fused") { *value = fused_active ? 1 : 0; return 0; }
 	if (k == "tma") { *value = (fused_active && tma_active) ? 1 : 0; return 0; }
 	if (k == "skip_shell") { *value = fused_active ? skip_active : 0; return 0; }
+	// rows / local planes the one-pass kernel works on (the all-UPML planes / rows at the mesh ends are skipped)
+	if (k == "onepass_rows") { *value = fused_active ? pF[0].je - pF[0].jb : 0; return 0; }
+	if (k == "onepass_planes") { *value = fused_active ? pF[0].kE1 - pF[0].kE0 : 0; return 0; }
 	if (k == "xslab") { *value = fused_active ? (xs_box[0] >= 0) + (xs_box[1] >= 0) : 0; return 0; }
 	if (k == "h2d_bytes") { *value = (long long)h2d_bytes; return 0; } // bytes copied host -> device since oems_cuda_create (counted at the copy calls)
 	return fail("get_option: unknown key " + k);
