@@ -23,6 +23,26 @@ int Engine::check(cudaError_t e, const char* what)
 	return 1;
 }
 
+// Every kernel launch goes through here.  With option "pdl" = 1 the launch carries the programmatic-stream-
+// serialization attribute (captured into the step graphs as programmatic edges): the next kernel of the stream may be
+// set up while this one is still running; every kernel starts with PDL_PROLOGUE (kernels.cuh: griddepcontrol.wait), so
+// it touches memory only after its predecessor has completed and flushed.  Measured (profiles/experiments_r02.md #8):
+// no gain -- the 16-28 us timesteps of the small configs are the latency of the dependent loads inside the two
+// stencil kernels, not launch gaps -- so it is off by default (bit-identical either way, tests run both).
+static bool g_pdl = false;
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kern)(KArgs...), dim3 g, dim3 b, size_t smem, cudaStream_t s, Args&&... args)
+{
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <typename T> T* Engine::dalloc(size_t n, bool zero)
 {
 	T* p = nullptr;
@@ -154,8 +174,8 @@ int Engine::set_operator_planes(unsigned nu, const oems_coeff_entry* table, unsi
 	h2d_bytes += np * n_uplanes * ib + gn[2] * sizeof(unsigned);
 	const long long rows = (long long)gn[1] * nzl, n = rows * pitch;
 	const unsigned blocks = (unsigned)((n + 255) / 256);
-	if (ib == 2) k_expand_planes<uint16_t><<<blocks, 256, 0, stream>>>((uint16_t*)p, (const uint16_t*)d_up, d_pz, z0, rows, (int)gn[0], (int)gn[1], pitch, (uint16_t)nu);
-	else k_expand_planes<uint32_t><<<blocks, 256, 0, stream>>>((uint32_t*)p, (const uint32_t*)d_up, d_pz, z0, rows, (int)gn[0], (int)gn[1], pitch, (uint32_t)nu);
+	if (ib == 2) launch_k(k_expand_planes<uint16_t>, blocks, 256, 0, stream, (uint16_t*)p, (const uint16_t*)d_up, d_pz, z0, rows, (int)gn[0], (int)gn[1], pitch, (uint16_t)nu);
+	else launch_k(k_expand_planes<uint32_t>, blocks, 256, 0, stream, (uint32_t*)p, (const uint32_t*)d_up, d_pz, z0, rows, (int)gn[0], (int)gn[1], pitch, (uint32_t)nu);
 	CK(cudaStreamSynchronize(stream)); // the caller's buffers are free again
 	CK(cudaGetLastError());
 	cudaFree(d_up);
@@ -191,8 +211,8 @@ int Engine::set_operator_compressed(unsigned nu, const oems_coeff_entry* table, 
 		const long long padn = rows * (pitch - (int)gn[0]);
 		if (padn > 0) {
 			const unsigned blocks = (unsigned)((padn + 255) / 256);
-			if (ib == 2) k_fill_index_padding<uint16_t><<<blocks, 256, 0, stream>>>((uint16_t*)p, rows, (int)gn[0], pitch, (uint16_t)nu);
-			else k_fill_index_padding<uint32_t><<<blocks, 256, 0, stream>>>((uint32_t*)p, rows, (int)gn[0], pitch, (uint32_t)nu);
+			if (ib == 2) launch_k(k_fill_index_padding<uint16_t>, blocks, 256, 0, stream, (uint16_t*)p, rows, (int)gn[0], pitch, (uint16_t)nu);
+			else launch_k(k_fill_index_padding<uint32_t>, blocks, 256, 0, stream, (uint32_t*)p, rows, (int)gn[0], pitch, (uint32_t)nu);
 		}
 	}
 	const char* src = (const char*)index + (size_t)z0 * gn[1] * gn[0] * ib;
@@ -1199,7 +1219,7 @@ template <typename K, typename P> static void launch1d(K kern, const P& p, long 
 {
 	if (n <= 0) return;
 	const int bs = 128;
-	kern<<<(unsigned)((n + bs - 1) / bs), bs, 0, s>>>(p);
+	launch_k(kern, (unsigned)((n + bs - 1) / bs), bs, 0, s, p);
 }
 
 void Engine::build_schedule()
@@ -1235,14 +1255,14 @@ void Engine::build_schedule()
 	if (multi && peer_lo)
 		(labels.push_back("halo_wait_H"), step.push_back([this](cudaStream_t s) {
 			WaitParams w{d_flagH, d_numTS, 0u, d_halo_err, halo_timeout_cycles()};
-			k_halo_wait<<<1, 1, 0, s>>>(w);
+			launch_k(k_halo_wait, 1, 1, 0, s, w);
 		}));
 	// ---- E half-step with fused UPML
 	if (pE.k1 > pE.k0)
 		(labels.push_back("update_E"), step.push_back([this, i16, block, stencil_grid](cudaStream_t s) {
 			const dim3 g = stencil_grid(pE, pE.ny);
-			if (i16) { if (has_pml) k_update_E<uint16_t, true><<<g, block, 0, s>>>(pE); else k_update_E<uint16_t, false><<<g, block, 0, s>>>(pE); }
-			else { if (has_pml) k_update_E<uint32_t, true><<<g, block, 0, s>>>(pE); else k_update_E<uint32_t, false><<<g, block, 0, s>>>(pE); }
+			if (i16) { if (has_pml) launch_k(k_update_E<uint16_t, true>, g, block, 0, s, pE); else launch_k(k_update_E<uint16_t, false>, g, block, 0, s, pE); }
+			else { if (has_pml) launch_k(k_update_E<uint32_t, true>, g, block, 0, s, pE); else launch_k(k_update_E<uint32_t, false>, g, block, 0, s, pE); }
 		}));
 	// ---- post-voltage hooks: UPML (fused), TFSF, absorbing sheets, Mur
 	if (pTfsf[0].groups) (labels.push_back("tfsf_V"), step.push_back([this](cudaStream_t s) { launch1d(k_tfsf, pTfsf[0], pTfsf[0].groups, s); }));
@@ -1251,9 +1271,9 @@ void Engine::build_schedule()
 	if (pMur.nplanes) (labels.push_back("mur_post"), step.push_back([this](cudaStream_t s) { launch1d(k_mur_post, pMur, pMur.total, s); }));
 	// ---- apply-voltage hooks in list order: SteadyState, RLC, Lorentz, Mur, Excitation
 	auto ss_launch = [this](const SsParams& q, cudaStream_t s) {
-		k_ss_record<<<std::max(1u, (q.count + 63) / 64), 64, 0, s>>>(q);
-		k_ss_energy<<<148 * 2, dim3(32, 8), 0, s>>>(q);
-		k_ss_snapshot<<<8, 256, 0, s>>>(q);
+		launch_k(k_ss_record, std::max(1u, (q.count + 63) / 64), 64, 0, s, q);
+		launch_k(k_ss_energy, 148 * 2, dim3(32, 8), 0, s, q);
+		launch_k(k_ss_snapshot, 8, 256, 0, s, q);
 	};
 	if (ss_on) (labels.push_back("steadystate"), step.push_back([this, ss_launch](cudaStream_t s) { ss_launch(pSs, s); }));
 	for (size_t a = sheet_dev.size(); a-- > 0;)
@@ -1269,7 +1289,7 @@ void Engine::build_schedule()
 		(labels.push_back("halo_push_E"), step.push_back([this](cudaStream_t s) {
 			HaloParams h{d_V, peer_lo_V, (long long)((int)zb - z0) * plane, peer_lo_ghostE_off, comp, peer_lo_comp, plane,
 			             d_halo_cnt, peer_lo_flagE, d_numTS, 1u};
-			k_halo_push<<<64, 256, 0, s>>>(h);
+			launch_k(k_halo_push, 64, 256, 0, s, h);
 		}));
 	// ---- pre-current hooks: Lorentz (UPML fused)
 	for (size_t o = 0; o < lor_dev.size(); ++o)
@@ -1279,14 +1299,14 @@ void Engine::build_schedule()
 	if (multi && peer_hi)
 		(labels.push_back("halo_wait_E"), step.push_back([this](cudaStream_t s) {
 			WaitParams w{d_flagE, d_numTS, 1u, d_halo_err, halo_timeout_cycles()};
-			k_halo_wait<<<1, 1, 0, s>>>(w);
+			launch_k(k_halo_wait, 1, 1, 0, s, w);
 		}));
 	// ---- H half-step with fused UPML, then the UPML cells the stencil never visits
 	if (pH.k1 > pH.k0)
 		(labels.push_back("update_H"), step.push_back([this, i16, block, stencil_grid](cudaStream_t s) {
 			const dim3 g = stencil_grid(pH, pH.ny - 1);
-			if (i16) { if (has_pml) k_update_H<uint16_t, true><<<g, block, 0, s>>>(pH); else k_update_H<uint16_t, false><<<g, block, 0, s>>>(pH); }
-			else { if (has_pml) k_update_H<uint32_t, true><<<g, block, 0, s>>>(pH); else k_update_H<uint32_t, false><<<g, block, 0, s>>>(pH); }
+			if (i16) { if (has_pml) launch_k(k_update_H<uint16_t, true>, g, block, 0, s, pH); else launch_k(k_update_H<uint16_t, false>, g, block, 0, s, pH); }
+			else { if (has_pml) launch_k(k_update_H<uint32_t, true>, g, block, 0, s, pH); else launch_k(k_update_H<uint32_t, false>, g, block, 0, s, pH); }
 		}));
 	if (pEdge.count && edge_dirty)
 		(labels.push_back("upml_untouched_H"), step.push_back([this, i16](cudaStream_t s) {
@@ -1306,9 +1326,9 @@ void Engine::build_schedule()
 		(labels.push_back("halo_push_H"), step.push_back([this](cudaStream_t s) {
 			HaloParams h{d_I, peer_hi_I, (long long)((int)ze - 1 - z0) * plane, peer_hi_ghostH_off, comp, peer_hi_comp, plane,
 			             d_halo_cnt + 1, peer_hi_flagH, d_numTS, 1u};
-			k_halo_push<<<64, 256, 0, s>>>(h);
+			launch_k(k_halo_push, 64, 256, 0, s, h);
 		}));
-	(labels.push_back("tick"), step.push_back([this](cudaStream_t s) { k_tick<<<1, 1, 0, s>>>(d_numTS); }));
+	(labels.push_back("tick"), step.push_back([this](cudaStream_t s) { launch_k(k_tick, 1, 1, 0, s, d_numTS); }));
 	kernels_per_step = (unsigned)step.size();
 	if (fused_active) build_schedule_fused();
 
@@ -1798,7 +1818,7 @@ void Engine::build_schedule_fused()
 			lab("halo_wait_H");
 			L.push_back([this](cudaStream_t s) {
 				WaitParams w{d_flagH, d_numTS, 0u, d_halo_err, halo_timeout_cycles()};
-				k_halo_wait<<<1, 1, 0, s>>>(w);
+				launch_k(k_halo_wait, 1, 1, 0, s, w);
 			});
 		}
 		// ---- E of the UPML shell, then E and H of everything else in one pass
@@ -1807,7 +1827,7 @@ void Engine::build_schedule_fused()
 			L.push_back([this, par, i16](cudaStream_t s) {
 				const ShellParams& q = pShE[par];
 				if (!q.nblocks) return;
-				if (i16) k_shell_E<uint16_t><<<q.nblocks, dim3(32, 8), 0, s>>>(q); else k_shell_E<uint32_t><<<q.nblocks, dim3(32, 8), 0, s>>>(q);
+				if (i16) launch_k(k_shell_E<uint16_t>, q.nblocks, dim3(32, 8), 0, s, q); else launch_k(k_shell_E<uint32_t>, q.nblocks, dim3(32, 8), 0, s, q);
 			});
 		}
 		if (nxs && !xslab_tma) {
@@ -1819,7 +1839,7 @@ void Engine::build_schedule_fused()
 				int rows = 0, planes = 0;
 				for (int b = 0; b < nxs; ++b) { rows = std::max(rows, q.box[b].n1); planes = std::max(planes, q.box[b].n2); }
 				const dim3 g((unsigned)((rows + XSLAB_ROWS - 1) / XSLAB_ROWS), (unsigned)((planes + q.zchunk - 1) / q.zchunk), (unsigned)nxs);
-				if (i16) k_xslab_EH<uint16_t><<<g, dim3(16, 16), 0, s>>>(q); else k_xslab_EH<uint32_t><<<g, dim3(16, 16), 0, s>>>(q);
+				if (i16) launch_k(k_xslab_EH<uint16_t>, g, dim3(16, 16), 0, s, q); else launch_k(k_xslab_EH<uint32_t>, g, dim3(16, 16), 0, s, q);
 			});
 		}
 		lab("fused_EH");
@@ -1832,16 +1852,16 @@ void Engine::build_schedule_fused()
 				const FusedTmaParams& t = pFT[par];
 				const int sm = i16 ? ft_smem_bytes<uint16_t, FT_STAGES>() : ft_smem_bytes<uint32_t, FT_STAGES>();
 				if (lor_fused) {
-					if (i16) { if (has_pml) k_fused_tma<uint16_t, true, FT_STAGES, true><<<g, block, sm, s>>>(t); else k_fused_tma<uint16_t, false, FT_STAGES, true><<<g, block, sm, s>>>(t); }
-					else { if (has_pml) k_fused_tma<uint32_t, true, FT_STAGES, true><<<g, block, sm, s>>>(t); else k_fused_tma<uint32_t, false, FT_STAGES, true><<<g, block, sm, s>>>(t); }
+					if (i16) { if (has_pml) launch_k(k_fused_tma<uint16_t, true, FT_STAGES, true>, g, block, sm, s, t); else launch_k(k_fused_tma<uint16_t, false, FT_STAGES, true>, g, block, sm, s, t); }
+					else { if (has_pml) launch_k(k_fused_tma<uint32_t, true, FT_STAGES, true>, g, block, sm, s, t); else launch_k(k_fused_tma<uint32_t, false, FT_STAGES, true>, g, block, sm, s, t); }
 					return;
 				}
-				if (i16) { if (has_pml) k_fused_tma<uint16_t, true, FT_STAGES><<<g, block, sm, s>>>(t); else k_fused_tma<uint16_t, false, FT_STAGES><<<g, block, sm, s>>>(t); }
-				else { if (has_pml) k_fused_tma<uint32_t, true, FT_STAGES><<<g, block, sm, s>>>(t); else k_fused_tma<uint32_t, false, FT_STAGES><<<g, block, sm, s>>>(t); }
+				if (i16) { if (has_pml) launch_k(k_fused_tma<uint16_t, true, FT_STAGES>, g, block, sm, s, t); else launch_k(k_fused_tma<uint16_t, false, FT_STAGES>, g, block, sm, s, t); }
+				else { if (has_pml) launch_k(k_fused_tma<uint32_t, true, FT_STAGES>, g, block, sm, s, t); else launch_k(k_fused_tma<uint32_t, false, FT_STAGES>, g, block, sm, s, t); }
 				return;
 			}
-			if (i16) { if (has_pml) k_fused_EH<uint16_t, true><<<g, block, 0, s>>>(q); else k_fused_EH<uint16_t, false><<<g, block, 0, s>>>(q); }
-			else { if (has_pml) k_fused_EH<uint32_t, true><<<g, block, 0, s>>>(q); else k_fused_EH<uint32_t, false><<<g, block, 0, s>>>(q); }
+			if (i16) { if (has_pml) launch_k(k_fused_EH<uint16_t, true>, g, block, 0, s, q); else launch_k(k_fused_EH<uint16_t, false>, g, block, 0, s, q); }
+			else { if (has_pml) launch_k(k_fused_EH<uint32_t, true>, g, block, 0, s, q); else launch_k(k_fused_EH<uint32_t, false>, g, block, 0, s, q); }
 		});
 		if (nxs && xslab_tma) {
 			// x slabs, TMA-staged: overwrites its 16-line windows in the destination set AFTER the big kernel (which
@@ -1850,8 +1870,8 @@ void Engine::build_schedule_fused()
 			L.push_back([this, par, i16](cudaStream_t s) {
 				const XTmaParams& q = pXt[par];
 				const dim3 g((unsigned)((q.x.je - q.x.jb + XT_TY - 1) / XT_TY), (unsigned)std::max(1, (q.x.kE1 - q.x.kE0 + q.x.zchunk - 1) / q.x.zchunk), (unsigned)nxs);
-				if (i16) k_xslab_tma<uint16_t, XT_STAGES><<<g, XT_THREADS, xt_smem_bytes<uint16_t, XT_STAGES>(), s>>>(q);
-				else k_xslab_tma<uint32_t, XT_STAGES><<<g, XT_THREADS, xt_smem_bytes<uint32_t, XT_STAGES>(), s>>>(q);
+				if (i16) launch_k(k_xslab_tma<uint16_t, XT_STAGES>, g, XT_THREADS, xt_smem_bytes<uint16_t, XT_STAGES>(), s, q);
+				else launch_k(k_xslab_tma<uint32_t, XT_STAGES>, g, XT_THREADS, xt_smem_bytes<uint32_t, XT_STAGES>(), s, q);
 			});
 		}
 		// ---- post / apply voltage hooks on the destination set
@@ -1870,9 +1890,9 @@ void Engine::build_schedule_fused()
 			lab("steadystate");
 			L.push_back([this, par](cudaStream_t s) {
 				const SsParams& q = pSsF[par];
-				k_ss_record<<<std::max(1u, (q.count + 63) / 64), 64, 0, s>>>(q);
-				k_ss_energy<<<148 * 2, dim3(32, 8), 0, s>>>(q);
-				k_ss_snapshot<<<8, 256, 0, s>>>(q);
+				launch_k(k_ss_record, std::max(1u, (q.count + 63) / 64), 64, 0, s, q);
+				launch_k(k_ss_energy, 148 * 2, dim3(32, 8), 0, s, q);
+				launch_k(k_ss_snapshot, 8, 256, 0, s, q);
 			});
 		}
 		for (size_t a = sheet_dev.size(); a-- > 0;) {
@@ -1888,7 +1908,7 @@ void Engine::build_schedule_fused()
 			L.push_back([this, D](cudaStream_t s) {
 				HaloParams h{sV[D], peer_lo_Vs[D], (long long)((int)zb - z0) * plane, peer_lo_ghostE_off, comp, peer_lo_comp, plane,
 				             d_halo_cnt, peer_lo_flagE, d_numTS, 1u};
-				k_halo_push<<<64, 256, 0, s>>>(h);
+				launch_k(k_halo_push, 64, 256, 0, s, h);
 			});
 		}
 		// ---- H cells that depend on E values changed by the hooks
@@ -1905,7 +1925,7 @@ void Engine::build_schedule_fused()
 			L.push_back([this, par, i16](cudaStream_t s) {
 				const ShellParams& q = pShH[par];
 				if (!q.nblocks) return;
-				if (i16) k_shell_H<uint16_t><<<q.nblocks, dim3(32, 8), 0, s>>>(q); else k_shell_H<uint32_t><<<q.nblocks, dim3(32, 8), 0, s>>>(q);
+				if (i16) launch_k(k_shell_H<uint16_t>, q.nblocks, dim3(32, 8), 0, s, q); else launch_k(k_shell_H<uint32_t>, q.nblocks, dim3(32, 8), 0, s, q);
 			});
 		}
 		// ---- slab top plane: needs the neighbour's E plane
@@ -1913,15 +1933,15 @@ void Engine::build_schedule_fused()
 			lab("halo_wait_E");
 			L.push_back([this](cudaStream_t s) {
 				WaitParams w{d_flagE, d_numTS, 1u, d_halo_err, halo_timeout_cycles()};
-				k_halo_wait<<<1, 1, 0, s>>>(w);
+				launch_k(k_halo_wait, 1, 1, 0, s, w);
 			});
 			lab("update_H_top");
 			L.push_back([this, par, i16](cudaStream_t s) {
 				const StencilParams& q = pHtop[par];
 				const dim3 block(32, tune_rows);
 				const dim3 g((unsigned)((pitch / 4 + 31) / 32), (unsigned)((q.ny + tune_rows - 1) / tune_rows), 1);
-				if (i16) { if (has_pml) k_update_H<uint16_t, true><<<g, block, 0, s>>>(q); else k_update_H<uint16_t, false><<<g, block, 0, s>>>(q); }
-				else { if (has_pml) k_update_H<uint32_t, true><<<g, block, 0, s>>>(q); else k_update_H<uint32_t, false><<<g, block, 0, s>>>(q); }
+				if (i16) { if (has_pml) launch_k(k_update_H<uint16_t, true>, g, block, 0, s, q); else launch_k(k_update_H<uint16_t, false>, g, block, 0, s, q); }
+				else { if (has_pml) launch_k(k_update_H<uint32_t, true>, g, block, 0, s, q); else launch_k(k_update_H<uint32_t, false>, g, block, 0, s, q); }
 			});
 			if (lor_fused)
 				for (size_t o = 0; o < lor_dev.size(); ++o) {
@@ -1954,11 +1974,11 @@ void Engine::build_schedule_fused()
 			L.push_back([this, D](cudaStream_t s) {
 				HaloParams h{sI[D], peer_hi_Is[D], (long long)((int)ze - 1 - z0) * plane, peer_hi_ghostH_off, comp, peer_hi_comp, plane,
 				             d_halo_cnt + 1, peer_hi_flagH, d_numTS, 1u};
-				k_halo_push<<<64, 256, 0, s>>>(h);
+				launch_k(k_halo_push, 64, 256, 0, s, h);
 			});
 		}
 		lab("tick");
-		L.push_back([this](cudaStream_t s) { k_tick<<<1, 1, 0, s>>>(d_numTS); });
+		L.push_back([this](cudaStream_t s) { launch_k(k_tick, 1, 1, 0, s, d_numTS); });
 	}
 	kernels_per_step = (unsigned)stepf[0].size();
 }
@@ -2037,7 +2057,7 @@ void Engine::launch_probes(double* dst)
 	p.V = sV[cur()]; p.I = sI[cur()];
 	p.out = dst;
 	const unsigned wpb = 4;
-	k_probes<<<(p.nprobes + wpb - 1) / wpb, wpb * 32, 0, stream>>>(p);
+	launch_k(k_probes, (p.nprobes + wpb - 1) / wpb, wpb * 32, 0, stream, p);
 	++kernels_launched;
 }
 
@@ -2086,6 +2106,11 @@ int Engine::set_option(const char* key, long long value)
 		if (finalized) return rebuild_schedule();
 		return 0;
 	}
+	if (k == "pdl") { // 1: programmatic dependent launch between the kernels of a timestep (process-wide)
+		g_pdl = value != 0;
+		if (finalized) return rebuild_schedule();
+		return 0;
+	}
 	if (k == "skip_shell") { // 1 (default): the one-pass kernel skips UPML boxes that span whole planes / rows, 0: passes them through
 		skip_req = value != 0;
 		if (finalized) return rebuild_schedule();
@@ -2127,6 +2152,7 @@ int Engine::get_option(const char* key, long long* value)
 	if (!value) return fail("get_option: null pointer");
 	if (k == "fused") { *value = fused_active ? 1 : 0; return 0; }
 	if (k == "tma") { *value = (fused_active && tma_active) ? 1 : 0; return 0; }
+	if (k == "pdl") { *value = g_pdl; return 0; }
 	if (k == "skip_shell") { *value = fused_active ? skip_active : 0; return 0; }
 	// rows / local planes the one-pass kernel works on (the all-UPML planes / rows at the mesh ends are skipped)
 	if (k == "onepass_rows") { *value = fused_active ? pF[0].je - pF[0].jb : 0; return 0; }
@@ -2395,7 +2421,7 @@ int Engine::energy(double* e)
 	const long long rows = (long long)(p.k1 - p.k0) * (p.ny - 1);
 	if (rows > 0) {
 		const unsigned blocks = (unsigned)std::min<long long>((rows + 7) / 8, 148 * 8);
-		k_energy<<<blocks, dim3(32, 8), 0, stream>>>(p);
+		launch_k(k_energy, blocks, dim3(32, 8), 0, stream, p);
 		++kernels_launched;
 	}
 	double acc[2];
@@ -2418,7 +2444,7 @@ int Engine::fill_fields(unsigned long long seed)
 	p.seed = seed;
 	const long long rows = (long long)nzl * gn[1];
 	const unsigned blocks = (unsigned)std::min<long long>((rows + 7) / 8, 148 * 16);
-	k_fill<<<blocks, dim3(32, 8), 0, stream>>>(p);
+	launch_k(k_fill, blocks, dim3(32, 8), 0, stream, p);
 	++kernels_launched;
 	CK(cudaStreamSynchronize(stream));
 	return 0;
@@ -2439,7 +2465,7 @@ int Engine::field_digest(int is_curr, unsigned long long* out)
 	CK(cudaMemsetAsync(d_acc, 0, sizeof(unsigned long long), stream));
 	const long long rows = (long long)(p.k1 - p.k0) * gn[1];
 	const unsigned blocks = (unsigned)std::min<long long>((rows + 7) / 8, 148 * 16);
-	k_digest<<<blocks, dim3(32, 8), 0, stream>>>(p);
+	launch_k(k_digest, blocks, dim3(32, 8), 0, stream, p);
 	++kernels_launched;
 	CK(cudaMemcpyAsync(out, d_acc, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
 	CK(cudaStreamSynchronize(stream));
@@ -2661,7 +2687,7 @@ int Engine::read_mode_match_raw(int id, double out[3])
 	ModeParams& M = modes[id];
 	if (ghosts_for_readout()) return 1;
 	M.d.V = sV[cur()]; M.d.I = sI[cur()];
-	k_mode_match<<<1, 32, 0, stream>>>(M);
+	launch_k(k_mode_match, 1, 32, 0, stream, M);
 	++kernels_launched;
 	CK(cudaMemcpyAsync(out, M.out, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
 	CK(cudaStreamSynchronize(stream));
@@ -2699,15 +2725,15 @@ int Engine::exchange_ghosts()
 	if (peer_lo) {
 		GhostPushParams g{sV[c], sI[c], peer_lo_Vs[c], peer_lo_Is[c], (long long)((int)zb - z0) * plane, peer_lo_ghostE_off, comp, peer_lo_comp,
 		                  plane, d_flagE + FLAG_GCNT, peer_lo_flags + FLAG_G_HI, ghost_seq};
-		k_ghost_push<<<64, 256, 0, stream>>>(g);
+		launch_k(k_ghost_push, 64, 256, 0, stream, g);
 	}
 	if (peer_hi) {
 		GhostPushParams g{sV[c], sI[c], peer_hi_Vs[c], peer_hi_Is[c], (long long)((int)ze - 1 - z0) * plane, peer_hi_ghostH_off, comp, peer_hi_comp,
 		                  plane, d_flagE + FLAG_GCNT + 1, peer_hi_flags + FLAG_G_LO, ghost_seq};
-		k_ghost_push<<<64, 256, 0, stream>>>(g);
+		launch_k(k_ghost_push, 64, 256, 0, stream, g);
 	}
 	FlagParams w{{peer_lo ? d_flagE + FLAG_G_LO : nullptr, peer_hi ? d_flagE + FLAG_G_HI : nullptr}, ghost_seq, d_halo_err, halo_timeout_cycles()};
-	k_flag_wait<<<1, 1, 0, stream>>>(w);
+	launch_k(k_flag_wait, 1, 1, 0, stream, w);
 	kernels_launched += 1 + (peer_lo != nullptr) + (peer_hi != nullptr);
 	ghost_open = true;
 	ghost_ts = numTS_host;
@@ -2720,9 +2746,9 @@ int Engine::release_ghosts()
 	if (!ghost_open) return 0;
 	CK(cudaSetDevice(device));
 	FlagParams a{{peer_lo ? peer_lo_flags + FLAG_ACK_HI : nullptr, peer_hi ? peer_hi_flags + FLAG_ACK_LO : nullptr}, ghost_seq, d_halo_err, 0};
-	k_flag_set<<<1, 1, 0, stream>>>(a);
+	launch_k(k_flag_set, 1, 1, 0, stream, a);
 	FlagParams w{{peer_lo ? d_flagE + FLAG_ACK_LO : nullptr, peer_hi ? d_flagE + FLAG_ACK_HI : nullptr}, ghost_seq, d_halo_err, halo_timeout_cycles()};
-	k_flag_wait<<<1, 1, 0, stream>>>(w);
+	launch_k(k_flag_wait, 1, 1, 0, stream, w);
 	kernels_launched += 2;
 	ghost_open = false;
 	CK(cudaGetLastError());

@@ -12,6 +12,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Programmatic dependent launch (Engine::launch_k): a kernel may be set up while its predecessor in the stream is still
+// running.  First statement of EVERY kernel: let the successor's launch begin (small grids only: blocks of a successor
+// that sit on an SM waiting would take slots from a predecessor that still has blocks to schedule), then wait until the
+// predecessor grid has completed and its memory operations are visible.  Without the launch attribute both are no-ops.
+#define PDL_EARLY_MAX_BLOCKS 1184   // 8 x 148
+#define PDL_PROLOGUE()                                                                                         \
+	do {                                                                                                       \
+		if (gridDim.x * gridDim.y * gridDim.z <= PDL_EARLY_MAX_BLOCKS) asm volatile("griddepcontrol.launch_dependents;"); \
+		asm volatile("griddepcontrol.wait;" ::: "memory");                                                     \
+	} while (0)
+
 #define OEMS_MAX_PML_BOXES 8
 // tuning macros (overridable from the nvcc command line for sweeps)
 #ifndef OEMS_MIN_BLOCKS
@@ -141,6 +152,7 @@ __device__ __forceinline__ float leap_pml(float X, float m_vv, float m_vi, float
 template <typename IdxT, bool HAS_PML>
 __global__ void __launch_bounds__(256, OEMS_MIN_BLOCKS) k_update_E(const __grid_constant__ StencilParams p)
 {
+	PDL_PROLOGUE();
 	const int lane = threadIdx.x;
 	const int i0 = (blockIdx.x * 32 + lane) * 4;
 	const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -232,6 +244,7 @@ __global__ void __launch_bounds__(256, OEMS_MIN_BLOCKS) k_update_E(const __grid_
 template <typename IdxT, bool HAS_PML>
 __global__ void __launch_bounds__(256, OEMS_MIN_BLOCKS) k_update_H(const __grid_constant__ StencilParams p)
 {
+	PDL_PROLOGUE();
 	const int lane = threadIdx.x;
 	const int i0 = (blockIdx.x * 32 + lane) * 4;
 	const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -345,6 +358,7 @@ struct PmlEdgeParams {
 template <typename IdxT>
 __global__ void k_upml_untouched_H(const __grid_constant__ PmlEdgeParams p)
 {
+	PDL_PROLOGUE();
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= p.count) return;
 	const long long o = p.cell[t];
@@ -408,6 +422,7 @@ __device__ __forceinline__ bool mur_locate(const MurParams& p, long long t, int&
 
 __global__ void k_mur_pre(const __grid_constant__ MurParams p)
 {
+	PDL_PROLOGUE();
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	int m; long long o[2], os[2];
 	if (!mur_locate(p, t, m, o, os)) return;
@@ -416,6 +431,7 @@ __global__ void k_mur_pre(const __grid_constant__ MurParams p)
 }
 __global__ void k_mur_post(const __grid_constant__ MurParams p)
 {
+	PDL_PROLOGUE();
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	int m; long long o[2], os[2];
 	if (!mur_locate(p, t, m, o, os)) return;
@@ -424,6 +440,7 @@ __global__ void k_mur_post(const __grid_constant__ MurParams p)
 }
 __global__ void k_mur_apply(const __grid_constant__ MurParams p)
 {
+	PDL_PROLOGUE();
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	int m; long long o[2], os[2];
 	if (!mur_locate(p, t, m, o, os)) return;
@@ -449,6 +466,7 @@ struct ExcParams {
 };
 __global__ void k_excite(const __grid_constant__ ExcParams p)
 {
+	PDL_PROLOGUE();
 	const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= p.groups) return;
 	const int numTS = (int)*p.numTS;
@@ -485,6 +503,7 @@ struct LorParams {
 };
 __global__ void k_lorentz_pre(const __grid_constant__ LorParams p)
 {
+	PDL_PROLOGUE();
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= p.count) return;
 	const long long c = p.cell[i];
@@ -510,6 +529,7 @@ __global__ void k_lorentz_pre(const __grid_constant__ LorParams p)
 }
 __global__ void k_lorentz_apply(const __grid_constant__ LorParams p)
 {
+	PDL_PROLOGUE();
 	const unsigned i = p.first + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= p.count) return;
 	const long long c = p.cell[i];
@@ -539,6 +559,7 @@ struct RlcParams {
 __device__ __forceinline__ unsigned ring(unsigned ts_plus1, unsigned q) { return (q + 3u - ts_plus1 % 3u) % 3u; }
 __global__ void k_rlc_pre(const __grid_constant__ RlcParams p)
 {
+	PDL_PROLOGUE();
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= p.count) return;
 	const unsigned r = *p.numTS + 1; // rotation count after this call
@@ -547,6 +568,7 @@ __global__ void k_rlc_pre(const __grid_constant__ RlcParams p)
 }
 __global__ void k_rlc_apply(const __grid_constant__ RlcParams p)
 {
+	PDL_PROLOGUE();
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= p.count) return;
 	const unsigned r = *p.numTS + 1;
@@ -597,6 +619,7 @@ __device__ __forceinline__ unsigned tfsf_lookup(unsigned numTS, unsigned n, unsi
 }
 __global__ void k_tfsf(const __grid_constant__ TfsfParams p)
 {
+	PDL_PROLOGUE();
 	const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= p.groups) return;
 	const unsigned numTS = *p.numTS;
@@ -629,24 +652,28 @@ struct SheetParams {
 };
 __global__ void k_sheet_pre(const __grid_constant__ SheetParams p)
 {
+	PDL_PROLOGUE();
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= p.count) return;
 	p.store[t] = fsub(p.X[p.os[t]], fmul(p.K1[t], p.X[p.o[t]]));          // :128-129, :246-247
 }
 __global__ void k_sheet_post(const __grid_constant__ SheetParams p)
 {
+	PDL_PROLOGUE();
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= p.count) return;
 	p.store[t] = fadd(p.store[t], fmul(p.K1[t], p.X[p.os[t]]));           // :164-165, :303-304
 }
 __global__ void k_sheet_apply_V(const __grid_constant__ SheetParams p)
 {
+	PDL_PROLOGUE();
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= p.count) return;
 	p.X[p.o[t]] = p.store[t];                                               // :199-200
 }
 __global__ void k_sheet_apply_I(const __grid_constant__ SheetParams p)
 {
+	PDL_PROLOGUE();
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= p.count) return;
 	// (Hsa*K2 + Hc)/(K2 + 1.0): float numerator, double denominator                       :355-356
@@ -654,13 +681,15 @@ __global__ void k_sheet_apply_I(const __grid_constant__ SheetParams p)
 	p.X[p.o[t]] = (float)__ddiv_rn((double)num, __dadd_rn((double)p.K2[t], 1.0));
 }
 
-__global__ void k_tick(unsigned* numTS) { *numTS += 1; }
+__global__ void k_tick(unsigned* numTS) {
+	PDL_PROLOGUE(); *numTS += 1; }
 
 // upload helper: expands an operator index given as unique xy planes + one plane id per z into the per-cell
 // index idx[z][y][pitch] (padding cells point at the all-zero entry `pad`)
 template <typename IdxT>
 __global__ void k_expand_planes(IdxT* idx, const IdxT* uplanes, const unsigned* plane_of_z, int z0, long long rows, int nx, int ny, int pitch, IdxT pad)
 {
+	PDL_PROLOGUE();
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; // one thread per (row, x)
 	if (t >= rows * pitch) return;
 	const long long r = t / pitch;
@@ -673,6 +702,7 @@ __global__ void k_expand_planes(IdxT* idx, const IdxT* uplanes, const unsigned* 
 template <typename IdxT>
 __global__ void k_fill_index_padding(IdxT* idx, long long rows, int nx, int pitch, IdxT value)
 {
+	PDL_PROLOGUE();
 	const int pad = pitch - nx;
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (pad <= 0 || t >= rows * pad) return;
@@ -697,6 +727,7 @@ struct ProbeParams {
 };
 __global__ void k_probes(const __grid_constant__ ProbeParams p)
 {
+	PDL_PROLOGUE();
 	const unsigned pr = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
 	const unsigned lane = threadIdx.x % 32;
 	if (pr >= p.nprobes) return;
@@ -739,6 +770,7 @@ struct EnergyParams {
 };
 __global__ void k_energy(const __grid_constant__ EnergyParams p)
 {
+	PDL_PROLOGUE();
 	double e = 0.0, h = 0.0;
 	const long long rows = (long long)(p.k1 - p.k0) * (p.ny - 1);
 	for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y) {
@@ -791,6 +823,7 @@ struct FillParams {
 // direction keeps H = 0 as in any reachable state (ii = iv = 0 there, operator.cpp:1176-1183)
 __global__ void k_fill(const __grid_constant__ FillParams p)
 {
+	PDL_PROLOGUE();
 	const long long rows = (long long)p.nzl * p.ny;
 	for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y) {
 		const int kl = (int)(r / p.ny), j = (int)(r % p.ny);
@@ -819,6 +852,7 @@ struct DigestParams {
 // order-independent: sum over owned cells and components of mix(global index, bits) mod 2^64
 __global__ void k_digest(const __grid_constant__ DigestParams p)
 {
+	PDL_PROLOGUE();
 	unsigned long long d = 0;
 	const long long rows = (long long)(p.k1 - p.k0) * p.ny;
 	for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y) {
@@ -860,6 +894,7 @@ struct SsParams {
 __device__ __forceinline__ bool ss_due(const SsParams& p) { const unsigned ts = *p.numTS; return ts % p.period == 0 && ts >= 2 * p.period; }
 __global__ void k_ss_record(const __grid_constant__ SsParams p)
 {
+	PDL_PROLOGUE();
 	const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned ts = *p.numTS;
 	if (n < p.count) p.rec[(size_t)(ts % (2 * p.period)) * p.count + n] = (double)p.V[p.off[n]];
@@ -867,6 +902,7 @@ __global__ void k_ss_record(const __grid_constant__ SsParams p)
 }
 __global__ void k_ss_energy(const __grid_constant__ SsParams p)
 {
+	PDL_PROLOGUE();
 	if (!ss_due(p)) return;
 	double e = 0.0, h = 0.0;
 	const long long rows = (long long)(p.k1 - p.k0) * (p.ny - 1);
@@ -890,6 +926,7 @@ __global__ void k_ss_energy(const __grid_constant__ SsParams p)
 }
 __global__ void k_ss_snapshot(const __grid_constant__ SsParams p)
 {
+	PDL_PROLOGUE();
 	if (!ss_due(p)) return;
 	const size_t n = (size_t)2 * p.period * p.count;
 	for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) p.snap[q] = p.rec[q];
@@ -932,6 +969,7 @@ struct FdParams {
 };
 __global__ void k_fd_accumulate(const __grid_constant__ FdParams p)
 {
+	PDL_PROLOGUE();
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= p.n) return;
 	const float v = p.td[t];
@@ -1017,6 +1055,7 @@ __device__ __forceinline__ void field_interp(const DumpParams& p, const int pos[
 
 __global__ void k_dump(const __grid_constant__ DumpParams p)
 {
+	PDL_PROLOGUE();
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long cnt = (long long)p.onx * p.ony * p.onz;
 	if (t >= cnt) return;
@@ -1050,6 +1089,7 @@ struct ModeParams {
 };
 __global__ void k_mode_match(const __grid_constant__ ModeParams p)
 {
+	PDL_PROLOGUE();
 	const unsigned lane = threadIdx.x;
 	const unsigned npts = p.nl0 * p.nl1;
 	const int nP = (p.ny + 1) % 3, nPP = (p.ny + 2) % 3;
@@ -1104,6 +1144,7 @@ struct HaloParams {
 };
 __global__ void k_halo_push(const __grid_constant__ HaloParams p)
 {
+	PDL_PROLOGUE();
 	const long long n4 = p.n / 4;
 	for (int c = 0; c < 2; ++c) {
 		const float4* s = reinterpret_cast<const float4*>(p.src + c * p.src_comp + p.src_plane_off);
@@ -1132,6 +1173,7 @@ struct WaitParams {
 };
 __global__ void k_halo_wait(const __grid_constant__ WaitParams p)
 {
+	PDL_PROLOGUE();
 	const unsigned want = *p.numTS + p.flag_add;
 	const long long t0 = clock64();
 	while ((int)(*p.flag - want) < 0) {
@@ -1170,6 +1212,7 @@ struct GhostPushParams {
 };
 __global__ void k_ghost_push(const __grid_constant__ GhostPushParams p)
 {
+	PDL_PROLOGUE();
 	const long long n4 = p.n / 4;
 	for (int c = 0; c < 6; ++c) {
 		const float* sb = c < 3 ? p.srcV : p.srcI;
@@ -1200,6 +1243,7 @@ struct FlagParams {
 };
 __global__ void k_flag_set(const __grid_constant__ FlagParams p)
 {
+	PDL_PROLOGUE();
 	__threadfence_system();
 	for (int q = 0; q < 2; ++q)
 		if (p.flag[q]) *p.flag[q] = p.value;
@@ -1207,6 +1251,7 @@ __global__ void k_flag_set(const __grid_constant__ FlagParams p)
 }
 __global__ void k_flag_wait(const __grid_constant__ FlagParams p)
 {
+	PDL_PROLOGUE();
 	const long long t0 = clock64();
 	for (int q = 0; q < 2; ++q) {
 		if (!p.flag[q]) continue;

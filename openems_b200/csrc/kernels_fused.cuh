@@ -72,6 +72,7 @@ __device__ __forceinline__ float leap_pml_oop(float X, float m_vv, float m_vi, f
 template <typename IdxT, bool HAS_PML>
 __global__ void __launch_bounds__(32 * (FUSED_TY + 1), 2) k_fused_EH(const __grid_constant__ FusedParams p)
 {
+	PDL_PROLOGUE();
 	__shared__ float4 xV0[3][FUSED_TY + 1][32];
 	__shared__ float4 xV2[3][FUSED_TY + 1][32];
 
@@ -272,6 +273,7 @@ struct FixParams {
 template <typename IdxT>
 __global__ void k_fix_H(const __grid_constant__ FixParams p)
 {
+	PDL_PROLOGUE();
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= p.count) return;
 	const int x = p.cell[3 * t], j = p.cell[3 * t + 1], k = p.cell[3 * t + 2];
@@ -361,6 +363,7 @@ __device__ __forceinline__ bool shell_earlier_box(const ShellParams& p, int b, i
 template <typename IdxT>
 __global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_E(const __grid_constant__ ShellParams p)
 {
+	PDL_PROLOGUE();
 	const ShellBlock sb = shell_block(p);
 	const ShellBoxParams& q = p.box[sb.b];
 	const int XL = q.xl;
@@ -476,6 +479,7 @@ __global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_E(const __grid_
 template <typename IdxT>
 __global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_H(const __grid_constant__ ShellParams p)
 {
+	PDL_PROLOGUE();
 	const ShellBlock sb = shell_block(p);
 	const ShellBoxParams& q = p.box[sb.b];
 	const int XL = q.xl;
@@ -580,5 +584,6 @@ __global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_H(const __grid_
 // kernel does not write (ghost planes are filled by the halo pushes)
 __global__ void k_copy_f4(const float4* __restrict__ src, float4* __restrict__ dst, long long n4)
 {
+	PDL_PROLOGUE();
 	for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) dst[q] = src[q];
 }

@@ -127,6 +127,7 @@ template <> struct SIdx4<uint32_t> {
 template <typename IdxT, bool HAS_PML, int STAGES, bool LOR = false>
 __global__ void __launch_bounds__(32 * (FUSED_TY + 1), FT_MIN_BLOCKS) k_fused_tma(const __grid_constant__ FusedTmaParams P)
 {
+	PDL_PROLOGUE();
 	extern __shared__ __align__(128) unsigned char ft_smem[];
 	typedef FtStage<IdxT> ST;
 	const FusedParams& p = P.f;

@@ -64,6 +64,7 @@ __device__ __forceinline__ bool xslab_in_shell(const XSlabParams& p, int chunk, 
 template <typename IdxT>
 __global__ void __launch_bounds__(256) k_xslab_EH(const __grid_constant__ XSlabParams p)
 {
+	PDL_PROLOGUE();
 	__shared__ float rV[3][3][XSLAB_ROWS + 1][16]; // [slot][component][row][x]
 
 	const XSlabBox& B = p.box[blockIdx.z];

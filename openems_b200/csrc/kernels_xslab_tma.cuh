@@ -62,6 +62,7 @@ template <typename IdxT, int STAGES> constexpr int xt_smem_bytes()
 template <typename IdxT, int STAGES>
 __global__ void __launch_bounds__(XT_THREADS, XT_MIN_BLOCKS) k_xslab_tma(const __grid_constant__ XTmaParams P)
 {
+	PDL_PROLOGUE();
 	extern __shared__ __align__(128) unsigned char xt_smem[];
 	typedef XtStage<IdxT> ST;
 	const XSlabParams& p = P.x;

@@ -139,6 +139,23 @@ def test_graded_mesh_wide_operator_index():
     assert_fields_equal(eng, s, "graded mesh, register-staged one-pass kernel")
 
 
+def test_programmatic_dependent_launch():
+    """option "pdl": every kernel of the timestep graph is launched with the programmatic-stream-serialization attribute
+    and starts with griddepcontrol.wait; same bits as plain stream order, both schedules, mixed boundary conditions"""
+    s = cases.engine_cavity()
+    eng = operator_from_oracle(s).CreateEngine()
+    try:
+        for steps, pdl, fused in ((5, 1, 1), (20, 1, 0), (7, 0, 1), (40, 1, 1)):
+            eng.SetOption("pdl", pdl)
+            eng.SetOption("fused", fused)
+            assert eng.GetOption("pdl") == pdl
+            s.iterate(steps)
+            eng.IterateTS(steps)
+            assert_fields_equal(eng, s, "pdl=%d fused=%d" % (pdl, fused))
+    finally:
+        eng.SetOption("pdl", 0)   # process-wide switch
+
+
 @pytest.mark.parametrize("n,pml", [((23, 26, 21), 4), ((150, 20, 18), 8), ((300, 12, 40), 8), ((12, 7, 60), 1)])
 def test_x_slab_boxes_inside_the_one_pass_kernel(n, pml):
     """option "xslab": the UPML boxes at the x ends are updated by lanes of the TMA one-pass kernel
