@@ -7,6 +7,8 @@
  * Engine_CUDA;` line per operator_ext header) and hands them to the library.
  */
 #include "engine_cuda.h"
+#include <thread>
+#include <algorithm>
 #include "operator_cuda.h"
 #include "extensions/operator_ext_excitation.h"
 #include "extensions/operator_ext_upml.h"
@@ -64,18 +66,32 @@ void Engine_CUDA::Init()
 	// no host field arrays: volt_ptr / curr_ptr stay NULL (all accessors are overridden)
 	Check( oems_cuda_create(numLines[0], numLines[1], numLines[2], m_Op_CUDA->GetDevice(), &m_h), "Init" );
 
-	// dense coefficients in ArrayNIJK order, as the C ABI wants them
+	// dense coefficients in ArrayNIJK order, as the C ABI wants them.  The operator keeps them in the lane-interleaved
+	// f4vector layout of Operator_sse (z -> (z % numVectors, lane z / numVectors), operator_sse.h:35-57), so this is a
+	// gather through the accessors, done once and spread over the host threads (one x range each)
 	const size_t N = (size_t)numLines[0]*numLines[1]*numLines[2];
 	std::vector<FDTD_FLOAT> vv(3*N), vi(3*N), ii(3*N), iv(3*N);
-	size_t p=0;
-	for (unsigned int n=0; n<3; ++n)
-		for (unsigned int x=0; x<numLines[0]; ++x)
-			for (unsigned int y=0; y<numLines[1]; ++y)
-				for (unsigned int z=0; z<numLines[2]; ++z, ++p)
-				{
-					vv[p] = Op->GetVV(n,x,y,z); vi[p] = Op->GetVI(n,x,y,z);
-					ii[p] = Op->GetII(n,x,y,z); iv[p] = Op->GetIV(n,x,y,z);
-				}
+	{
+		unsigned int nt = std::max(1u, std::min(std::thread::hardware_concurrency(), numLines[0]));
+		std::vector<std::thread> pool;
+		for (unsigned int t=0; t<nt; ++t)
+			pool.emplace_back([&, t]()
+			{
+				const unsigned int x0 = (unsigned int)((size_t)numLines[0]*t/nt), x1 = (unsigned int)((size_t)numLines[0]*(t+1)/nt);
+				for (unsigned int n=0; n<3; ++n)
+					for (unsigned int x=x0; x<x1; ++x)
+						for (unsigned int y=0; y<numLines[1]; ++y)
+						{
+							size_t p = (((size_t)n*numLines[0] + x)*numLines[1] + y)*numLines[2];
+							for (unsigned int z=0; z<numLines[2]; ++z, ++p)
+							{
+								vv[p] = Op->GetVV(n,x,y,z); vi[p] = Op->GetVI(n,x,y,z);
+								ii[p] = Op->GetII(n,x,y,z); iv[p] = Op->GetIV(n,x,y,z);
+							}
+						}
+			});
+		for (std::thread& th : pool) th.join();
+	}
 	Check( oems_cuda_set_operator_dense(m_h, vv.data(), vi.data(), ii.data(), iv.data()), "set_operator" );
 
 	InitExtensions();

@@ -1675,6 +1675,7 @@ void Engine::build_schedule_fused()
 		}
 		// one entry of the two shell launches: rows [jr0, jr1) (box-local) and local planes [k0, k1) of box B
 		int nent = 0;
+		int xs_sh[2] = {-1, -1};
 		auto add_shell = [&](const PmlBox& B, int jr0, int jr1, int k0, int k1, bool pingpong = false) {
 			if (jr1 <= jr0 || k1 <= k0 || nent >= OEMS_MAX_SHELL_ENTRIES) return;
 			ShellBoxParams q;
@@ -1724,6 +1725,17 @@ void Engine::build_schedule_fused()
 				// skipped planes / rows go through the shell launches like the other boxes' cells there
 				Q.oj0 = std::max(B.s[1], F.jb); Q.oj1 = std::min(B.s[1] + B.n[1], F.je);
 				Q.ok0 = std::max(B.s[2], F.kE0); Q.ok1 = std::min(B.s[2] + B.n[2], F.kE1);
+				if (xslab_tma && ns < OEMS_MAX_PML_BOXES) {
+					// the big kernel need not compute the window cells (graded UPML coefficients: a table gather per
+					// cell): it passes them through like shell cells and k_xslab_tma overwrites them.  Not the first
+					// chunk of the high window: the plain cell left of the window takes its E_new from there.
+					const int wc0 = Q.w0 / 4 + (g == 1 ? 1 : 0), wcn = 4 - (g == 1 ? 1 : 0);
+					F.sh[ns].c0 = wc0; F.sh[ns].cn = wcn;
+					F.sh[ns].j0 = Q.oj0; F.sh[ns].jn = Q.oj1 - Q.oj0;
+					F.sh[ns].k0 = Q.ok0; F.sh[ns].kn = Q.ok1 - Q.ok0;
+					xs_sh[g] = ns;
+					++ns;
+				}
 				if (xslab_tma) {
 					add_shell(B, 0, B.n[1], B.s[2], Q.ok0, true);
 					add_shell(B, 0, B.n[1], Q.ok1, B.s[2] + B.n[2], true);
@@ -1740,9 +1752,16 @@ void Engine::build_schedule_fused()
 		}
 		F.nsh = ns;
 		SE.nboxes = SH.nboxes = nent;
-		XP.nsh = ns;
 		XP.jb = F.jb; XP.je = F.je;
-		for (int q = 0; q < ns; ++q) { XP.sh[q].c0 = F.sh[q].c0; XP.sh[q].cn = F.sh[q].cn; XP.sh[q].j0 = F.sh[q].j0; XP.sh[q].jn = F.sh[q].jn; XP.sh[q].k0 = F.sh[q].k0; XP.sh[q].kn = F.sh[q].kn; }
+		{   // the window kernel's list of foreign footprints: the boxes on the shell path, not its own windows
+			int m = 0;
+			for (int q = 0; q < ns; ++q) {
+				if (q == xs_sh[0] || q == xs_sh[1]) continue;
+				XP.sh[m].c0 = F.sh[q].c0; XP.sh[m].cn = F.sh[q].cn; XP.sh[m].j0 = F.sh[q].j0; XP.sh[m].jn = F.sh[q].jn; XP.sh[m].k0 = F.sh[q].k0; XP.sh[m].kn = F.sh[q].kn;
+				++m;
+			}
+			XP.nsh = m;
+		}
 		for (ShellParams* w : {&SE, &SH}) {
 			unsigned nb = 0;
 			for (int b = 0; b < w->nboxes; ++b) {

@@ -14,7 +14,11 @@
 //   * stages its inputs like k_fused_tma: three bulk tensor copies per plane (H 24 x 17 x 3, E 24 x 16 x 3, index
 //     24 x 16) into a ring of STAGES shared-memory stages with one mbarrier each, so several planes of every block
 //     are in flight and HBM latency is covered by the ring, not by occupancy;
-//   * one float4 chunk per thread, 4 lanes side by side in x, 16 rows (15 + halo row) = 64 threads per block;
+//   * one float4 chunk per thread, 4 lanes side by side in x, 16 rows (15 + halo row) = 64 threads per block.  Other
+//     thread mappings were tried and are slower (profiles/experiments_r02.md #9): a warp per chunk column inside one
+//     block (straight-line UPML / plain code, but the plain warp waits at the per-plane barrier: 1.11 ms), a warp per
+//     chunk column as its own block (no barrier, but the columns drift apart in z and the 32-byte sectors they share
+//     are fetched and written half-filled several times: 2.9 ms), one interleaved coefficient table (0.94 ms);
 //     same E_new(kk) -> ring -> H_new(kk-1) schedule, helpers and roundings as everywhere else: bit-identical.
 // The voltage flux is ping-ponged with the field sets (E of halo rows / the extra plane is recomputed by
 // neighbouring blocks), the current flux is updated in place.  Cells of the window that belong to ANOTHER box
