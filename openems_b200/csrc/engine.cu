@@ -1231,6 +1231,9 @@ void Engine::build_schedule()
 	// GPU with z-marching blocks: below ~160^3 cells the two-pass kernels, which have a thread per cell
 	// column and z chunk, are faster (tools/size_sweep.py, profiles/experiments_r01.md #13)
 	fused_active = fused_possible && !edge_dirty && (fused_req == 1 || (fused_req < 0 && fused_auto_choice())) && !(lor_fused && !tma_req);
+	// two-pass kernels with one cell per thread below 300 M cells per GPU (faster than the float4 z-march kernels up
+	// to 640^3, equal at 1024 x 1024 x 512; option "small": 1 / 0 force, -1 automatic)
+	small_active = small_req > 0 || (small_req < 0 && (long long)gn[0] * gn[1] * (ze - zb) < small_max_cells);
 	const bool i16 = index_bytes == 2;
 	const dim3 block(32, tune_rows);
 	auto stencil_grid = [&](const StencilParams& p, int rows_total) {
@@ -1260,6 +1263,12 @@ void Engine::build_schedule()
 	// ---- E half-step with fused UPML
 	if (pE.k1 > pE.k0)
 		(labels.push_back("update_E"), step.push_back([this, i16, block, stencil_grid](cudaStream_t s) {
+			if (small_active) { // one cell per thread (small meshes)
+				const dim3 g((unsigned)((gn[0] + 31) / 32), (unsigned)((pE.ny + tune_rows - 1) / tune_rows), (unsigned)(pE.k1 - pE.k0));
+				if (i16) { if (has_pml) launch_k(k_small_E<uint16_t, true>, g, block, 0, s, pE); else launch_k(k_small_E<uint16_t, false>, g, block, 0, s, pE); }
+				else { if (has_pml) launch_k(k_small_E<uint32_t, true>, g, block, 0, s, pE); else launch_k(k_small_E<uint32_t, false>, g, block, 0, s, pE); }
+				return;
+			}
 			const dim3 g = stencil_grid(pE, pE.ny);
 			if (i16) { if (has_pml) launch_k(k_update_E<uint16_t, true>, g, block, 0, s, pE); else launch_k(k_update_E<uint16_t, false>, g, block, 0, s, pE); }
 			else { if (has_pml) launch_k(k_update_E<uint32_t, true>, g, block, 0, s, pE); else launch_k(k_update_E<uint32_t, false>, g, block, 0, s, pE); }
@@ -1304,6 +1313,12 @@ void Engine::build_schedule()
 	// ---- H half-step with fused UPML, then the UPML cells the stencil never visits
 	if (pH.k1 > pH.k0)
 		(labels.push_back("update_H"), step.push_back([this, i16, block, stencil_grid](cudaStream_t s) {
+			if (small_active) {
+				const dim3 g((unsigned)((gn[0] - 1 + 31) / 32), (unsigned)((pH.ny - 1 + tune_rows - 1) / tune_rows), (unsigned)(pH.k1 - pH.k0));
+				if (i16) { if (has_pml) launch_k(k_small_H<uint16_t, true>, g, block, 0, s, pH); else launch_k(k_small_H<uint16_t, false>, g, block, 0, s, pH); }
+				else { if (has_pml) launch_k(k_small_H<uint32_t, true>, g, block, 0, s, pH); else launch_k(k_small_H<uint32_t, false>, g, block, 0, s, pH); }
+				return;
+			}
 			const dim3 g = stencil_grid(pH, pH.ny - 1);
 			if (i16) { if (has_pml) launch_k(k_update_H<uint16_t, true>, g, block, 0, s, pH); else launch_k(k_update_H<uint16_t, false>, g, block, 0, s, pH); }
 			else { if (has_pml) launch_k(k_update_H<uint32_t, true>, g, block, 0, s, pH); else launch_k(k_update_H<uint32_t, false>, g, block, 0, s, pH); }
@@ -2039,7 +2054,9 @@ int Engine::rebuild_schedule()
 
 bool Engine::fused_auto_choice() const
 {
-	return (long long)gn[0] * gn[1] * (long long)(ze - zb) >= 4000000ll;
+	// measured crossover (profiles/experiments_r02.md #10): the one-cell-per-thread two-pass kernels equal the one-pass
+	// schedule at 256^3 (16.8 M cells) and lose 8 % at 320^3
+	return (long long)gn[0] * gn[1] * (long long)(ze - zb) >= fused_min_cells;
 }
 
 // switching between the one-pass and the two-pass schedule keeps the current fields: the two-pass
@@ -2125,6 +2142,21 @@ int Engine::set_option(const char* key, long long value)
 		if (finalized) return rebuild_schedule();
 		return 0;
 	}
+	if (k == "small") { // two-pass stencil kernels with one cell per thread: 1 / 0 / -1 = automatic (small meshes)
+		small_req = value < 0 ? -1 : (value != 0);
+		if (finalized) return rebuild_schedule();
+		return 0;
+	}
+	if (k == "fused_min_cells") { // automatic schedule choice: one-pass from this many cells per GPU
+		fused_min_cells = value;
+		if (finalized && fused_req < 0) return set_fused_active(-1);
+		return 0;
+	}
+	if (k == "small_max_cells") {
+		small_max_cells = value;
+		if (finalized) return rebuild_schedule();
+		return 0;
+	}
 	if (k == "pdl") { // 1: programmatic dependent launch between the kernels of a timestep (process-wide)
 		g_pdl = value != 0;
 		if (finalized) return rebuild_schedule();
@@ -2172,6 +2204,7 @@ int Engine::get_option(const char* key, long long* value)
 	if (k == "fused") { *value = fused_active ? 1 : 0; return 0; }
 	if (k == "tma") { *value = (fused_active && tma_active) ? 1 : 0; return 0; }
 	if (k == "pdl") { *value = g_pdl; return 0; }
+	if (k == "small") { *value = !fused_active && small_active; return 0; }
 	if (k == "skip_shell") { *value = fused_active ? skip_active : 0; return 0; }
 	// rows / local planes the one-pass kernel works on (the all-UPML planes / rows at the mesh ends are skipped)
 	if (k == "onepass_rows") { *value = fused_active ? pF[0].je - pF[0].jb : 0; return 0; }

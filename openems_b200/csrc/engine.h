@@ -285,6 +285,10 @@ private:
 	XTmaParams pXt[2];           // the same + TMA descriptors (k_xslab_tma)
 	bool xslab_tma = false;
 	bool skip_req = true;        // option "skip_shell"
+	int small_req = -1;          // option "small": one-cell-per-thread two-pass kernels (k_small_E / k_small_H)
+	long long small_max_cells = 300000000;
+	long long fused_min_cells = 20000000;   // automatic schedule choice (option "fused_min_cells")
+	bool small_active = false;
 	int skip_active = 0;         // boxes the one-pass kernel skips
 	int xs_win[2] = {0, 0};      // first line of the 16-line windows of k_xslab_tma
 	int xt_zchunk = 16;

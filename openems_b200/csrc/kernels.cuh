@@ -337,6 +337,96 @@ __global__ void __launch_bounds__(256, OEMS_MIN_BLOCKS) k_update_H(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------
+// Small meshes (a few 10^5 cells: the tutorial configs C1-C3): the same two half-steps with ONE CELL PER THREAD.
+// k_update_E / k_update_H give every thread four cells and a z march -- the right shape to stream a large mesh,
+// but a 196 k cell mesh then runs on 10 warps per SM and a timestep half costs 8-13 us of exposed load latency
+// (profiles/experiments_r02.md #10).  Here a thread updates one cell of one plane: four times the warps, all loads
+// of a cell independent of each other except the coefficient gather behind the index load; the neighbours come
+// through L1/L2 (the mesh fits L2 many times over).  Same helpers, same operand order: bit-identical.
+// block = (32, rows), grid = (ceil(nx / 32), ceil(ny / rows), planes).
+// ---------------------------------------------------------------------------------------
+template <typename IdxT, bool HAS_PML>
+__global__ void __launch_bounds__(256) k_small_E(const __grid_constant__ StencilParams p)
+{
+	PDL_PROLOGUE();
+	const int i = blockIdx.x * 32 + threadIdx.x;
+	const int j = blockIdx.y * blockDim.y + threadIdx.y;
+	const int k = p.k0 + blockIdx.z;
+	if (i >= p.nx || j >= p.ny || k >= p.k1) return;
+	const long long o = (long long)k * p.plane + (long long)j * p.pitch + i;
+	const long long om = o - (j > 0 ? p.pitch : 0);
+	const long long ok = o - (k > 0 ? p.plane : 0);   // z-1 clamp only at the bottom of the (local) domain
+	const long long ox = o - (i > 0 ? 1 : 0);
+	const float* __restrict__ I0 = p.I;
+	const float* __restrict__ I1 = p.I + p.comp;
+	const float* __restrict__ I2 = p.I + 2 * p.comp;
+	const unsigned e = reinterpret_cast<const IdxT*>(p.idx)[o];
+	const float i0c = I0[o], i1c = I1[o], i2c = I2[o];
+	const float i0jm = I0[om], i2jm = I2[om];
+	const float i0km = I0[ok], i1km = I1[ok];
+	const float i1xm = I1[ox], i2xm = I2[ox];
+	float v0 = p.V[o], v1 = p.V[p.comp + o], v2 = p.V[2 * p.comp + o];
+	const float4 A = __ldg(p.tA + e), B = __ldg(p.tB + e);
+	// ((a - b) - c) + d, engine.cpp:139-144
+	const float curl0 = fadd(fsub(fsub(i2c, i2jm), i1c), i1km);
+	const float curl1 = fadd(fsub(fsub(i0c, i0km), i2c), i2xm);
+	const float curl2 = fadd(fsub(fsub(i1c, i1xm), i0c), i0jm);
+	if (HAS_PML && A.w != 0.0f) {
+		long long cs;
+		const long long fo = pml_flux_offset(p, i, j, k, cs);
+		if (fo < 0) return; // flagged cell outside the boxes held here: left alone, as in k_update_E
+		const float4 P0 = __ldg(p.tP0 + e), P1 = __ldg(p.tP1 + e), P2 = __ldg(p.tP2 + e);
+		v0 = leap_pml(v0, A.x, B.x, curl0, P0.x, P1.x, P2.x, p.flux + fo, p.flux + fo);
+		v1 = leap_pml(v1, A.y, B.y, curl1, P0.y, P1.y, P2.y, p.flux + fo + cs, p.flux + fo + cs);
+		v2 = leap_pml(v2, A.z, B.z, curl2, P0.z, P1.z, P2.z, p.flux + fo + 2 * cs, p.flux + fo + 2 * cs);
+	} else {
+		v0 = leap(v0, A.x, B.x, curl0);
+		v1 = leap(v1, A.y, B.y, curl1);
+		v2 = leap(v2, A.z, B.z, curl2);
+	}
+	p.V[o] = v0; p.V[p.comp + o] = v1; p.V[2 * p.comp + o] = v2;
+}
+
+template <typename IdxT, bool HAS_PML>
+__global__ void __launch_bounds__(256) k_small_H(const __grid_constant__ StencilParams p)
+{
+	PDL_PROLOGUE();
+	const int i = blockIdx.x * 32 + threadIdx.x;
+	const int j = blockIdx.y * blockDim.y + threadIdx.y;
+	const int k = p.k0 + blockIdx.z;
+	// UpdateCurrents stops one line short in every direction (engine.cpp:179-183; k1 <= held planes - 1: host)
+	if (i >= p.nx - 1 || j >= p.ny - 1 || k >= p.k1) return;
+	const long long o = (long long)k * p.plane + (long long)j * p.pitch + i;
+	const float* __restrict__ V0 = p.V;
+	const float* __restrict__ V1 = p.V + p.comp;
+	const float* __restrict__ V2 = p.V + 2 * p.comp;
+	const unsigned e = reinterpret_cast<const IdxT*>(p.idx)[o];
+	const float v0c = V0[o], v1c = V1[o], v2c = V2[o];
+	const float v0jp = V0[o + p.pitch], v2jp = V2[o + p.pitch];
+	const float v0n = V0[o + p.plane], v1n = V1[o + p.plane];
+	const float v1xp = V1[o + 1], v2xp = V2[o + 1];
+	float c0 = p.I[o], c1 = p.I[p.comp + o], c2 = p.I[2 * p.comp + o];
+	const float4 A = __ldg(p.tA + e), B = __ldg(p.tB + e);
+	const float curl0 = fadd(fsub(fsub(v2c, v2jp), v1c), v1n);
+	const float curl1 = fadd(fsub(fsub(v0c, v0n), v2c), v2xp);
+	const float curl2 = fadd(fsub(fsub(v1c, v1xp), v0c), v0jp);
+	if (HAS_PML && A.w != 0.0f) {
+		long long cs;
+		const long long fo = pml_flux_offset(p, i, j, k, cs);
+		if (fo < 0) return;
+		const float4 P0 = __ldg(p.tP0 + e), P1 = __ldg(p.tP1 + e), P2 = __ldg(p.tP2 + e);
+		c0 = leap_pml(c0, A.x, B.x, curl0, P0.x, P1.x, P2.x, p.flux + fo, p.flux + fo);
+		c1 = leap_pml(c1, A.y, B.y, curl1, P0.y, P1.y, P2.y, p.flux + fo + cs, p.flux + fo + cs);
+		c2 = leap_pml(c2, A.z, B.z, curl2, P0.z, P1.z, P2.z, p.flux + fo + 2 * cs, p.flux + fo + 2 * cs);
+	} else {
+		c0 = leap(c0, A.x, B.x, curl0);
+		c1 = leap(c1, A.y, B.y, curl1);
+		c2 = leap(c2, A.z, B.z, curl2);
+	}
+	p.I[o] = c0; p.I[p.comp + o] = c1; p.I[2 * p.comp + o] = c2;
+}
+
+// ---------------------------------------------------------------------------------------
 // UPML cells the stencil kernels do not visit.  Engine_Ext_UPML runs its pre/post hooks on
 // EVERY cell of a box (engine_ext_upml.cpp:63-90), but UpdateCurrents skips the last line of
 // each direction (engine.cpp:179-183).  For those cells pre+post collapse to

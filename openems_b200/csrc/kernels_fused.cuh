@@ -329,8 +329,9 @@ struct ShellParams {
 	long long plane, comp;
 	int nboxes;
 	unsigned nblocks;
-	// k_shell_E: cells outside the planes [sk0, sk1) / rows [sjb, sje) are skipped by the one-pass kernel: their E_new
-	// is also stored in the destination set Xd2 (NULL: nothing is skipped)
+	// k_shell_E: cells outside the planes [sk0, sk1) / rows [sjb, sje) are skipped by the one-pass kernels: their E_new
+	// is stored in the destination set Xd2 (NULL: nothing is skipped) instead of in place -- in both sets on the
+	// plane sk1 / row sje, which the one-pass kernels read from the source set as +1 neighbours
 	float* Xd2;
 	int sk0, sk1, sjb, sje;
 	ShellBoxParams box[OEMS_MAX_SHELL_ENTRIES];
@@ -446,12 +447,17 @@ __global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_E(const __grid_
 				}
 				done |= 1u << c;
 			}
-			const bool dual = p.Xd2 && (k < p.sk0 || k >= p.sk1 || j < p.sjb || j >= p.sje);
+			// cells the one-pass kernels skip: E_new goes to the destination set; in place (source set) only where a
+			// one-pass kernel reads it as the +y / +z neighbour of its last row / plane
+			const bool skipped = p.Xd2 && (k < p.sk0 || k >= p.sk1 || j < p.sjb || j >= p.sje);
+			const bool inplace = !skipped || k == p.sk1 || j == p.sje;
 			if (done == 15u) {
-				st4(p.Xd + o, v0);
-				st4(p.Xd + p.comp + o, v1);
-				st4(p.Xd + 2 * p.comp + o, v2);
-				if (dual) {
+				if (inplace) {
+					st4(p.Xd + o, v0);
+					st4(p.Xd + p.comp + o, v1);
+					st4(p.Xd + 2 * p.comp + o, v2);
+				}
+				if (skipped) {
 					st4(p.Xd2 + o, v0);
 					st4(p.Xd2 + p.comp + o, v1);
 					st4(p.Xd2 + 2 * p.comp + o, v2);
@@ -460,10 +466,12 @@ __global__ void __launch_bounds__(256, SHELL_MIN_BLOCKS) k_shell_E(const __grid_
 #pragma unroll
 				for (int c = 0; c < 4; ++c)
 					if (done >> c & 1u) {
-						p.Xd[o + c] = comp(v0, c);
-						p.Xd[p.comp + o + c] = comp(v1, c);
-						p.Xd[2 * p.comp + o + c] = comp(v2, c);
-						if (dual) {
+						if (inplace) {
+							p.Xd[o + c] = comp(v0, c);
+							p.Xd[p.comp + o + c] = comp(v1, c);
+							p.Xd[2 * p.comp + o + c] = comp(v2, c);
+						}
+						if (skipped) {
 							p.Xd2[o + c] = comp(v0, c);
 							p.Xd2[p.comp + o + c] = comp(v1, c);
 							p.Xd2[2 * p.comp + o + c] = comp(v2, c);

@@ -12,28 +12,34 @@ pytestmark = pytest.mark.gpu
 
 
 def run_both(s, steps=(1, 2, 17, 80), what="", **kw):
-    """the oracle against BOTH timestep schedules of the CUDA engine (one-pass requested -- it runs
-    where the hook set allows it -- and the two-pass schedule forced); returns the one-pass engine"""
+    """the oracle against ALL timestep schedules of the CUDA engine: one-pass requested (it runs where the hook set
+    allows it), two-pass with one cell per thread (k_small_E/H, the automatic choice on meshes of this size) and
+    two-pass with the float4 / z-march kernels (k_update_E/H, large meshes); returns the one-pass engine"""
     op = operator_from_oracle(s)
     eng = op.CreateEngine()
     eng.SetOption("fused", 1)
     eng2 = op.CreateEngine()
     eng2.SetOption("fused", 0)
-    assert "fused_EH" not in [n for n, _ in eng2.TimeSchedule(0)]
+    assert "fused_EH" not in [n for n, _ in eng2.TimeSchedule(0)] and eng2.GetOption("small") == 1
+    eng3 = op.CreateEngine()
+    eng3.SetOption("fused", 0)
+    eng3.SetOption("small", 0)
+    assert eng3.GetOption("small") == 0
     for k, v in kw.items():
         if k == "tuning":
-            eng.SetTuning(*v)
-            eng2.SetTuning(*v)
+            for e in (eng, eng2, eng3):
+                e.SetTuning(*v)
     total = 0
     for n in steps:
         s.iterate(n)
         total += n
-        for e, name in ((eng, "one-pass requested"), (eng2, "two-pass")):
+        for e, name in ((eng, "one-pass requested"), (eng2, "two-pass, cell per thread"), (eng3, "two-pass, float4 march")):
             e.IterateTS(n)
             assert e.GetNumberOfTimesteps() == s.num_ts == total
             mv, mc = assert_fields_equal(e, s, "%s (%s) after %d steps" % (what, name, total))
     assert mv > 0 and mc > 0, "fields stayed zero: the comparison would be vacuous"
     eng2.close()
+    eng3.close()
     return eng
 
 
@@ -79,19 +85,30 @@ def test_materials_and_metal():
 
 
 def test_one_pass_and_two_pass_schedules_agree_and_are_used():
-    """the one-pass timestep is the automatic choice for meshes of 4 M cells and more when the hook set
-    allows it (smaller ones run faster two-pass), the option forces either; both match the oracle bit
-    for bit, also when toggled mid-run"""
+    """the one-pass timestep is the automatic choice from 20 M cells per GPU when the hook set allows it (smaller
+    meshes run faster on the one-cell-per-thread two-pass kernels), the option forces either; both match the
+    oracle bit for bit, also when toggled mid-run"""
     s = cases.engine_cavity()
     op = operator_from_oracle(s)
     eng = op.CreateEngine()
-    assert eng.GetOption("fused") == 0          # automatic choice on a small mesh
+    assert eng.GetOption("fused") == 0 and eng.GetOption("small") == 1   # automatic choice on a small mesh
     big = cases.uniform_box(n=(200, 170, 130), bc=(BC_PML,) * 6, pml=8)
     eb = operator_from_oracle(big).CreateEngine()
-    assert eb.GetOption("fused") == 1 and eb.GetOption("tma") == 1   # 4.4 M cells: one-pass, TMA-staged
-    big.iterate(12)
-    eb.IterateTS(12)
+    assert eb.GetOption("fused") == 0 and eb.GetOption("small") == 1     # 4.4 M cells: still two-pass, one cell per thread
+    big.iterate(5)
+    eb.IterateTS(5)
+    assert_fields_equal(eb, big, "automatic two-pass (one cell per thread) on a 4.4 M cell mesh")
+    eb.SetOption("fused_min_cells", 4000000)                              # the automatic rule with a lower threshold
+    assert eb.GetOption("fused") == 1 and eb.GetOption("tma") == 1        # one-pass, TMA-staged
+    big.iterate(7)
+    eb.IterateTS(7)
     assert_fields_equal(eb, big, "automatic one-pass on a 4.4 M cell mesh")
+    eb.SetOption("fused", 0)
+    eb.SetOption("small", 0)                                              # the float4 / z-march two-pass kernels
+    assert eb.GetOption("small") == 0
+    big.iterate(4)
+    eb.IterateTS(4)
+    assert_fields_equal(eb, big, "float4 two-pass kernels on a 4.4 M cell mesh")
     eb.close()
     # requested: one-pass, with the UPML boxes on the two-pass shell around it
     eng.SetOption("fused", 1)
