@@ -1343,7 +1343,10 @@ void Engine::build_schedule()
 			             d_halo_cnt + 1, peer_hi_flagH, d_numTS, 1u};
 			launch_k(k_halo_push, 64, 256, 0, s, h);
 		}));
-	(labels.push_back("tick"), step.push_back([this](cudaStream_t s) { launch_k(k_tick, 1, 1, 0, s, d_numTS); }));
+	// the timestep counter: advanced by k_small_H itself when that is the last kernel of the timestep
+	pH.tick = nullptr;
+	if (small_active && !labels.empty() && labels.back() == "update_H" && pH.k1 > pH.k0) pH.tick = d_numTS;
+	else (labels.push_back("tick"), step.push_back([this](cudaStream_t s) { launch_k(k_tick, 1, 1, 0, s, d_numTS); }));
 	kernels_per_step = (unsigned)step.size();
 	if (fused_active) build_schedule_fused();
 

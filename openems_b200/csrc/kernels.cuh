@@ -64,6 +64,7 @@ struct StencilParams {
 	long long comp;      // plane*nz
 	int k0, k1;          // local plane range to update
 	int zchunk;
+	unsigned* tick;      // k_small_H: the timestep counter, advanced by this launch when it is the last kernel of the timestep (else NULL)
 	int nboxes;
 	PmlBox box[OEMS_MAX_PML_BOXES];
 };
@@ -394,6 +395,8 @@ __global__ void __launch_bounds__(256) k_small_H(const __grid_constant__ Stencil
 	const int i = blockIdx.x * 32 + threadIdx.x;
 	const int j = blockIdx.y * blockDim.y + threadIdx.y;
 	const int k = p.k0 + blockIdx.z;
+	// last kernel of the timestep: one thread advances numTS (no kernel of this launch reads it; saves the k_tick launch)
+	if (p.tick && (blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x | threadIdx.y) == 0) *p.tick += 1;
 	// UpdateCurrents stops one line short in every direction (engine.cpp:179-183; k1 <= held planes - 1: host)
 	if (i >= p.nx - 1 || j >= p.ny - 1 || k >= p.k1) return;
 	const long long o = (long long)k * p.plane + (long long)j * p.pitch + i;
