@@ -271,17 +271,26 @@ int oems_cuda_get_stats(oems_cuda_engine* h, oems_cuda_stats* out);
 /* tuning knobs (0 keeps the default): block rows and z-chunk of the stencil kernels, graph on/off */
 int oems_cuda_set_tuning(oems_cuda_engine* h, int block_rows, int z_chunk, int use_graph);
 
-/* named integer options.  "fused" = 0 / 1 / -1: two-pass (in place), one-pass (E and H in one
-   kernel, ping-pong buffers) or automatic choice of the timestep schedule.  Both give identical
-   results.  One-pass needs a hook set without Lorentz/RLC, disjoint UPML boxes and memory for
-   the second field set; automatic picks it whenever that holds.  UPML cells stay on a two-pass
-   "shell" (k_shell_E / k_shell_H) around the one-pass interior. */
+/* named integer options (all variants give identical results; they select kernels):
+   "fused" = 0 / 1 / -1: two-pass (in place), one-pass (E and H in one kernel, ping-pong field sets) or automatic
+     choice of the timestep schedule.  One-pass needs a hook set without lumped RLC, Lorentz/Drude cells only where no
+     other hook reads them between the stencil and Apply2Voltages, disjoint UPML boxes and memory for
+     the second field set; automatic picks it from "fused_min_cells" (default 20 M) cells per GPU.
+   "small" = 0 / 1 / -1: two-pass half-steps with one cell per thread (k_small_E / k_small_H) instead of the float4 /
+     z-march kernels; automatic below "small_max_cells" (default 300 M) cells per GPU.
+   "tma" = 1 / 0: the one-pass kernel stages its inputs in shared memory through TMA bulk tensor copies (default) or
+     loads them into registers itself (k_fused_EH).
+   "xslab" = 2 / 1 / 0: UPML boxes that are thin in x and sit at the x ends of the mesh are updated by the
+     TMA-staged one-pass window kernel k_xslab_tma (default), by k_xslab_EH, or by the shell launches.
+   "skip_shell" = 1 / 0: the one-pass kernels skip the planes / rows at the mesh ends that consist of UPML cells only
+     (default) or pass them through.
+   "pdl" = 0 / 1: programmatic dependent launch between the kernels of a timestep (default off: no gain measured).
+   "halo_timeout_s": seconds a z-slab waits for its neighbour's halo before the device traps (default 600).
+   "xslab_zchunk", "shell_zchunk": planes a block of those kernels marches (tuning aids). */
 int oems_cuda_set_option(oems_cuda_engine* h, const char* key, long long value);
-/* "tma" = 1 / 0: the one-pass kernel stages its inputs in shared memory through TMA bulk tensor
-   copies (default) or loads them into registers itself (k_fused_EH); identical results.
-   "xslab" = 1 / 0 (default 0, experimental): UPML boxes that are thin in x and sit at the x ends
-   of the mesh are updated by their own one-pass kernel (k_xslab_EH) instead of the shell launches.
-   oems_cuda_get_option reports what is ACTIVE ("fused", "tma": 0 / 1; "xslab": boxes inlined). */
+/* reports what is ACTIVE: "fused", "tma", "small", "pdl": 0 / 1; "xslab": boxes on the window kernel; "skip_shell": ends
+   of the mesh that are skipped; "onepass_rows" / "onepass_planes": rows / local planes the one-pass kernel works on;
+   "h2d_bytes": bytes copied host -> device by this engine so far. */
 int oems_cuda_get_option(oems_cuda_engine* h, const char* key, long long* value);
 
 /* measurement aid: runs n_ts timesteps without the graph and returns the average duration in

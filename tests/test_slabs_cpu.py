@@ -146,3 +146,105 @@ def test_halo_protocol_two_gloo_ranks():
     for rank, okV, okI, vmax in res:
         assert okV and okI, "rank %d differs from the single-domain oracle" % rank
         assert vmax > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# read-out on slabs: the host-side merge logic of openems_b200/slabs.py on two gloo ranks.  Every rank
+# stands in for a slab engine with a stub that evaluates the ORACLE's dump / mode-matching / steady-state
+# terms on the planes the rank owns (what the device kernels are tested to do in
+# tests/test_gpu_slab_readout.py); the merged results must equal the single-domain oracle.
+# ---------------------------------------------------------------------------------------------
+class _StubSlabEngine:
+    def __init__(self, s, zb, ze, box, mode):
+        self.s, self.zb, self.ze, self.box, self.mode = s, zb, ze, box, mode
+
+    def ReadDump(self, dump_id):
+        start, stop = self.box
+        full = self.s.dump_field(0, 1, start, stop)               # {3, nz, ny, nx}
+        zs = [z for z in range(start[2], stop[2] + 1) if self.zb <= z < self.ze]
+        return full[:, [z - start[2] for z in zs]].copy()
+
+    def ReadModeMatchRaw(self, mode_id):
+        is_H, ny, start, stop, d0, d1, area = self.mode
+        nP, nPP = (ny + 1) % 3, (ny + 2) % 3
+        value = purity = 0.0
+        for a in range(stop[nP] - start[nP] + 1):
+            for b in range(stop[nPP] - start[nPP] + 1):
+                pos = [0, 0, 0]
+                pos[ny] = start[ny]; pos[nP] = start[nP] + a; pos[nPP] = start[nPP] + b
+                if not (self.zb <= pos[2] < self.ze):
+                    continue
+                f = self.s.dump_field(is_H, 1, tuple(pos), tuple(pos))[:, 0, 0, 0].astype(np.float64)
+                value += f[nP] * d0[a, b] * area[a, b] + f[nPP] * d1[a, b] * area[a, b]
+                purity += f[nP] * f[nP] * area[a, b] + f[nPP] * f[nPP] * area[a, b]
+        return value, (value * value / purity if purity else 0.0), purity
+
+
+def _readout_rank(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.pyoracle import BC_PEC, BC_MUR
+    from tests import cases
+    from openems_b200 import slabs
+    s = cases.uniform_box(n=(14, 12, 20), bc=(BC_MUR, BC_PEC, BC_PEC, BC_MUR, BC_PEC, BC_MUR))
+    s.iterate(40)
+    nz = s.N[2]
+    zb, ze = slab_range(nz, world, rank)
+    box = ((2, 1, 3), (11, 9, 17))
+    ny, start, stop = 0, (6, 1, 2), (6, 10, 18)
+    rng = np.random.default_rng(3)
+    d0, d1, area = rng.random((10, 17)), rng.random((10, 17)), 1e-6 * (1 + rng.random((10, 17)))
+    eng = _StubSlabEngine(s, zb, ze, box, (0, ny, start, stop, d0, d1, area))
+    got = slabs.read_dump_distributed(eng, 0, dist, world)
+    ok_dump = np.array_equal(got.view(np.uint32), s.dump_field(0, 1, *box).view(np.uint32))
+    mm = slabs.mode_match_distributed(eng, 0, dist, world)
+    ref = _StubSlabEngine(s, 0, nz, box, (0, ny, start, stop, d0, d1, area)).ReadModeMatchRaw(0)
+    ok_mode = abs(mm[0] - ref[0]) <= 1e-12 * abs(ref[0]) and abs(mm[1] - ref[1]) <= 1e-12 * abs(ref[1]) and ref[0] != 0
+    q.put((rank, bool(ok_dump), bool(ok_mode)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_readout_merge_two_gloo_ranks():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_readout_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok_dump, ok_mode in res:
+        assert ok_dump, "rank %d: concatenated slab dumps differ from the single-domain dump" % rank
+        assert ok_mode, "rank %d: merged mode-matching partial sums differ" % rank
+
+
+def test_steadystate_eval_and_merge():
+    """oems_cuda_steadystate_eval (host arithmetic of Engine_Ext_SteadyState::Apply2Voltages,
+    engine_ext_steadystate.cpp:62-106) against a numpy restatement, and the slab merge: energies add up,
+    records are concatenated; the criterion is a maximum over the probes, so the slab order is free"""
+    from openems_b200 import slabs
+    rng = np.random.default_rng(9)
+    p, cnt = 7, 5
+    snap = rng.standard_normal((2 * p, cnt))
+    snap[p:] = snap[:p] * (1 + 1e-3 * rng.standard_normal((p, cnt)))       # nearly periodic
+    snap[:, 3] *= 1e-4                                                     # a probe below 1 % of the strongest: ignored
+    info = np.array([3, 5 * p], np.uint32)                                 # rel_pos = 5p % 2p = p <= p: new = rows 0..p-1
+    en = np.array([0.0, 0.0, 2.0, 2.002])
+    new, old = snap[:p], snap[p:]
+    cur = (new ** 2).sum(0)
+    dif = ((old - new) ** 2).sum(0)
+    want = max(abs(en[3] - en[2]) / en[2], max(dif[n] / cur[n] for n in range(cnt) if cur[n] > cur.max() * 1e-2))
+    whole = slabs.combine_steadystate([(info, en, snap)], p)
+    assert whole[1] == 3 and whole[0] == pytest.approx(want, rel=1e-12)
+    # two slabs: probes 0..1 on the first, 2..4 on the second, each with a part of the energy
+    parts = [(info, en * 0.25, snap[:, :2]), (info, en * 0.75, snap[:, 2:])]
+    assert slabs.combine_steadystate(parts, p)[0] == pytest.approx(want, rel=1e-12)
+    assert slabs.combine_steadystate(parts[::-1], p)[0] == pytest.approx(want, rel=1e-12)
+    # no completed check yet -> 1
+    assert slabs.combine_steadystate([(np.array([0, 0], np.uint32), en, snap)], p)[0] == 1.0
+    assert slabs.combine_mode_match([(1.0, 0, 2.0), (3.0, 0, 6.0)]) == (4.0, 2.0)
