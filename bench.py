@@ -331,6 +331,9 @@ def run_gpu(args):
     if world > 2 and not args.no_rebalance:
         from openems_b200.slabs import slab_range
         e0 = op.CreateEngine(device=local_rank, slab=slab)
+        for kv in args.opt:
+            k, v = kv.split("=")
+            e0.SetOption(k, int(v))
         blobs = [None] * world
         dist.all_gather_object(blobs, e0.ExportIPC())
         e0.OpenPeers(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
@@ -338,7 +341,8 @@ def run_gpu(args):
         e0.FillFields(0)
         e0.IterateTS(3)
         e0.Synchronize()
-        busy = sum(ms for name, ms in e0.TimeSchedule(4) if not name.startswith("halo_wait"))
+        # (join_side = the main stream waiting for the side stream, i.e. for the neighbour's E plane: a wait as well)
+        busy = sum(ms for name, ms in e0.TimeSchedule(4) if not name.startswith("halo_wait") and name != "join_side")
         e0.close()
         del e0
         parts = [None] * world
@@ -364,6 +368,9 @@ def run_gpu(args):
     # ---------------- e2e leg: engine creation from HOST buffers + K timesteps with probe readback
     def make_engine():
         eng = op.CreateEngine(device=local_rank, slab=slab)
+        for kv in args.opt:                      # experiments: engine options, e.g. --opt overlap_halo=0
+            k, v = kv.split("=")
+            eng.SetOption(k, int(v))
         add_c5_probes(eng, n)
         return eng
 
@@ -732,6 +739,7 @@ def main():
                     help="bounded sample mesh of the CPU arm (default 192^3 inside the GPU line, 256^3 for --impl reference)")
     ap.add_argument("--cpu-steps", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value for the timed engine (experiments)")
     ap.add_argument("--no-dump-leg", action="store_true", help="skip the asynchronous-dump overhead measurement (N = 1)")
     ap.add_argument("--pml-weight", type=float, default=1.7,
                     help="first z-slab split: extra cost of a z-PML plane relative to a plain plane (136 vs 50 bytes per cell)")

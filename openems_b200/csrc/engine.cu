@@ -89,6 +89,15 @@ Engine::~Engine()
 		if (d.ev_copied) cudaEventDestroy(d.ev_copied);
 	}
 	if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+	if (side_stream) {
+		cudaStreamSynchronize(side_stream);
+		cudaStreamDestroy(side_stream);
+		for (int q = 0; q < 2; ++q) {
+			if (ev_fork[q][0]) cudaEventDestroy(ev_fork[q][0]);
+			if (ev_fork[q][1]) cudaEventDestroy(ev_fork[q][1]);
+			if (ev_join[q]) cudaEventDestroy(ev_join[q]);
+		}
+	}
 	for (auto& f : fds) {
 		if (f.h_w) cudaFreeHost(f.h_w);
 		for (int r = 0; r < FdHost::RING; ++r) if (f.ev[r]) cudaEventDestroy(f.ev[r]);
@@ -1298,7 +1307,7 @@ void Engine::build_schedule()
 		(labels.push_back("halo_push_E"), step.push_back([this](cudaStream_t s) {
 			HaloParams h{d_V, peer_lo_V, (long long)((int)zb - z0) * plane, peer_lo_ghostE_off, comp, peer_lo_comp, plane,
 			             d_halo_cnt, peer_lo_flagE, d_numTS, 1u};
-			launch_k(k_halo_push, 64, 256, 0, s, h);
+			launch_k(k_halo_push, 296, 256, 0, s, h);
 		}));
 	// ---- pre-current hooks: Lorentz (UPML fused)
 	for (size_t o = 0; o < lor_dev.size(); ++o)
@@ -1341,7 +1350,7 @@ void Engine::build_schedule()
 		(labels.push_back("halo_push_H"), step.push_back([this](cudaStream_t s) {
 			HaloParams h{d_I, peer_hi_I, (long long)((int)ze - 1 - z0) * plane, peer_hi_ghostH_off, comp, peer_hi_comp, plane,
 			             d_halo_cnt + 1, peer_hi_flagH, d_numTS, 1u};
-			launch_k(k_halo_push, 64, 256, 0, s, h);
+			launch_k(k_halo_push, 296, 256, 0, s, h);
 		}));
 	// the timestep counter: advanced by k_small_H itself when that is the last kernel of the timestep
 	pH.tick = nullptr;
@@ -1551,6 +1560,14 @@ void Engine::build_schedule_fused()
 	const bool multi = peers_linked;
 	labelsf.clear();
 	sched_error.clear();
+	if (multi && !side_stream) {
+		if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); side_stream = nullptr; }
+		for (int q = 0; q < 2 && side_stream; ++q) {
+			cudaEventCreateWithFlags(&ev_fork[q][0], cudaEventDisableTiming);
+			cudaEventCreateWithFlags(&ev_fork[q][1], cudaEventDisableTiming);
+			cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming);
+		}
+	}
 	// TMA descriptors of both source sets; without them the register-staged kernel is used
 	tma_active = tma_req != 0 && make_tma_maps(0) == 0 && make_tma_maps(1) == 0;
 	// UPML boxes updated by their own one-pass kernel k_xslab_EH ("x slabs", kernels_xslab.cuh): thin in x, at
@@ -1824,6 +1841,7 @@ void Engine::build_schedule_fused()
 		pExcD[par][1] = pExc[1]; pExcD[par][1].X = sI[D];
 		StencilParams& T = pHtop[par];
 		T = pH;
+		T.tick = nullptr;
 		T.V = sV[D]; T.I = sI[S]; T.Iout = sI[D]; T.flux = d_flux_i; T.flux_out = nullptr; // flux in place
 		T.k0 = pE.k1 - 1; T.k1 = pE.k1; T.zchunk = 1;
 
@@ -1940,12 +1958,19 @@ void Engine::build_schedule_fused()
 			lab("mur_apply"); L.push_back([this, par](cudaStream_t s) { launch1d(k_mur_apply, pMurD[par], pMurD[par].total, s); });
 		}
 		if (pExc[0].groups) { lab("excite_V"); L.push_back([this, par](cudaStream_t s) { launch1d(k_excite, pExcD[par][0], pExcD[par][0].groups, s); }); }
+		// Slabs: the E halo push, the wait for the upper neighbour's E plane and the H update of the slab's top plane
+		// are small kernels with a long latency chain (NVLink, the neighbour's pace).  They run on a SIDE stream (a
+		// parallel branch of the step graph) next to fix_H / k_shell_H and join before the current-side hooks: at 8
+		// GPUs ~60 of the 1500 us of a timestep no longer sit at the end of the step with the GPU idle.
+		const bool side = multi && overlap_halo && side_stream;
 		if (multi && peer_lo) {
 			lab("halo_push_E");
-			L.push_back([this, D](cudaStream_t s) {
+			L.push_back([this, D, par, side](cudaStream_t s) {
+				cudaStream_t t = s;
+				if (side) { cudaEventRecord(ev_fork[par][0], s); cudaStreamWaitEvent(side_stream, ev_fork[par][0], 0); t = side_stream; }
 				HaloParams h{sV[D], peer_lo_Vs[D], (long long)((int)zb - z0) * plane, peer_lo_ghostE_off, comp, peer_lo_comp, plane,
 				             d_halo_cnt, peer_lo_flagE, d_numTS, 1u};
-				launch_k(k_halo_push, 64, 256, 0, s, h);
+				launch_k(k_halo_push, 296, 256, 0, t, h);
 			});
 		}
 		// ---- H cells that depend on E values changed by the hooks
@@ -1956,6 +1981,37 @@ void Engine::build_schedule_fused()
 				else launch1d(k_fix_H<uint32_t>, pFix[par], pFix[par].count, s);
 			});
 		}
+		// ---- slab top plane: needs the neighbour's E plane (side stream; after fix_H, which may touch top-plane cells)
+		if (multi && peer_hi) {
+			lab("halo_wait_E");
+			L.push_back([this, par, side](cudaStream_t s) {
+				if (side) { cudaEventRecord(ev_fork[par][1], s); cudaStreamWaitEvent(side_stream, ev_fork[par][1], 0); s = side_stream; }
+				WaitParams w{d_flagE, d_numTS, 1u, d_halo_err, halo_timeout_cycles()};
+				launch_k(k_halo_wait, 1, 1, 0, s, w);
+			});
+			lab("update_H_top");
+			L.push_back([this, par, i16, side](cudaStream_t s) {
+				if (side) s = side_stream;
+				const StencilParams& q = pHtop[par];
+				const dim3 block(32, tune_rows);
+				// one plane: the one-cell-per-thread kernel, out of place (source set -> destination set)
+				const dim3 g((unsigned)((gn[0] - 1 + 31) / 32), (unsigned)((q.ny - 1 + tune_rows - 1) / tune_rows), 1);
+				if (i16) { if (has_pml) launch_k(k_small_H<uint16_t, true>, g, block, 0, s, q); else launch_k(k_small_H<uint16_t, false>, g, block, 0, s, q); }
+				else { if (has_pml) launch_k(k_small_H<uint32_t, true>, g, block, 0, s, q); else launch_k(k_small_H<uint32_t, false>, g, block, 0, s, q); }
+			});
+			if (lor_fused)
+				for (size_t o = 0; o < lor_dev.size(); ++o) {
+					if (!lor_dev[o].i_on || lor_dev[o].top_first >= lor_dev[o].i.count) continue;
+					lab("lorentz_apply_I_top");
+					L.push_back([this, par, o, side](cudaStream_t s) {
+						if (side) s = side_stream;
+						// Apply2Current for the dispersive cells of the top plane: the tail of the (z-sorted) list
+						LorParams q = lor_dev[o].i;
+						q.X = sI[par ^ 1]; q.first = lor_dev[o].top_first;
+						launch1d(k_lorentz_apply, q, q.count - q.first, s);
+					});
+				}
+		}
 		// ---- H of the UPML shell, from the final E
 		if (has_pml) {
 			lab("shell_H");
@@ -1965,32 +2021,9 @@ void Engine::build_schedule_fused()
 				if (i16) launch_k(k_shell_H<uint16_t>, q.nblocks, dim3(32, 8), 0, s, q); else launch_k(k_shell_H<uint32_t>, q.nblocks, dim3(32, 8), 0, s, q);
 			});
 		}
-		// ---- slab top plane: needs the neighbour's E plane
-		if (multi && peer_hi) {
-			lab("halo_wait_E");
-			L.push_back([this](cudaStream_t s) {
-				WaitParams w{d_flagE, d_numTS, 1u, d_halo_err, halo_timeout_cycles()};
-				launch_k(k_halo_wait, 1, 1, 0, s, w);
-			});
-			lab("update_H_top");
-			L.push_back([this, par, i16](cudaStream_t s) {
-				const StencilParams& q = pHtop[par];
-				const dim3 block(32, tune_rows);
-				const dim3 g((unsigned)((pitch / 4 + 31) / 32), (unsigned)((q.ny + tune_rows - 1) / tune_rows), 1);
-				if (i16) { if (has_pml) launch_k(k_update_H<uint16_t, true>, g, block, 0, s, q); else launch_k(k_update_H<uint16_t, false>, g, block, 0, s, q); }
-				else { if (has_pml) launch_k(k_update_H<uint32_t, true>, g, block, 0, s, q); else launch_k(k_update_H<uint32_t, false>, g, block, 0, s, q); }
-			});
-			if (lor_fused)
-				for (size_t o = 0; o < lor_dev.size(); ++o) {
-					if (!lor_dev[o].i_on || lor_dev[o].top_first >= lor_dev[o].i.count) continue;
-					lab("lorentz_apply_I_top");
-					L.push_back([this, par, o](cudaStream_t s) {
-						// Apply2Current for the dispersive cells of the top plane: the tail of the (z-sorted) list
-						LorParams q = lor_dev[o].i;
-						q.X = sI[par ^ 1]; q.first = lor_dev[o].top_first;
-						launch1d(k_lorentz_apply, q, q.count - q.first, s);
-					});
-				}
+		if (side && (peer_lo || peer_hi)) {
+			lab("join_side");
+			L.push_back([this, par](cudaStream_t s) { cudaEventRecord(ev_join[par], side_stream); cudaStreamWaitEvent(s, ev_join[par], 0); });
 		}
 		// ---- post-current hook of the TFSF box, then post / apply current hooks of the absorbing sheets: H of the
 		//      destination set is final here
@@ -2011,7 +2044,7 @@ void Engine::build_schedule_fused()
 			L.push_back([this, D](cudaStream_t s) {
 				HaloParams h{sI[D], peer_hi_Is[D], (long long)((int)ze - 1 - z0) * plane, peer_hi_ghostH_off, comp, peer_hi_comp, plane,
 				             d_halo_cnt + 1, peer_hi_flagH, d_numTS, 1u};
-				launch_k(k_halo_push, 64, 256, 0, s, h);
+				launch_k(k_halo_push, 296, 256, 0, s, h);
 			});
 		}
 		lab("tick");
@@ -2157,6 +2190,11 @@ int Engine::set_option(const char* key, long long value)
 	}
 	if (k == "small_max_cells") {
 		small_max_cells = value;
+		if (finalized) return rebuild_schedule();
+		return 0;
+	}
+	if (k == "overlap_halo") { // 1 (default): halo push / top plane of a z-slab on a side stream next to the UPML shell
+		overlap_halo = value != 0;
 		if (finalized) return rebuild_schedule();
 		return 0;
 	}

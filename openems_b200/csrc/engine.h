@@ -285,6 +285,9 @@ private:
 	XTmaParams pXt[2];           // the same + TMA descriptors (k_xslab_tma)
 	bool xslab_tma = false;
 	bool skip_req = true;        // option "skip_shell"
+	bool overlap_halo = true;    // option "overlap_halo"
+	cudaStream_t side_stream = nullptr;   // parallel branch of the one-pass step graph on z-slab engines
+	cudaEvent_t ev_fork[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, ev_join[2] = {nullptr, nullptr};
 	int small_req = -1;          // option "small": one-cell-per-thread two-pass kernels (k_small_E / k_small_H)
 	long long small_max_cells = 300000000;
 	long long fused_min_cells = 20000000;   // automatic schedule choice (option "fused_min_cells")

@@ -409,6 +409,7 @@ __global__ void __launch_bounds__(256) k_small_H(const __grid_constant__ Stencil
 	const float v0n = V0[o + p.plane], v1n = V1[o + p.plane];
 	const float v1xp = V1[o + 1], v2xp = V2[o + 1];
 	float c0 = p.I[o], c1 = p.I[p.comp + o], c2 = p.I[2 * p.comp + o];
+	float* O = p.Iout ? p.Iout : p.I;   // out-of-place: the slab's top plane in the one-pass schedule (cells that are never updated hold the same value in both sets)
 	const float4 A = __ldg(p.tA + e), B = __ldg(p.tB + e);
 	const float curl0 = fadd(fsub(fsub(v2c, v2jp), v1c), v1n);
 	const float curl1 = fadd(fsub(fsub(v0c, v0n), v2c), v2xp);
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(256) k_small_H(const __grid_constant__ Stencil
 	if (HAS_PML && A.w != 0.0f) {
 		long long cs;
 		const long long fo = pml_flux_offset(p, i, j, k, cs);
-		if (fo < 0) return;
+		if (fo < 0) { if (p.Iout) { O[o] = c0; O[p.comp + o] = c1; O[2 * p.comp + o] = c2; } return; }
 		const float4 P0 = __ldg(p.tP0 + e), P1 = __ldg(p.tP1 + e), P2 = __ldg(p.tP2 + e);
 		c0 = leap_pml(c0, A.x, B.x, curl0, P0.x, P1.x, P2.x, p.flux + fo, p.flux + fo);
 		c1 = leap_pml(c1, A.y, B.y, curl1, P0.y, P1.y, P2.y, p.flux + fo + cs, p.flux + fo + cs);
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(256) k_small_H(const __grid_constant__ Stencil
 		c1 = leap(c1, A.y, B.y, curl1);
 		c2 = leap(c2, A.z, B.z, curl2);
 	}
-	p.I[o] = c0; p.I[p.comp + o] = c1; p.I[2 * p.comp + o] = c2;
+	O[o] = c0; O[p.comp + o] = c1; O[2 * p.comp + o] = c2;
 }
 
 // ---------------------------------------------------------------------------------------
