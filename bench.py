@@ -467,6 +467,17 @@ def run_gpu(args):
     eng.close()
     del eng
     barrier()
+    # The engine that was just closed held 55 GB; the driver hands freed memory back asynchronously, and an allocation
+    # of the same size right behind the free waits for that (engine creation then measured 0.03 ... 0.35 s from run to
+    # run).  An application creates its engine on an idle device: the CPU baseline leg (N = 1, ~10 s of host work) or a
+    # short pause goes in between, untimed.
+    cpu_leg = None
+    if world == 1 and not args.no_cpu and rank == 0:
+        threads = os.cpu_count() or 1
+        cpu_leg = cpu_baseline(tuple(args.cpu_sample), args.cpu_steps, threads) + (threads,)
+    else:
+        time.sleep(2.0)
+    barrier()
     t0 = time.perf_counter()
     eng = make_engine()
     link(eng)
@@ -571,10 +582,9 @@ def run_gpu(args):
         }
         if energy_after is not None:
             out["parity_check"]["full_size_digest"]["energy_estimate_J"] = energy_after
-        if world == 1 and not args.no_cpu:
-            threads = os.cpu_count() or 1
+        if cpu_leg is not None:
+            v, dt, kind, what, threads = cpu_leg
             sample = tuple(args.cpu_sample)
-            v, dt, kind, what = cpu_baseline(sample, args.cpu_steps, threads)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
                                    "sample": "%dx%dx%d PML_8 mesh, %d timesteps in %.1f s; %s" % (sample + (args.cpu_steps, dt, what))}
         print(json.dumps(out))
@@ -681,9 +691,15 @@ def run_gpu_c4(args):
     t_dom = kern.get(dom, 0.0)
     achieved = per_launch / (t_dom * 1e-3) / 1e9 if t_dom else 0.0
     step_ms = sum(kern.values())
-    # e2e: engine from host buffers + K steps
+    # e2e: engine from host buffers + K steps (the CPU leg goes between the close and the new engine: see run_gpu)
     eng.close()
     torch.cuda.synchronize()
+    cpu_leg = None
+    if not args.no_cpu:
+        threads = os.cpu_count() or 1
+        cpu_leg = c4_cpu_baseline(tuple(args.cpu_sample), min(args.cpu_steps, 60), threads) + (threads,)
+    else:
+        time.sleep(2.0)
     t0 = time.perf_counter()
     eng = op.CreateEngine(device=0)
     h2d = eng.GetOption("h2d_bytes")
@@ -718,10 +734,9 @@ def run_gpu_c4(args):
         "parity_check": {"compared": "one-pass (ADE in the kernel) vs two-pass schedule, %d timesteps from the same pre-fill" % (args.warmup + args.steps),
                          "digest_E": "%016x" % dig[0], "digest_H": "%016x" % dig[1], "equal": bool(list(dig) == list(dig2))},
     }
-    if not args.no_cpu:
-        threads = os.cpu_count() or 1
+    if cpu_leg is not None:
         sample = tuple(args.cpu_sample)
-        v, dt, kind = c4_cpu_baseline(sample, min(args.cpu_steps, 60), threads)
+        v, dt, kind, threads = cpu_leg
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
                                "sample": "%dx%dx%d C4 mesh (Drude block %d^3), %d timesteps in %.1f s, %s" % (sample + (sample[0] // 2, min(args.cpu_steps, 60), dt, "unmodified reference engine (oracle/_ref)" if kind == "reference" else "sse restatement"))}
     print(json.dumps(out))
