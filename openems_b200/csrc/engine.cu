@@ -974,21 +974,25 @@ int Engine::build_lorentz()
 	for (const LorHost& L : h_lor) {
 		// keep only the cells on owned planes, in storage order (z, y, x): the list kernels then read the fields
 		// coalesced, and the one-pass kernel finds a cell's ADE through one {first x, cells, first index} per row
-		std::vector<unsigned> keep;
+		std::vector<std::pair<long long, unsigned>> kv; // (storage offset, list entry) of the owned cells
 		for (unsigned i = 0; i < L.count; ++i)
-			if (owned(L.pos[(size_t)2 * L.count + i])) keep.push_back(i);
-		auto off_of = [&](unsigned i) { return cell_off(L.pos[i], L.pos[(size_t)L.count + i], L.pos[(size_t)2 * L.count + i]); };
-		std::sort(keep.begin(), keep.end(), [&](unsigned a, unsigned b) { return off_of(a) < off_of(b); });
-		const unsigned cnt = (unsigned)keep.size();
+			if (owned(L.pos[(size_t)2 * L.count + i]))
+				kv.emplace_back(cell_off(L.pos[i], L.pos[(size_t)L.count + i], L.pos[(size_t)2 * L.count + i]), i);
+		std::sort(kv.begin(), kv.end());
+		const unsigned cnt = (unsigned)kv.size();
+		std::vector<unsigned> keep(cnt);
 		std::vector<long long> cell(cnt);
-		for (unsigned q = 0; q < cnt; ++q) cell[q] = off_of(keep[q]);
+		for (unsigned q = 0; q < cnt; ++q) { cell[q] = kv[q].first; keep[q] = kv[q].second; }
+		std::vector<std::pair<long long, unsigned>>().swap(kv);
 		for (unsigned i : keep) { lor_xmin = std::min(lor_xmin, (int)L.pos[i]); lor_xmax = std::max(lor_xmax, (int)L.pos[i]); }
 		for (unsigned q = 1; q < cnt; ++q)
 			if (cell[q] == cell[q - 1]) return fail("add_lorentz: a cell is listed twice");
 		auto pick = [&](const std::vector<float>& src) {
 			std::vector<float> d((size_t)3 * cnt);
-			for (int n = 0; n < 3; ++n)
-				for (unsigned q = 0; q < cnt; ++q) d[(size_t)n * cnt + q] = src[(size_t)n * L.count + keep[q]];
+			for (int n = 0; n < 3; ++n) {
+#pragma omp parallel for schedule(static)
+				for (long long q = 0; q < (long long)cnt; ++q) d[(size_t)n * cnt + q] = src[(size_t)n * L.count + keep[q]];
+			}
 			return d;
 		};
 		LorDev D;
