@@ -1792,6 +1792,17 @@ void Engine::build_schedule_fused()
 		F.nsh = ns;
 		SE.nboxes = SH.nboxes = nent;
 		XP.jb = F.jb; XP.je = F.je;
+		if (tma_active && tune_zchunk <= 0) {
+			// marches of equal length: 131 planes of a slab as 8 x 17 rather than 8 x 16 + 3 (every block pays the same
+			// start-up: barrier set-up, first TMA round trip, the carried plane)
+			auto even = [](int planes, int zc) {
+				const int n = std::max(1, (planes + zc / 2) / zc);
+				return std::min(63, (planes + n - 1) / n);
+			};
+			const int planes = std::max(1, F.kE1 - F.kE0);
+			F.zchunk = even(planes, F.zchunk);
+			if (xslab_tma) XP.zchunk = even(planes, XP.zchunk);
+		}
 		{   // the window kernel's list of foreign footprints: the boxes on the shell path, not its own windows
 			int m = 0;
 			for (int q = 0; q < ns; ++q) {
