@@ -839,6 +839,19 @@ int Engine::build_sheets()
 	return 0;
 }
 
+// no voltage excitation entry writes a component that a Mur plane writes (the two tangential components on the plane's
+// boundary line): Apply2Voltages of the two extensions then commute and share a launch (k_mur_apply_excite)
+bool Engine::mur_exc_disjoint() const
+{
+	const ExcHost& E = h_exc[0];
+	for (size_t n = 0; n < E.dir.size(); ++n) {
+		const unsigned pos[3] = {E.idx[0][n], E.idx[1][n], E.idx[2][n]};
+		for (const MurHost& M : h_mur)
+			if (pos[M.ny] == M.line && (int)E.dir[n] != M.ny) return false;
+	}
+	return true;
+}
+
 int Engine::build_mur()
 {
 	memset(&pMur, 0, sizeof(pMur));
@@ -1304,8 +1317,14 @@ void Engine::build_schedule()
 		(labels.push_back("rlc_apply"), step.push_back([this, r](cudaStream_t s) { launch1d(k_rlc_apply, rlc_dev[r], rlc_dev[r].count, s); }));
 	for (size_t o = 0; o < lor_dev.size(); ++o)
 		if (lor_dev[o].v_on) (labels.push_back("lorentz_apply_V"), step.push_back([this, o](cudaStream_t s) { launch1d(k_lorentz_apply, lor_dev[o].v, lor_dev[o].v.count, s); }));
-	if (pMur.nplanes) (labels.push_back("mur_apply"), step.push_back([this](cudaStream_t s) { launch1d(k_mur_apply, pMur, pMur.total, s); }));
-	if (pExc[0].groups) (labels.push_back("excite_V"), step.push_back([this](cudaStream_t s) { launch1d(k_excite, pExc[0], pExc[0].groups, s); }));
+	const bool mur_exc = pMur.nplanes && pMur.total > 0 && pExc[0].groups && mur_exc_disjoint();
+	if (mur_exc)
+		(labels.push_back("mur_apply+excite_V"), step.push_back([this](cudaStream_t s) {
+			const unsigned mb = (unsigned)((pMur.total + 127) / 128), eb = (pExc[0].groups + 127) / 128;
+			launch_k(k_mur_apply_excite, mb + eb, 128, 0, s, pMur, pExc[0], mb);
+		}));
+	else if (pMur.nplanes) (labels.push_back("mur_apply"), step.push_back([this](cudaStream_t s) { launch1d(k_mur_apply, pMur, pMur.total, s); }));
+	if (pExc[0].groups && !mur_exc) (labels.push_back("excite_V"), step.push_back([this](cudaStream_t s) { launch1d(k_excite, pExc[0], pExc[0].groups, s); }));
 	// ---- multi-GPU: tangential E of my lowest owned plane -> lower neighbour's ghost plane
 	if (multi && peer_lo)
 		(labels.push_back("halo_push_E"), step.push_back([this](cudaStream_t s) {

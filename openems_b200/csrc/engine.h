@@ -235,6 +235,7 @@ private:
 	std::vector<LorDev> lor_dev;
 	bool lor_fused = false;          // Lorentz/Drude ADE applied inside the one-pass kernel (kernels_fused_tma.cuh, LOR)
 	bool lorentz_fusable() const;
+	bool mur_exc_disjoint() const;
 	int lor_xmin = 1 << 30, lor_xmax = -1; // x range of the dispersive cells on this engine
 	std::string sched_error;         // a schedule that cannot run (reported by iterate)
 	std::vector<RlcParams> rlc_dev;

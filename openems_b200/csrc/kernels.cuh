@@ -532,15 +532,18 @@ __global__ void k_mur_post(const __grid_constant__ MurParams p)
 	p.vP[t] = fadd(p.vP[t], fmul(p.cP[t], p.V[os[0]]));
 	p.vPP[t] = fadd(p.vPP[t], fmul(p.cPP[t], p.V[os[1]]));
 }
-__global__ void k_mur_apply(const __grid_constant__ MurParams p)
+__device__ __forceinline__ void mur_apply_entry(const MurParams& p, long long t)
 {
-	PDL_PROLOGUE();
-	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	int m; long long o[2], os[2];
 	if (!mur_locate(p, t, m, o, os)) return;
 	const unsigned ts = *p.numTS;
 	if (ts < p.ovr_start[t]) p.V[o[0]] = p.vP[t];
 	if (ts < p.ovr_start[p.total + t]) p.V[o[1]] = p.vPP[t];
+}
+__global__ void k_mur_apply(const __grid_constant__ MurParams p)
+{
+	PDL_PROLOGUE();
+	mur_apply_entry(p, (long long)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -558,10 +561,23 @@ struct ExcParams {
 	const unsigned* numTS;
 	unsigned groups, length, period;
 };
+__device__ __forceinline__ void excite_group(const ExcParams& p, unsigned g);
 __global__ void k_excite(const __grid_constant__ ExcParams p)
 {
 	PDL_PROLOGUE();
-	const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+	excite_group(p, blockIdx.x * blockDim.x + threadIdx.x);
+}
+// Apply2Voltages of the Mur planes and of the excitation in ONE launch (small meshes: a launch less per timestep).
+// The reference runs Mur first, then the excitation (engine.cpp:239-244 over the priority-sorted list); the two write
+// different cells -- checked at upload, Engine::mur_exc_disjoint -- so they may run side by side.
+__global__ void k_mur_apply_excite(const __grid_constant__ MurParams m, const __grid_constant__ ExcParams e, unsigned mur_blocks)
+{
+	PDL_PROLOGUE();
+	if (blockIdx.x < mur_blocks) mur_apply_entry(m, (long long)blockIdx.x * blockDim.x + threadIdx.x);
+	else excite_group(e, (blockIdx.x - mur_blocks) * blockDim.x + threadIdx.x);
+}
+__device__ __forceinline__ void excite_group(const ExcParams& p, unsigned g)
+{
 	if (g >= p.groups) return;
 	const int numTS = (int)*p.numTS;
 	int per = numTS + 1;
